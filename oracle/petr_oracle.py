@@ -1,0 +1,353 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU fp32 restatement of the reference PETR head hot path.
+
+This is the *oracle*: a functional, state_dict-driven restatement (torch CPU fp32 + numpy
+float64 on the host, exactly where the reference uses them) of
+
+    PETRHead.forward / position_embeding      projects/mmdet3d_plugin/models/dense_heads/petr_head.py:286-468
+    PETRv2Head.forward (SELayer, RegLayer)    .../dense_heads/petrv2_head.py:48-95, :348-540
+    PETRTransformer / Decoder / DecoderLayer  .../models/utils/petr_transformer.py:69-109, :423-447
+    PETRMultiheadAttention                    .../models/utils/petr_transformer.py:280-367
+    SinePositionalEncoding3D                  .../models/utils/positional_encoding.py:58-100
+    mmcv BaseTransformerLayer / FFN / MultiheadAttention (un-vendored mmcv-full 1.4.0; the
+        reference pins them through its vendored copies multi_atten_decoder_layer.py:72-293
+        and petr_transformer.py:228-367)
+    mmdet inverse_sigmoid (vendored copy utils/detr.py:15-31)
+
+Pinning: ``tests/test_oracle_vs_reference.py`` runs this file against the UNMODIFIED reference
+(loaded by ``oracle/ref_loader.py``) in the build container, and ``tests/golden/*.npz`` hold
+outputs of the reference itself (``oracle/make_golden.py``) which the oracle must reproduce
+everywhere, including on the GPU box where /root/reference does not exist.  The reference
+ships no tests or golden vectors of its own, so these are the pins.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
+reference`` legs may import this module.  The product (``petr_b200``) never does.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------------------
+# small pieces
+# --------------------------------------------------------------------------------------
+def inverse_sigmoid(x: Tensor, eps: float = 1e-5) -> Tensor:
+    """mmdet inverse_sigmoid; reference copy at models/utils/detr.py:15-31."""
+    x = x.clamp(min=0, max=1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+def frustum_axes(H: int, W: int, pad_h: int, pad_w: int, depth_num: int = 64,
+                 depth_start: float = 1.0, position_range=(-61.2, -61.2, -10.0, 61.2, 61.2, 10.0),
+                 LID: bool = True, depth_step: float = 0.8):
+    """petr_head.py:290-302.  fp32 pixel-corner grids and depth bins (bit-exact class)."""
+    coords_h = torch.arange(H).float() * pad_h / H
+    coords_w = torch.arange(W).float() * pad_w / W
+    index = torch.arange(0, depth_num, 1).float()
+    if LID:
+        bin_size = (position_range[3] - depth_start) / (depth_num * (1 + depth_num))
+        coords_d = depth_start + bin_size * index * (index + 1)
+    else:
+        bin_size = (position_range[3] - depth_start) / depth_num
+        coords_d = depth_start + bin_size * index
+    return coords_h, coords_w, coords_d
+
+
+def key_padding_masks(img_metas: Sequence[dict], B: int, N: int, H: int, W: int) -> Tensor:
+    """petr_head.py:383-394: ones(pad) with zeros over each view's img_shape, nearest-resized
+    to the feature map.  Returns bool (B,N,H,W), True = padded key."""
+    pad_h, pad_w, _ = img_metas[0]["pad_shape"][0]
+    masks = torch.ones((B, N, pad_h, pad_w), dtype=torch.float32)
+    for b in range(B):
+        for n in range(N):
+            img_h, img_w, _ = img_metas[b]["img_shape"][n]
+            masks[b, n, :img_h, :img_w] = 0
+    return F.interpolate(masks, size=(H, W)).to(torch.bool)
+
+
+def img2lidar_matrices(img_metas: Sequence[dict]) -> Tensor:
+    """petr_head.py:308-315: float64 np.linalg.inv per view on the host, then one rounding
+    to fp32.  Returns (B,N,4,4) fp32."""
+    out = []
+    for meta in img_metas:
+        out.append(np.asarray([np.linalg.inv(m) for m in meta["lidar2img"]]))
+    return torch.tensor(np.asarray(out), dtype=torch.float32)
+
+
+def frustum_coords3d(img2lidars: Tensor, coords_h: Tensor, coords_w: Tensor, coords_d: Tensor,
+                     position_range) -> Tensor:
+    """petr_head.py:303-325.  Returns normalised coords3d, shape (B,N,W,H,D,3) fp32.
+
+    The 4x4 . 4x1 product is evaluated as ((m0*p0 + m1*p1) + m2*p2) + m3*p3 with separately
+    rounded fp32 multiplies and adds, which is bit-identical to torch.matmul on CPU for this
+    shape (verified against the reference in tests/test_oracle_vs_reference.py)."""
+    eps = 1e-5
+    W, H, D = coords_w.numel(), coords_h.numel(), coords_d.numel()
+    u = coords_w.view(W, 1, 1).expand(W, H, D)
+    v = coords_h.view(1, H, 1).expand(W, H, D)
+    d = coords_d.view(1, 1, D).expand(W, H, D)
+    dm = torch.maximum(d, torch.full_like(d, eps))
+    p = [u * dm, v * dm, d, torch.ones_like(d)]                     # (W,H,D) each
+    M = img2lidars[:, :, None, None, None]                          # (B,N,1,1,1,4,4)
+    rows = []
+    for i in range(3):
+        acc = M[..., i, 0] * p[0]
+        acc = acc + M[..., i, 1] * p[1]
+        acc = acc + M[..., i, 2] * p[2]
+        acc = acc + M[..., i, 3] * p[3]
+        rows.append(acc)
+    c = torch.stack(rows, -1)                                       # (B,N,W,H,D,3)
+    pr = position_range
+    c[..., 0:1] = (c[..., 0:1] - pr[0]) / (pr[3] - pr[0])
+    c[..., 1:2] = (c[..., 1:2] - pr[1]) / (pr[4] - pr[1])
+    c[..., 2:3] = (c[..., 2:3] - pr[2]) / (pr[5] - pr[2])
+    return c
+
+
+def position_features(img_metas, B, N, H, W, masks: Optional[Tensor], depth_num=64,
+                      depth_start=1.0, position_range=(-61.2, -61.2, -10.0, 61.2, 61.2, 10.0),
+                      LID=True):
+    """petr_head.py:286-331 up to (excluding) the MLP.
+
+    Returns (feat (B*N, 3*D, H, W) fp32 = inverse_sigmoid(coords), channel = 3*d+c;
+             coords_mask (B,N,H,W) bool; raw normalised coords (B,N,W,H,D,3))."""
+    pad_h, pad_w, _ = img_metas[0]["pad_shape"][0]
+    ch, cw, cd = frustum_axes(H, W, pad_h, pad_w, depth_num, depth_start, position_range, LID)
+    D = cd.numel()
+    c3 = frustum_coords3d(img2lidar_matrices(img_metas), ch, cw, cd, position_range)
+    cmask = (c3 > 1.0) | (c3 < 0.0)
+    cmask = cmask.flatten(-2).sum(-1) > (D * 0.5)                    # (B,N,W,H)
+    cmask = cmask.permute(0, 1, 3, 2)
+    if masks is not None:
+        cmask = masks | cmask
+    feat = c3.permute(0, 1, 4, 5, 3, 2).contiguous().view(B * N, -1, H, W)
+    return inverse_sigmoid(feat), cmask, c3
+
+
+def conv1x1_mlp(x: Tensor, w1, b1, w2, b2) -> Tensor:
+    """Conv2d(1x1) + ReLU + Conv2d(1x1) (petr_head.py:249-267)."""
+    return F.conv2d(F.relu(F.conv2d(x, w1, b1)), w2, b2)
+
+
+def sine_positional_encoding_3d(mask: Tensor, num_feats=128, temperature=10000, normalize=True,
+                                scale=2 * math.pi, eps=1e-6, offset=0.0) -> Tensor:
+    """positional_encoding.py:58-100.  mask bool (B,N,H,W) -> (B,N,3*num_feats,H,W)."""
+    not_mask = 1 - mask.to(torch.int)
+    embeds = [not_mask.cumsum(a, dtype=torch.float32) for a in (1, 2, 3)]   # n, y, x
+    if normalize:
+        sl = [(slice(None), slice(-1, None)), (slice(None), slice(None), slice(-1, None)),
+              (slice(None), slice(None), slice(None), slice(-1, None))]
+        embeds = [(e + offset) / (e[s] + eps) * scale for e, s in zip(embeds, sl)]
+    dim_t = torch.arange(num_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * (dim_t // 2) / num_feats)
+    B, N, H, W = mask.shape
+    outs = []
+    for e in embeds:
+        p = e[..., None] / dim_t
+        # NB: dim=4 on 5-D tensors => channel order is [64 sines | 64 cosines] per axis, not
+        # interleaved (positional_encoding.py:88-96); a reference quirk that must be kept.
+        outs.append(torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=4).view(B, N, H, W, -1))
+    pos_n, pos_y, pos_x = outs
+    return torch.cat((pos_n, pos_y, pos_x), dim=4).permute(0, 1, 4, 2, 3)
+
+
+def pos2posemb3d(pos: Tensor, num_pos_feats=128, temperature=10000) -> Tensor:
+    """petr_head.py:31-43.  (.., 3) -> (.., 384) in (y, x, z) order."""
+    pos = pos * (2 * math.pi)
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * (dim_t // 2) / num_pos_feats)
+    emb = []
+    for a in (1, 0, 2):
+        p = pos[..., a, None] / dim_t
+        emb.append(torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=-1).flatten(-2))
+    return torch.cat(emb, dim=-1)
+
+
+# --------------------------------------------------------------------------------------
+# transformer
+# --------------------------------------------------------------------------------------
+def multihead_attention(sd: Dict[str, Tensor], prefix: str, query, key, value, identity,
+                        query_pos, key_pos, key_padding_mask, num_heads=8) -> Tensor:
+    """petr_transformer.py:280-367 (== mmcv MultiheadAttention), eval mode, seq-first.
+    Calls the same torch functional as nn.MultiheadAttention (need_weights=True as the
+    reference leaves it)."""
+    q = query + query_pos if query_pos is not None else query
+    k = key + key_pos if key_pos is not None else key
+    E = q.shape[-1]
+    out, _ = F.multi_head_attention_forward(
+        q, k, value, E, num_heads,
+        sd[prefix + "attn.in_proj_weight"], sd[prefix + "attn.in_proj_bias"],
+        None, None, False, 0.0,
+        sd[prefix + "attn.out_proj.weight"], sd[prefix + "attn.out_proj.bias"],
+        training=False, key_padding_mask=key_padding_mask, need_weights=True)
+    return identity + out
+
+
+def decoder_layer(sd, p: str, query, memory, query_pos, key_pos, key_padding_mask,
+                  num_heads=8, taps: Optional[dict] = None) -> Tensor:
+    """operation_order = (self_attn, norm, cross_attn, norm, ffn, norm); post-norm layer
+    (mmcv BaseTransformerLayer; reference near-copy multi_atten_decoder_layer.py:160-293)."""
+    E = query.shape[-1]
+
+    def ln(x, i):
+        return F.layer_norm(x, (E,), sd[f"{p}norms.{i}.weight"], sd[f"{p}norms.{i}.bias"], 1e-5)
+
+    x = multihead_attention(sd, p + "attentions.0.", query, query, query, query,
+                            query_pos, query_pos, None, num_heads)
+    if taps is not None:
+        taps["self_attn"] = x
+    x = ln(x, 0)
+    y = multihead_attention(sd, p + "attentions.1.", x, memory, memory, x,
+                            query_pos, key_pos, key_padding_mask, num_heads)
+    if taps is not None:
+        taps["cross_attn"] = y
+    y = ln(y, 1)
+    h = F.relu(F.linear(y, sd[p + "ffns.0.layers.0.0.weight"], sd[p + "ffns.0.layers.0.0.bias"]))
+    z = y + F.linear(h, sd[p + "ffns.0.layers.1.weight"], sd[p + "ffns.0.layers.1.bias"])
+    return ln(z, 2)
+
+
+def transformer(sd, x: Tensor, mask: Tensor, query_embed: Tensor, pos_embed: Tensor,
+                num_layers=6, num_heads=8, prefix="transformer.", taps: Optional[list] = None):
+    """PETRTransformer.forward petr_transformer.py:69-109 + PETRTransformerDecoder.forward
+    :423-447 (return_intermediate=True, post_norm on a copy).  Returns (L,B,Lq,E)."""
+    bs, n, c, h, w = x.shape
+    memory = x.permute(1, 3, 4, 0, 2).reshape(-1, bs, c)
+    pos = pos_embed.permute(1, 3, 4, 0, 2).reshape(-1, bs, c)
+    qpos = query_embed.unsqueeze(1).repeat(1, bs, 1)
+    kpm = mask.view(bs, -1)
+    query = torch.zeros_like(qpos)
+    E = c
+    inter = []
+    for l in range(num_layers):
+        t = {} if taps is not None else None
+        query = decoder_layer(sd, f"{prefix}decoder.layers.{l}.", query, memory, qpos, pos, kpm,
+                              num_heads, t)
+        if taps is not None:
+            t["out"] = query
+            taps.append(t)
+        inter.append(F.layer_norm(query, (E,), sd[prefix + "decoder.post_norm.weight"],
+                                  sd[prefix + "decoder.post_norm.bias"], 1e-5))
+    return torch.stack(inter).transpose(1, 2)
+
+
+# --------------------------------------------------------------------------------------
+# branches
+# --------------------------------------------------------------------------------------
+def cls_branch(sd, p: str, x: Tensor, num_reg_fcs=2) -> Tensor:
+    """petr_head.py:226-236: (Linear, LayerNorm, ReLU) x num_reg_fcs, Linear."""
+    E = x.shape[-1]
+    for i in range(num_reg_fcs):
+        x = F.linear(x, sd[f"{p}{3 * i}.weight"], sd[f"{p}{3 * i}.bias"])
+        x = F.relu(F.layer_norm(x, (E,), sd[f"{p}{3 * i + 1}.weight"], sd[f"{p}{3 * i + 1}.bias"], 1e-5))
+    j = 3 * num_reg_fcs
+    return F.linear(x, sd[f"{p}{j}.weight"], sd[f"{p}{j}.bias"])
+
+
+def reg_branch(sd, p: str, x: Tensor, num_reg_fcs=2) -> Tensor:
+    """petr_head.py:238-243: (Linear, ReLU) x num_reg_fcs, Linear."""
+    for i in range(num_reg_fcs):
+        x = F.relu(F.linear(x, sd[f"{p}{2 * i}.weight"], sd[f"{p}{2 * i}.bias"]))
+    j = 2 * num_reg_fcs
+    return F.linear(x, sd[f"{p}{j}.weight"], sd[f"{p}{j}.bias"])
+
+
+def reg_layer_multi(sd, p: str, x: Tensor, num_reg_fcs=2, num_tasks=5) -> Tensor:
+    """PETRv2 RegLayer petrv2_head.py:63-95: shared trunk + per-task heads, concatenated."""
+    for i in range(num_reg_fcs):
+        x = F.relu(F.linear(x, sd[f"{p}reg_branch.{3 * i}.weight"], sd[f"{p}reg_branch.{3 * i}.bias"]))
+    outs = []
+    for t in range(num_tasks):
+        h = F.relu(F.linear(x, sd[f"{p}task_heads.{t}.0.weight"], sd[f"{p}task_heads.{t}.0.bias"]))
+        outs.append(F.linear(h, sd[f"{p}task_heads.{t}.2.weight"], sd[f"{p}task_heads.{t}.2.bias"]))
+    return torch.cat(outs, -1)
+
+
+# --------------------------------------------------------------------------------------
+# whole head
+# --------------------------------------------------------------------------------------
+DEFAULT_CFG = dict(
+    num_query=900, depth_num=64, depth_start=1.0, LID=True, with_position=True,
+    with_multiview=True, position_range=(-61.2, -61.2, -10.0, 61.2, 61.2, 10.0),
+    pc_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0), num_layers=6, num_heads=8,
+    num_reg_fcs=2, with_fpe=False, with_time=False, with_multi=False,
+    num_feats=128, normalize=True)
+
+
+def head_forward(sd: Dict[str, Tensor], feats: Tensor, img_metas: List[dict],
+                 cfg: Optional[dict] = None, taps: Optional[dict] = None):
+    """PETRHead.forward petr_head.py:366-468 / PETRv2Head.forward petrv2_head.py:429-540,
+    eval mode, fp32, CPU.  ``feats`` is mlvl_feats[position_level], (B,N,Cin,H,W).
+    Returns dict(all_cls_scores (L,B,Lq,C), all_bbox_preds (L,B,Lq,10))."""
+    c = dict(DEFAULT_CFG)
+    if cfg:
+        c.update(cfg)
+    B, N, Cin, H, W = feats.shape
+    masks = key_padding_masks(img_metas, B, N, H, W)
+    x = F.conv2d(feats.flatten(0, 1), sd["input_proj.weight"], sd["input_proj.bias"])
+    x = x.view(B, N, *x.shape[-3:])
+    assert c["with_position"] and c["with_multiview"], "oracle covers the shipped configs"
+    feat, cmask, _ = position_features(img_metas, B, N, H, W, masks, c["depth_num"],
+                                       c["depth_start"], c["position_range"], c["LID"])
+    pos = conv1x1_mlp(feat, sd["position_encoder.0.weight"], sd["position_encoder.0.bias"],
+                      sd["position_encoder.2.weight"], sd["position_encoder.2.bias"])
+    if taps is not None:
+        taps["coords_position_embeding"] = pos.view(x.shape)
+        taps["coords_mask"] = cmask
+        taps["masks"] = masks
+        taps["memory"] = x
+    if c["with_fpe"]:
+        # SELayer petrv2_head.py:48-60, called at petrv2_head.py:464-466
+        xf = x.flatten(0, 1)
+        se = F.conv2d(F.relu(F.conv2d(xf, sd["fpe.conv_reduce.weight"], sd["fpe.conv_reduce.bias"])),
+                      sd["fpe.conv_expand.weight"], sd["fpe.conv_expand.bias"])
+        pos = pos * torch.sigmoid(se)
+    pos = pos.view(x.shape)
+    sin = sine_positional_encoding_3d(masks, c["num_feats"], normalize=c["normalize"])
+    sin = conv1x1_mlp(sin.flatten(0, 1), sd["adapt_pos3d.0.weight"], sd["adapt_pos3d.0.bias"],
+                      sd["adapt_pos3d.2.weight"], sd["adapt_pos3d.2.bias"]).view(x.shape)
+    pos_embed = pos + sin
+    ref = sd["reference_points.weight"]
+    qe = pos2posemb3d(ref)
+    qe = F.linear(F.relu(F.linear(qe, sd["query_embedding.0.weight"], sd["query_embedding.0.bias"])),
+                  sd["query_embedding.2.weight"], sd["query_embedding.2.bias"])
+    if taps is not None:
+        taps["pos_embed"] = pos_embed
+        taps["query_embeds"] = qe
+        taps["layers"] = []
+    outs_dec = transformer(sd, x, masks, qe, pos_embed, c["num_layers"], c["num_heads"],
+                           taps=taps["layers"] if taps is not None else None)
+    outs_dec = torch.nan_to_num(outs_dec)
+    if taps is not None:
+        taps["outs_dec"] = outs_dec
+    reference = inverse_sigmoid(ref.unsqueeze(0).repeat(B, 1, 1))
+    mean_ts = None
+    if c["with_time"]:
+        ts = torch.tensor(np.asarray([np.asarray(m["timestamp"]) for m in img_metas]),
+                          dtype=torch.float32).view(B, -1, 6)
+        mean_ts = (ts[:, 1, :] - ts[:, 0, :]).mean(-1)
+    cls_out, reg_out = [], []
+    for l in range(outs_dec.shape[0]):
+        cls_out.append(cls_branch(sd, f"cls_branches.{l}.", outs_dec[l], c["num_reg_fcs"]))
+        if c["with_multi"]:
+            tmp = reg_layer_multi(sd, f"reg_branches.{l}.", outs_dec[l], c["num_reg_fcs"])
+        else:
+            tmp = reg_branch(sd, f"reg_branches.{l}.", outs_dec[l], c["num_reg_fcs"])
+        tmp[..., 0:2] = (tmp[..., 0:2] + reference[..., 0:2]).sigmoid()
+        tmp[..., 4:5] = (tmp[..., 4:5] + reference[..., 2:3]).sigmoid()
+        if mean_ts is not None:
+            tmp[..., 8:] = tmp[..., 8:] / mean_ts            # petrv2_head.py:520-521 (B == 1)
+        reg_out.append(tmp)
+    cls = torch.stack(cls_out)
+    box = torch.stack(reg_out)
+    pc = c["pc_range"]
+    box[..., 0:1] = box[..., 0:1] * (pc[3] - pc[0]) + pc[0]
+    box[..., 1:2] = box[..., 1:2] * (pc[4] - pc[1]) + pc[1]
+    box[..., 4:5] = box[..., 4:5] * (pc[5] - pc[2]) + pc[2]
+    return dict(all_cls_scores=cls, all_bbox_preds=box, enc_cls_scores=None, enc_bbox_preds=None)
