@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py -- PETR head (position embedding + 6-layer decoder) samples/sec on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload vov-p4-1600x640] [--batch B_per_gpu] [--precision bf16|fp32]
+
+One "step" = one head forward (PETRHead.forward, petr_head.py:366-468) over a batch of B
+synthetic samples of the named BASELINE config (random-init weights, synthetic 6-view features and
+nuScenes-like img_metas; petr_b200.synth).  N>1: launched by torch.distributed.run, one process per
+GPU, samples sharded data-parallel (weak scaling, no data-path collective; NCCL only for the timing
+barrier / max over ranks).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "PETR head 6-view samples/sec at 1600x640, 1/2/4/8 B200; attn % of bf16 peak"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(source="measured", hbm=d["hbm_gbs"], bf16=d["bf16_tflops"],
+                    bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]))
+    return dict(source="fallback", hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=float(max(smax)) if smax else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def cpu_oracle_setup(wl, seed=0):
+    import petr_b200 as pb
+    from petr_b200 import synth
+    head = pb.build_head(wl.head_cfg())
+    head.load_state_dict(synth.head_state_dict(head, seed), strict=True)
+    sd = {k: v.detach().clone() for k, v in head.state_dict().items()}
+    v2 = wl.head == "PETRv2Head"
+    return sd, dict(with_fpe=v2, with_time=v2, with_multi=v2)
+
+
+def time_cpu_oracle(wl, nsamples, seed=0):
+    """Reference's CPU implementation of the path (oracle port, fp32, all host threads):
+    per-sample loop as BASELINE.md section 2 prescribes."""
+    from oracle import petr_oracle as po          # the one place bench.py executes oracle/
+    from petr_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd, ocfg = cpu_oracle_setup(wl, seed)
+    metas = synth.make_img_metas(wl, 1, seed)
+    x = synth.make_features(wl, 1, seed)
+    with torch.no_grad():
+        po.head_forward(sd, x, metas, ocfg)                       # warm-up
+        times = []
+        for _ in range(nsamples):
+            t = time.perf_counter()
+            po.head_forward(sd, x, metas, ocfg)
+            times.append(time.perf_counter() - t)
+    return times, cores
+
+
+def run_reference(args, wl, rank):
+    if rank != 0:
+        return
+    warm = max(0, args.warmup)
+    times, cores = time_cpu_oracle(wl, max(1, args.steps) + warm, 0)
+    times = times[warm:] if len(times) > warm else times
+    total = float(sum(times))
+    value = len(times) / total
+    line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=args.gpus, steps=len(times),
+                warmup=warm, ms_per_step=1000.0 * total / len(times), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=wl.name, batch_per_step=1, num_keys=wl.num_keys,
+                            note="reference head forward on host CPU, fp32, per-sample loop"),
+                cpu_baseline=dict(value=value, unit="samples/s", cores=cores, kind="port",
+                                  sample=f"{len(times)} single-sample head forwards of {wl.name} "
+                                         f"(oracle/petr_oracle.py, torch CPU fp32, {cores} threads)"),
+                e2e=dict(value=value, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="vov-p4-1600x640")
+    ap.add_argument("--batch", type=int, default=16, help="samples per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-samples", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import petr_b200 as pb
+    from petr_b200 import ops, synth
+    wl = pb.WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; petr_b200 has no CPU fallback")
+    args.warmup = max(3, args.warmup)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    head = pb.build_head(wl.head_cfg())
+    head.load_state_dict(synth.head_state_dict(head, 0), strict=True)
+    head = head.eval().to(dev)
+    head.precision = args.precision
+    # each rank gets its own shard of the global batch (different seeds per rank)
+    metas = synth.make_img_metas(wl, B, seed=rank)
+    x_host = synth.make_features(wl, B, seed=rank, pin=True)
+    x_dev = x_host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing (`value`) ---------------------------------------------------
+    for _ in range(args.warmup):
+        out = head([x_dev], metas)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.KERNEL_TIMERS = {}
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = head([x_dev], metas)
+    e1.record()
+    barrier()
+    launches = ops.launch_count()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    timers = ops.KERNEL_TIMERS
+    ops.KERNEL_TIMERS = None
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1000.0)
+
+    # ---- end-to-end through the public API with host buffers (`e2e`) -------------------------
+    out_host = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+                for k in ("all_cls_scores", "all_bbox_preds")}
+
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        o = head([xd], metas)
+        for k in out_host:
+            out_host[k].copy_(o[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * B * args.steps / e2e_s
+    h2d = x_host.numel() * 4 + B * wl.num_cams * (64 + 8)
+    d2h = sum(t.numel() * 4 for t in out_host.values())
+
+    # ---- roofline of the dominant kernel (flash cross-attention) ------------------------------
+    peaks = load_peaks()
+    roofline = None
+    if timers and timers.get("cross_attention_bf16"):
+        evs = timers["cross_attention_bf16"]
+        avg_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        s = head.engine.spec
+        flops = 4.0 * s.Lq * wl.num_keys * s.E * B                  # per launch (one layer, B samples)
+        achieved = flops / (avg_ms * 1e-3) / 1e12
+        roofline = dict(kernel="cross_attention_tc_kernel", bound="tensor", achieved=achieved,
+                        peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_sustained"],
+                        traffic=None, peak_source=peaks["source"] + " bf16 sustained",
+                        launches_timed=len(evs), avg_launch_ms=avg_ms,
+                        share_of_step=avg_ms * s.L / ms_per_step,
+                        alg_flops_per_launch=flops)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            times, cores = time_cpu_oracle(wl, args.cpu_samples, 0)
+            v = len(times) / float(sum(times))
+            cpu = dict(value=v, unit="samples/s", cores=cores, kind="port",
+                       sample=f"{len(times)} single-sample head forwards of {wl.name} "
+                              f"(oracle/petr_oracle.py, torch CPU fp32, {cores} threads)")
+        line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="bf16" if args.precision == "bf16" else "f32",
+                    data="synthetic",
+                    config=dict(workload=wl.name, batch_per_gpu=B, global_batch=B * world,
+                                num_keys=wl.num_keys, num_query=900, decoder_layers=6,
+                                parallelism=f"dp{world}", precision=args.precision,
+                                l2="inputs larger than L2 (%.0f MB features per step)" % (x_host.numel() * 4 / 1e6)),
+                    e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=int(h2d),
+                             d2h_bytes_per_step=int(d2h)),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roofline, cpu_baseline=cpu)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

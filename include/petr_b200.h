@@ -1,0 +1,175 @@
+/*
+ * petr_b200.h -- C ABI of the B200-native PETR detection-head hot path (libpetr_b200.so).
+ *
+ * Drop-in boundary for sty61010/PETR's head hot path.  The reference has no native code and no
+ * FFI of its own: the hot path is straight-line PyTorch inside
+ *   projects/mmdet3d_plugin/models/dense_heads/petr_head.py      (PETRHead.forward :366-468,
+ *                                                                  position_embeding :286-334)
+ *   projects/mmdet3d_plugin/models/dense_heads/petrv2_head.py    (PETRv2Head.forward :429-540)
+ *   projects/mmdet3d_plugin/models/utils/petr_transformer.py     (PETRMultiheadAttention :280-367,
+ *                                                                  decoder :423-447)
+ *   projects/mmdet3d_plugin/models/utils/positional_encoding.py  (SinePositionalEncoding3D :58-100)
+ * so each entry point below cites the reference lines whose library calls it replaces.  The
+ * binding a maintainer adds is a ctypes stub (see INTEGRATION.md and petr_b200/_lib.py).
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the parameter name starts with `h_` (host, read
+ *    during the call).  The caller allocates every input, output and workspace; the library
+ *    never allocates, frees or retains device memory.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), does not
+ *    synchronise, and is CUDA-graph capturable.  Device = the calling thread's current device.
+ *  - Return value: 0 = success; < 0 = argument/shape/alignment error found on the host before
+ *    any launch (PETR_E_*); > 0 = a cudaError_t from the launch.  petr_last_error_string()
+ *    returns a thread-local description of the last non-zero return.  Nothing throws or exits.
+ *  - "tokens" are the position-aware image keys, flattened (b, n, h, w) with w fastest:
+ *    T = B*N*H*W rows, Lk = N*H*W per sample (order of petr_transformer.py:90).
+ *  - Query-side rows are flattened (b, q): row = b*Lq + q.
+ */
+#ifndef PETR_B200_H_
+#define PETR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PETR_B200_ABI_VERSION 1
+
+#define PETR_E_BADARG   (-1)   /* null pointer / non-positive dimension */
+#define PETR_E_SHAPE    (-2)   /* unsupported shape (see each function) */
+#define PETR_E_ALIGN    (-3)   /* pointer or leading dimension not aligned as required */
+#define PETR_E_ARCH     (-4)   /* device is not sm_100 */
+
+#define PETR_DTYPE_F32  0
+#define PETR_DTYPE_BF16 1
+
+#define PETR_ACT_NONE         0
+#define PETR_ACT_RELU         1
+#define PETR_ACT_SIGMOID_GATE 2   /* out = gate[m,n] * sigmoid(acc + bias)  (PETRv2 SELayer) */
+
+#define PETR_A_ROWMAJOR 0         /* A[m*lda + k] */
+#define PETR_A_NCHW     1         /* A[(m/hw)*K*hw + k*hw + (m%hw)]: conv1x1 over (G,K,h,w) maps */
+
+int petr_abi_version(void);
+const char* petr_last_error_string(void);
+/* number of kernels this library has launched on the calling thread since the last reset */
+int64_t petr_launch_count(void);
+void petr_launch_count_reset(void);
+
+/* ---- a4: key-padding masks.  petr_head.py:383-394 (ones(pad) / zero img_shape /
+ * F.interpolate nearest / .to(bool)).  img_hw: int32 [B*N*2] = (img_h, img_w) per view.
+ * mask: uint8 [B,N,H,W], 1 = padded key.  Bit-exact. */
+int petr_key_padding_mask(const int32_t* img_hw, int B, int N, int pad_h, int pad_w,
+                          int H, int W, uint8_t* mask, void* stream);
+
+/* ---- a1 (first half): frustum -> img2lidar -> normalise -> coords_mask -> inverse_sigmoid.
+ * petr_head.py:286-331 (== petrv2_head.py:348-394).  img2lidar: fp32 [B,N,4,4], the float64
+ * host inverse of lidar2img rounded once to fp32 (petr_head.py:308-315; done by the caller).
+ * h_range_lo[i] = (float)position_range[i], h_range_span[i] = (float)(position_range[3+i] -
+ * position_range[i]), bin_size = (float)bin_size_double (petr_head.py:296/:301).
+ * feat: [T, 3*D] (channel = 3*d + c), fp32 or bf16.  masks (nullable): uint8 [B,N,H,W] OR'ed
+ * into coords_mask (nullable, uint8 [B,N,H,W]).  coords3d (nullable): fp32 [B,N,H,W,D,3], the
+ * normalised coordinates before inverse_sigmoid, for bit-exactness tests.
+ * Grid, depth bins, transform and normalisation use separately rounded fp32 mul/add/div (no FMA
+ * contraction) and are bit-exact against the CPU reference; log is within 2 ulp. */
+int petr_frustum_features(const float* img2lidar, const uint8_t* masks,
+                          int B, int N, int H, int W, int D, int pad_h, int pad_w,
+                          int lid, float depth_start, float bin_size,
+                          const float* h_range_lo, const float* h_range_span,
+                          void* feat, int feat_dtype, uint8_t* coords_mask, float* coords3d,
+                          void* stream);
+
+/* ---- a3 (first half): SinePositionalEncoding3D features.  positional_encoding.py:58-100.
+ * mask uint8 [B,N,H,W]; dim_t fp32 [num_feats] (= temperature ** (2*(i//2)/num_feats), computed
+ * by the caller exactly as positional_encoding.py:81-83).  out: [T, 3*num_feats] with the
+ * reference's channel order (n | y | x, each = [sin of even dims | cos of odd dims]). */
+int petr_sine3d_features(const uint8_t* mask, const float* dim_t, int B, int N, int H, int W,
+                         int num_feats, int normalize, float scale, float eps, float offset,
+                         void* out, int out_dtype, void* stream);
+
+/* ---- a6: pos2posemb3d.  petr_head.py:31-43.  ref fp32 [Q,3] -> out fp32 [Q, 3*num_feats]
+ * in (y, x, z) order, interleaved sin/cos. */
+int petr_pos2posemb3d(const float* ref, const float* dim_t, int Q, int num_feats, float* out,
+                      void* stream);
+
+/* ---- fp32 GEMM with fused prologue/epilogue: every nn.Linear / 1x1 Conv2d on the path
+ * (petr_head.py:219-274 layers; FFN; MultiheadAttention in/out projections).
+ *   C[m,n] = epi( sum_k (A[m,k] + A2[m % a2_rows, k]) * W[n,k] + bias[n] ) + residual[m,n]
+ * A2/bias/residual/gate/C_bf16 nullable.  residual, gate and C share ldc.  C_bf16 (nullable) receives
+ * a bf16 copy of C with the same ldc.  W is [N,K] row-major (nn.Linear / conv weight layout).
+ * Exact fp32 FFMA accumulation (fp32-parity path: <= 1e-6 relative to tensor scale). */
+int petr_gemm_f32(const float* A, int lda, int a_layout, int hw,
+                  const float* A2, int a2_rows,
+                  const float* W, const float* bias, const float* residual, const float* gate,
+                  int act, float* C, void* C_bf16, int ldc, int M, int N, int K, void* stream);
+
+/* ---- a9/a10: multi-head attention core (softmax(Q K^T * scale + mask) V), fp32, flash-style
+ * streaming over keys; no score matrix is materialised.  torch.nn.MultiheadAttention as called
+ * by petr_transformer.py:357-362 (packed projections are separate petr_gemm_* calls).
+ * Q rows b*Lq+q (ldq), K/V rows b*Lk+k (ldk/ldv), head h occupies columns [h*head_dim, ...).
+ * key_mask nullable uint8 [B,Lk], 1 = ignore.  A row whose keys are all masked yields NaN,
+ * like the reference (zeroed later by nan_to_num, petr_head.py:435).  head_dim must be 32. */
+int petr_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
+                       const uint8_t* key_mask, float* O, int ldo,
+                       int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
+
+/* ---- nn.LayerNorm over the last dim (eps 1e-5 on this path), optional fused ReLU
+ * (cls_branches, petr_head.py:226-231) and nan_to_num (petr_head.py:435).  Y may alias X. */
+int petr_layernorm_f32(const float* X, const float* gamma, const float* beta, float* Y,
+                       int rows, int E, float eps, int relu, int nan_to_num, void* stream);
+
+/* ---- a12: reference-point add, sigmoid and pc_range affine.  petr_head.py:440-460
+ * (+ PETRv2 with_time petrv2_head.py:499-505,:520-521).  reg: fp32 [L*B*Q, code_size] in place.
+ * ref: fp32 [Q,3] (reference_points.weight).  h_pc_range: host float[6].  time_div nullable
+ * fp32 [B]: channels 8.. are divided by time_div[b]. */
+int petr_decode_boxes(float* reg, const float* ref, const float* h_pc_range,
+                      const float* time_div, int L, int B, int Q, int code_size, void* stream);
+
+/* ---- tcgen05 tier (sm_100a tensor cores, TMA-fed, TMEM accumulators) ----------------- */
+
+/* bf16 x bf16 -> fp32 GEMM on tcgen05:  C = epi(A[M,K] * W[N,K]^T + bias) (+ residual).
+ * A, W: bf16 row-major, K % 64 == 0, 16-byte aligned rows.  out_mode selects the store:
+ *   0: fp32 C[m*ldc+n];  1: bf16 C[m*ldc+n];
+ *   2: bf16 head-split layout C[n / 256][b][(n % 256) / 32][key][32] with b = m / kv_Lk,
+ *      key = m % kv_Lk -- the K/V layout petr_cross_attention_bf16 reads.
+ * Used for the Lk-side work: K/V projection of all decoder layers in one launch
+ * (petr_transformer.py:341-344,:357-360), position_encoder / adapt_pos3d MLPs. */
+int petr_gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias,
+                      const float* residual, int act, void* C, int ldc, int out_mode,
+                      int M, int N, int K, int kv_Lk, void* stream);
+
+/* fp32 Q [B*Lq, heads*32] (row stride ldq) -> bf16 [B, heads, Lq, 32] multiplied by `scale`
+ * (head_dim^-1/2 * log2 e: the softmax of petr_cross_attention_bf16 runs in the exp2 domain). */
+int petr_pack_q_bf16(const float* Q, int ldq, void* out, int B, int Lq, int heads, float scale,
+                     void* stream);
+
+/* Flash cross-attention on tcgen05 (QK^T -> TMEM, online softmax in registers, P -> bf16,
+ * PV -> TMEM), petr_transformer.py:357-362 for one decoder layer.
+ *   Qs : bf16 [B, heads, Lq, 32]  (petr_pack_q_bf16)
+ *   Kh : bf16 [B, heads, Lk, 32]  (out_mode 2 of petr_gemm_bf16_tc)
+ *   Vh : bf16 [B, heads, Lk, 32]
+ *   key_mask nullable uint8 [B, Lk], 1 = ignore.
+ * nsplit key splits run as separate CTAs (split-KV for small B).  write_partial == 0: O fp32
+ * [B*Lq, heads*32] (row stride ldo) receives the normalised result (partials of nsplit > 1 are
+ * merged internally; `partial` is then the scratch, petr_attention_partial_floats * nsplit).
+ * write_partial == 1: only the un-normalised partials (O, m, l) are written to `partial`
+ * (layout below) for a later petr_attention_merge -- the key-split-across-GPUs path. */
+int petr_cross_attention_bf16(const void* Qs, const void* Kh, const void* Vh,
+                              const uint8_t* key_mask, float* O, int ldo, float* partial,
+                              int B, int Lq, int Lk, int heads, int nsplit, int write_partial,
+                              void* stream);
+
+/* Merge `nparts` partial attention results (on-GPU split-KV or key-split across GPUs after an
+ * all-gather):  m = max m_r;  O = sum e^{m_r-m} O_r / sum e^{m_r-m} l_r.
+ * partial: fp32 [nparts][ rows*32 (O) | rows*2 (m, l) ], rows = B*heads*Lq ordered (b, head, q);
+ * m is in the log2 domain. */
+int petr_attention_merge(const float* partial, int nparts, float* O, int ldo,
+                         int B, int Lq, int heads, void* stream);
+
+int64_t petr_attention_partial_floats(int B, int Lq, int heads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PETR_B200_H_ */

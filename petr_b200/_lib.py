@@ -1,0 +1,92 @@
+"""ctypes binding of libpetr_b200.so (the C ABI declared in include/petr_b200.h).
+
+The library is the product: there is no Python/PyTorch fallback for any op.  If the shared
+object is missing or an entry point fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpetr_b200.so")
+
+_P, _I, _F = c_void_p, c_int, c_float
+
+# name -> (restype, argtypes); mirrors include/petr_b200.h one to one
+SIGNATURES = {
+    "petr_abi_version": (c_int, []),
+    "petr_last_error_string": (c_char_p, []),
+    "petr_launch_count": (c_int64, []),
+    "petr_launch_count_reset": (None, []),
+    "petr_key_padding_mask": (c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "petr_frustum_features": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P,
+                                      _P, _I, _P, _P, _P]),
+    "petr_sine3d_features": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _I, _P]),
+    "petr_pos2posemb3d": (c_int, [_P, _P, _I, _I, _P, _P]),
+    "petr_gemm_f32": (c_int, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "petr_attention_f32": (c_int, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "petr_layernorm_f32": (c_int, [_P, _P, _P, _P, _I, _I, _F, _I, _I, _P]),
+    "petr_decode_boxes": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "petr_gemm_bf16_tc": (c_int, [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "petr_pack_q_bf16": (c_int, [_P, _I, _P, _I, _I, _I, _F, _P]),
+    "petr_cross_attention_bf16": (c_int, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "petr_attention_merge": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P]),
+    "petr_attention_partial_floats": (c_int64, [_I, _I, _I]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m petr_b200.build` "
+                "(petr_b200 has no CPU / PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.petr_abi_version() != 1:
+            raise RuntimeError("libpetr_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def ptr(t):
+    """Device (or host) pointer of a tensor / None."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def host_floats(vals):
+    return (c_float * len(vals))(*[float(v) for v in vals])
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def check(rc: int, name: str):
+    if rc != 0:
+        msg = lib().petr_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"{name} failed with code {rc}: {msg}")
+
+
+def call(name: str, *args):
+    check(getattr(lib(), name)(*args), name)
+
+
+def launch_count() -> int:
+    return int(lib().petr_launch_count())
+
+
+def reset_launch_count():
+    lib().petr_launch_count_reset()

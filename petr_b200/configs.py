@@ -15,8 +15,9 @@ VOXEL_SIZE = [0.2, 0.2, 8]
 POSITION_RANGE = [-61.2, -61.2, -10.0, 61.2, 61.2, 10.0]
 
 
-def _transformer_cfg(num_layers=6, embed_dims=256, num_heads=8, feedforward_channels=2048):
-    return dict(
+def _transformer_cfg(num_layers=6, embed_dims=256, num_heads=8, feedforward_channels=2048,
+                     with_cp=True):
+    cfg = dict(
         type='PETRTransformer',
         decoder=dict(
             type='PETRTransformerDecoder',
@@ -35,9 +36,12 @@ def _transformer_cfg(num_layers=6, embed_dims=256, num_heads=8, feedforward_chan
                 with_cp=True,
                 operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')),
         ))
+    if with_cp is None:          # petr_vovnet_gridmask_p4_800x320.py leaves with_cp at its default
+        del cfg['decoder']['transformerlayers']['with_cp']
+    return cfg
 
 
-def _common(in_channels):
+def _common(in_channels, with_cp=True):
     return dict(
         num_classes=10,
         in_channels=in_channels,
@@ -46,7 +50,7 @@ def _common(in_channels):
         with_position=True,
         with_multiview=True,
         position_range=list(POSITION_RANGE),
-        transformer=_transformer_cfg(),
+        transformer=_transformer_cfg(with_cp=with_cp),
         bbox_coder=dict(
             type='NMSFreeCoder',
             post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0],
@@ -60,16 +64,18 @@ def _common(in_channels):
         loss_iou=dict(type='GIoULoss', loss_weight=0.0))
 
 
-def petr_head_cfg(in_channels=256):
+def petr_head_cfg(in_channels=256, with_cp=True, **overrides):
     cfg = dict(type='PETRHead', normedlinear=False)
-    cfg.update(_common(in_channels))
+    cfg.update(_common(in_channels, with_cp))
+    cfg.update(overrides)
     return cfg
 
 
-def petrv2_head_cfg(in_channels=256):
+def petrv2_head_cfg(in_channels=256, **overrides):
     cfg = dict(type='PETRv2Head', with_fpe=True, with_time=True, with_multi=True,
                code_weights=[1.0] * 10)
     cfg.update(_common(in_channels))
+    cfg.update(overrides)
     return cfg
 
 
@@ -102,6 +108,6 @@ WORKLOADS = {
         Workload('v2-vov-p4-800x320', 'PETRv2Head', 12, 256, 20, 50, 320, 800),
         # small shapes for fast tests (not BASELINE configs)
         Workload('tiny', 'PETRHead', 2, 64, 4, 10, 64, 160),
-        Workload('tiny-v2', 'PETRv2Head', 4, 64, 4, 10, 64, 160),
+        Workload('tiny-v2', 'PETRv2Head', 12, 64, 4, 10, 64, 160),
     ]
 }

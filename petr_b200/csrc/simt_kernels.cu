@@ -1,0 +1,648 @@
+// fp32 CUDA-core kernels of the PETR head hot path (sm_100a).
+//
+// These are the exact-arithmetic kernels: coordinate/mask generation (bit-exact against the CPU
+// reference), the fp32 GEMM used where the 1e-5 / 2e-2 tolerances need fp32-class accuracy
+// (query-side projections, branches, fp32 position-embedding path), LayerNorm, box decode and a
+// flash-style fp32 attention (self-attention and the fp32 cross-attention path).  The Lk-side
+// tensor-core work lives in tc_gemm.cu / tc_attention.cu.
+#include "common.cuh"
+#include <math.h>
+
+namespace petr {
+
+// ------------------------------------------------------------------------------------------
+// a4: key-padding masks (petr_head.py:383-394)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size) {
+    // torch upsample_nearest: identity / >>1 shortcuts, else min(floorf(dst * (float)in/out), in-1)
+    if (out_size == in_size) return dst;
+    if (out_size == 2 * in_size) return dst >> 1;
+    float scale = (float)in_size / (float)out_size;
+    int s = (int)floorf(__fmul_rn((float)dst, scale));
+    return s < in_size - 1 ? s : in_size - 1;
+}
+
+__global__ void key_padding_mask_kernel(const int32_t* __restrict__ img_hw, int BN, int pad_h,
+                                        int pad_w, int H, int W, uint8_t* __restrict__ mask) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)BN * H * W;
+    if (i >= total) return;
+    int c = (int)(i % W);
+    int r = (int)((i / W) % H);
+    int bn = (int)(i / ((int64_t)W * H));
+    int ih = img_hw[2 * bn], iw = img_hw[2 * bn + 1];
+    int sr = nearest_src(r, pad_h, H), sc = nearest_src(c, pad_w, W);
+    mask[i] = (sr < ih && sc < iw) ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// a1: frustum features (petr_head.py:286-331).  One warp per token (b,n,h,w); lane handles
+// depths lane and lane+32 (D <= 64) or strides over D in general.
+// ------------------------------------------------------------------------------------------
+struct FrustumParams {
+    int B, N, H, W, D, pad_h, pad_w, lid;
+    float depth_start, bin_size;
+    float lo[3], span[3];
+};
+
+__device__ __forceinline__ float inv_sigmoid_f(float x) {
+    const float eps = 1e-5f;
+    x = fminf(fmaxf(x, 0.f), 1.f);
+    float x1 = fmaxf(x, eps);
+    float x2 = fmaxf(__fsub_rn(1.f, x), eps);
+    return logf(__fdiv_rn(x1, x2));
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+frustum_features_kernel(FrustumParams p, const float* __restrict__ img2lidar,
+                        const uint8_t* __restrict__ masks, OutT* __restrict__ feat,
+                        uint8_t* __restrict__ coords_mask, float* __restrict__ coords3d) {
+    __shared__ float sM[8][12];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t T = (int64_t)p.B * p.N * p.H * p.W;
+    const int64_t t = (int64_t)blockIdx.x * 8 + warp;
+    const bool live = t < T;
+    int w = 0, h = 0, bn = 0;
+    if (live) {
+        w = (int)(t % p.W);
+        h = (int)((t / p.W) % p.H);
+        bn = (int)(t / ((int64_t)p.W * p.H));
+        if (lane < 12) sM[warp][lane] = img2lidar[(int64_t)bn * 16 + lane];   // rows 0..2
+    }
+    __syncwarp();
+    if (!live) return;
+    const float* M = sM[warp];
+    // pixel-corner grids: arange().float() * pad / size  (petr_head.py:290-291)
+    const float u = __fdiv_rn(__fmul_rn((float)w, (float)p.pad_w), (float)p.W);
+    const float v = __fdiv_rn(__fmul_rn((float)h, (float)p.pad_h), (float)p.H);
+    int bad = 0;
+    for (int d = lane; d < p.D; d += 32) {
+        float fd = (float)d, depth;
+        if (p.lid)   // depth_start + bin_size * index * (index + 1)  (petr_head.py:294-297)
+            depth = __fadd_rn(p.depth_start, __fmul_rn(__fmul_rn(p.bin_size, fd), __fadd_rn(fd, 1.f)));
+        else         // depth_start + bin_size * index               (petr_head.py:299-302)
+            depth = __fadd_rn(p.depth_start, __fmul_rn(p.bin_size, fd));
+        const float dm = fmaxf(depth, 1e-5f);
+        const float p0 = __fmul_rn(u, dm), p1 = __fmul_rn(v, dm), p2 = depth;
+        float c[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            // ((m0*p0 + m1*p1) + m2*p2) + m3*1 with separately rounded ops (petr_head.py:319)
+            float acc = __fmul_rn(M[4 * i + 0], p0);
+            acc = __fadd_rn(acc, __fmul_rn(M[4 * i + 1], p1));
+            acc = __fadd_rn(acc, __fmul_rn(M[4 * i + 2], p2));
+            acc = __fadd_rn(acc, M[4 * i + 3]);
+            c[i] = __fdiv_rn(__fsub_rn(acc, p.lo[i]), p.span[i]);          // :320-325
+            bad += (c[i] > 1.0f) | (c[i] < 0.0f);                          // :327
+        }
+        if (coords3d) {
+            float* o = coords3d + (t * p.D + d) * 3;
+            o[0] = c[0]; o[1] = c[1]; o[2] = c[2];
+        }
+        OutT* f = feat + t * (int64_t)(3 * p.D) + 3 * d;
+        if constexpr (sizeof(OutT) == 4) {
+            f[0] = inv_sigmoid_f(c[0]); f[1] = inv_sigmoid_f(c[1]); f[2] = inv_sigmoid_f(c[2]);
+        } else {
+            f[0] = __float2bfloat16_rn(inv_sigmoid_f(c[0]));
+            f[1] = __float2bfloat16_rn(inv_sigmoid_f(c[1]));
+            f[2] = __float2bfloat16_rn(inv_sigmoid_f(c[2]));
+        }
+    }
+    if (coords_mask) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        if (lane == 0) {
+            // sum > D * 0.5 (python float compare, petr_head.py:328)
+            uint8_t m = ((float)bad > (float)p.D * 0.5f) ? 1 : 0;
+            if (masks) m |= (masks[t] != 0);
+            coords_mask[t] = m;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// a3: SinePositionalEncoding3D features (positional_encoding.py:58-100).  One block per
+// (b, n, h) feature row.
+// ------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+sine3d_features_kernel(const uint8_t* __restrict__ mask, const float* __restrict__ dim_t,
+                       int B, int N, int H, int W, int F, int normalize, float scale, float eps,
+                       float offset, OutT* __restrict__ out) {
+    extern __shared__ float sm[];            // [3][W] values, then [F] dim_t
+    float* vn = sm;
+    float* vy = sm + W;
+    float* vx = sm + 2 * W;
+    float* sdt = sm + 3 * W;
+    const int h = blockIdx.x % H;
+    const int n = (blockIdx.x / H) % N;
+    const int b = blockIdx.x / (H * N);
+    const int64_t HW = (int64_t)H * W;
+    const uint8_t* mb = mask + (int64_t)b * N * HW;
+    for (int i = threadIdx.x; i < F; i += blockDim.x) sdt[i] = dim_t[i];
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        int en = 0, ln = 0, ey = 0, ly = 0;
+        for (int k = 0; k < N; ++k) {
+            int nm = mb[k * HW + (int64_t)h * W + w] ? 0 : 1;
+            ln += nm;
+            if (k <= n) en += nm;
+        }
+        for (int k = 0; k < H; ++k) {
+            int nm = mb[n * HW + (int64_t)k * W + w] ? 0 : 1;
+            ly += nm;
+            if (k <= h) ey += nm;
+        }
+        float fn = (float)en, fy = (float)ey;
+        if (normalize) {
+            fn = __fmul_rn(__fdiv_rn(__fadd_rn(fn, offset), __fadd_rn((float)ln, eps)), scale);
+            fy = __fmul_rn(__fdiv_rn(__fadd_rn(fy, offset), __fadd_rn((float)ly, eps)), scale);
+        }
+        vn[w] = fn;
+        vy[w] = fy;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        const uint8_t* row = mb + n * HW + (int64_t)h * W;
+        for (int w = 0; w < W; ++w) { acc += row[w] ? 0 : 1; vx[w] = (float)acc; }
+        if (normalize) {
+            float last = __fadd_rn((float)acc, eps);
+            for (int w = 0; w < W; ++w)
+                vx[w] = __fmul_rn(__fdiv_rn(__fadd_rn(vx[w], offset), last), scale);
+        }
+    }
+    __syncthreads();
+    const int C = 3 * F, half = F / 2;
+    OutT* orow = out + ((int64_t)blockIdx.x * W) * C;
+    for (int i = threadIdx.x; i < W * C; i += blockDim.x) {
+        int w = i / C, ch = i % C;
+        int axis = ch / F, j = ch % F;
+        float val = axis == 0 ? vn[w] : (axis == 1 ? vy[w] : vx[w]);
+        float r;
+        if (j < half) r = sinf(__fdiv_rn(val, sdt[2 * j]));
+        else          r = cosf(__fdiv_rn(val, sdt[2 * (j - half) + 1]));
+        if constexpr (sizeof(OutT) == 4) orow[i] = r; else orow[i] = __float2bfloat16_rn(r);
+    }
+}
+
+// a6: pos2posemb3d (petr_head.py:31-43)
+__global__ void pos2posemb3d_kernel(const float* __restrict__ ref, const float* __restrict__ dim_t,
+                                    int Q, int F, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int C = 3 * F;
+    if (i >= Q * C) return;
+    int q = i / C, ch = i % C, blk = ch / F, j = ch % F;
+    const int axis_of_blk[3] = {1, 0, 2};                       // cat((pos_y, pos_x, pos_z))
+    float p = __fmul_rn(ref[q * 3 + axis_of_blk[blk]], 6.283185307179586f);
+    float a = __fdiv_rn(p, dim_t[j]);
+    out[i] = (j & 1) ? cosf(a) : sinf(a);
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 GEMM: C = epi((A + A2) W^T + bias) + residual.  128x64 tile, BK 16, 256 threads, 8x4/thread
+// ------------------------------------------------------------------------------------------
+constexpr int GBM = 128, GBN = 64, GBK = 16;
+
+struct GemmParams {
+    const float* A; int lda; int a_layout; int hw;
+    const float* A2; int a2_rows;
+    const float* W; const float* bias; const float* residual; const float* gate;
+    int act; float* C; __nv_bfloat16* Cb; int ldc; int M, N, K;
+};
+
+__device__ __forceinline__ float gemm_load_a(const GemmParams& p, int m, int k) {
+    if (m >= p.M || k >= p.K) return 0.f;
+    float v;
+    if (p.a_layout == PETR_A_NCHW) {
+        int g = m / p.hw, r = m - g * p.hw;
+        v = p.A[((int64_t)g * p.K + k) * p.hw + r];
+    } else {
+        v = p.A[(int64_t)m * p.lda + k];
+    }
+    if (p.A2) v += p.A2[(int64_t)(m % p.a2_rows) * p.lda + k];
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+gemm_f32_kernel(GemmParams p) {
+    __shared__ __align__(16) float As[2][GBK][GBM + 4];
+    __shared__ __align__(16) float Bs[2][GBK][GBN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * GBM, n0 = blockIdx.y * GBN;
+    const int tm = (tid / 16) * 8, tn = (tid % 16) * 4;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const bool vecA = (p.a_layout == PETR_A_ROWMAJOR) && ((p.lda & 3) == 0) && ((p.K & 3) == 0) &&
+                      aligned16(p.A) && (!p.A2 || aligned16(p.A2));
+    const bool vecB = ((p.K & 3) == 0) && aligned16(p.W);
+    float ra[8], rb[4];
+
+    auto load_tiles = [&](int k0) {
+        if (p.a_layout == PETR_A_NCHW) {
+            // contiguous along m for fixed k: thread -> (k = tid/16 .. , m = tid%16*8..)
+            int k = tid / 16, mm = (tid % 16) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ra[i] = gemm_load_a(p, m0 + mm + i, k0 + k);
+        } else if (vecA) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                int idx = tid + r * 256;                 // 512 float4: 128 rows x 4
+                int m = m0 + idx / 4, k = k0 + (idx % 4) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < p.M && k < p.K) {
+                    v = *reinterpret_cast<const float4*>(p.A + (int64_t)m * p.lda + k);
+                    if (p.A2) {
+                        float4 w = *reinterpret_cast<const float4*>(p.A2 + (int64_t)(m % p.a2_rows) * p.lda + k);
+                        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+                    }
+                }
+                ra[r * 4 + 0] = v.x; ra[r * 4 + 1] = v.y; ra[r * 4 + 2] = v.z; ra[r * 4 + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                int idx = tid + r * 256;                 // 2048 scalars: 128 rows x 16
+                ra[r] = gemm_load_a(p, m0 + idx / 16, k0 + idx % 16);
+            }
+        }
+        if (vecB) {
+            int n = n0 + tid / 4, k = k0 + (tid % 4) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < p.N && k < p.K) v = *reinterpret_cast<const float4*>(p.W + (int64_t)n * p.K + k);
+            rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; rb[3] = v.w;
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                int idx = tid + r * 256;
+                int n = n0 + idx / 16, k = k0 + idx % 16;
+                rb[r] = (n < p.N && k < p.K) ? p.W[(int64_t)n * p.K + k] : 0.f;
+            }
+        }
+    };
+    auto store_tiles = [&](int buf) {
+        if (p.a_layout == PETR_A_NCHW) {
+            int k = tid / 16, mm = (tid % 16) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) As[buf][k][mm + i] = ra[i];
+        } else if (vecA) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                int idx = tid + r * 256;
+                int m = idx / 4, k = (idx % 4) * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) As[buf][k + j][m] = ra[r * 4 + j];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                int idx = tid + r * 256;
+                As[buf][idx % 16][idx / 16] = ra[r];
+            }
+        }
+        if (vecB) {
+            int n = tid / 4, k = (tid % 4) * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Bs[buf][k + j][n] = rb[j];
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                int idx = tid + r * 256;
+                Bs[buf][idx % 16][idx / 16] = rb[r];
+            }
+        }
+    };
+
+    const int nk = (p.K + GBK - 1) / GBK;
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kb = 0; kb < nk; ++kb) {
+        const int buf = kb & 1;
+        if (kb + 1 < nk) load_tiles((kb + 1) * GBK);
+#pragma unroll
+        for (int k = 0; k < GBK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][tm + 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tn]);
+            float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kb + 1 < nk) {
+            store_tiles(buf ^ 1);
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int m = m0 + tm + i;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tn + j;
+            if (n >= p.N) continue;
+            float v = acc[i][j];
+            if (p.bias) v += p.bias[n];
+            int64_t o = (int64_t)m * p.ldc + n;
+            if (p.act == PETR_ACT_RELU) v = fmaxf(v, 0.f);
+            else if (p.act == PETR_ACT_SIGMOID_GATE) v = p.gate[o] * (1.f / (1.f + expf(-v)));
+            if (p.residual) v += p.residual[o];
+            if (p.C) p.C[o] = v;
+            if (p.Cb) p.Cb[o] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 flash-style attention, head_dim 32.  One thread per query row; keys staged in smem.
+// ------------------------------------------------------------------------------------------
+constexpr int ATT_THREADS = 64, ATT_KT = 64;
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk,
+                     const float* __restrict__ V, int ldv, const uint8_t* __restrict__ key_mask,
+                     float* __restrict__ O, int ldo, int Lq, int Lk, float scale_log2) {
+    __shared__ __align__(16) float sK[ATT_KT][32];
+    __shared__ __align__(16) float sV[ATT_KT][32];
+    __shared__ float sBias[ATT_KT];
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int q = blockIdx.x * ATT_THREADS + threadIdx.x;
+    const bool live = q < Lq;
+    float qv[32], o[32];
+    {
+        const float* qp = Q + ((int64_t)b * Lq + (live ? q : 0)) * ldq + head * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { qv[i] = qp[i] * scale_log2; o[i] = 0.f; }
+    }
+    float m = -INFINITY, l = 0.f;
+    const float* Kb = K + (int64_t)b * Lk * ldk + head * 32;
+    const float* Vb = V + (int64_t)b * Lk * ldv + head * 32;
+    for (int k0 = 0; k0 < Lk; k0 += ATT_KT) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < ATT_KT * 8; i += ATT_THREADS) {
+            int r = i / 8, c4 = (i % 8) * 4;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (k0 + r < Lk) {
+                kv = *reinterpret_cast<const float4*>(Kb + (int64_t)(k0 + r) * ldk + c4);
+                vv = *reinterpret_cast<const float4*>(Vb + (int64_t)(k0 + r) * ldv + c4);
+            }
+            *reinterpret_cast<float4*>(&sK[r][c4]) = kv;
+            *reinterpret_cast<float4*>(&sV[r][c4]) = vv;
+        }
+        for (int r = threadIdx.x; r < ATT_KT; r += ATT_THREADS) {
+            bool dead = (k0 + r >= Lk) || (key_mask && key_mask[(int64_t)b * Lk + k0 + r]);
+            sBias[r] = dead ? -INFINITY : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int r0 = 0; r0 < ATT_KT; r0 += 8) {
+            float s[8];
+            float mx = m;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    float4 kk = *reinterpret_cast<const float4*>(&sK[r0 + j][i]);
+                    a = fmaf(qv[i], kk.x, a); a = fmaf(qv[i + 1], kk.y, a);
+                    a = fmaf(qv[i + 2], kk.z, a); a = fmaf(qv[i + 3], kk.w, a);
+                }
+                s[j] = a + sBias[r0 + j];
+                mx = fmaxf(mx, s[j]);
+            }
+            if (mx == -INFINITY) continue;             // everything so far masked
+            float alpha = exp2f(m - mx);               // m = -inf -> 0
+            m = mx;
+            l *= alpha;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] *= alpha;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float pj = exp2f(s[j] - mx);
+                l += pj;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    float4 vv = *reinterpret_cast<const float4*>(&sV[r0 + j][i]);
+                    o[i] = fmaf(pj, vv.x, o[i]); o[i + 1] = fmaf(pj, vv.y, o[i + 1]);
+                    o[i + 2] = fmaf(pj, vv.z, o[i + 2]); o[i + 3] = fmaf(pj, vv.w, o[i + 3]);
+                }
+            }
+        }
+    }
+    if (live) {
+        float inv = 1.f / l;                           // l == 0 (all keys masked) -> NaN, as torch
+        float* op = O + ((int64_t)b * Lq + q) * ldo + head * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) op[i] = o[i] * inv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, E multiple of 32, E <= 2048
+// ------------------------------------------------------------------------------------------
+template <int PER>
+__global__ void __launch_bounds__(256)
+layernorm_f32_kernel(const float* __restrict__ X, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float* __restrict__ Y, int rows,
+                     float eps, int relu, int nan_to_num) {
+    constexpr int E = PER * 32;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* x = X + (int64_t)row * E;
+    float v[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] = x[lane + 32 * i]; s += v[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)E;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q += d * d; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)E + eps);
+    float* y = Y + (int64_t)row * E;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int c = lane + 32 * i;
+        float r = (v[i] - mean) * rstd * gamma[c] + beta[c];
+        if (relu) r = fmaxf(r, 0.f);       // only used on finite branch inputs
+        if (nan_to_num) {
+            if (isnan(r)) r = 0.f;
+            else if (isinf(r)) r = r > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+        }
+        y[c] = r;
+    }
+}
+
+// a12: reference add + sigmoid + pc_range affine (petr_head.py:440-460)
+struct DecodeParams { float pc[6]; };
+
+__global__ void decode_boxes_kernel(float* __restrict__ reg, const float* __restrict__ ref,
+                                    DecodeParams dp, const float* __restrict__ time_div,
+                                    int64_t rows, int B, int Q, int cs) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    int q = (int)(r % Q);
+    int b = (int)((r / Q) % B);
+    float* t = reg + r * cs;
+    float rx = inv_sigmoid_f(ref[q * 3 + 0]), ry = inv_sigmoid_f(ref[q * 3 + 1]),
+          rz = inv_sigmoid_f(ref[q * 3 + 2]);
+    float x = 1.f / (1.f + expf(-(t[0] + rx)));
+    float y = 1.f / (1.f + expf(-(t[1] + ry)));
+    float z = 1.f / (1.f + expf(-(t[4] + rz)));
+    t[0] = x * (dp.pc[3] - dp.pc[0]) + dp.pc[0];
+    t[1] = y * (dp.pc[4] - dp.pc[1]) + dp.pc[1];
+    t[4] = z * (dp.pc[5] - dp.pc[2]) + dp.pc[2];
+    if (time_div) {
+        float d = time_div[b];
+        for (int c = 8; c < cs; ++c) t[c] = t[c] / d;
+    }
+}
+
+}  // namespace petr
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace petr;
+
+extern "C" int petr_key_padding_mask(const int32_t* img_hw, int B, int N, int pad_h, int pad_w,
+                                     int H, int W, uint8_t* mask, void* stream) {
+    PETR_REQUIRE(img_hw && mask, PETR_E_BADARG, "petr_key_padding_mask: null pointer");
+    PETR_REQUIRE(B > 0 && N > 0 && H > 0 && W > 0 && pad_h > 0 && pad_w > 0, PETR_E_BADARG,
+                 "petr_key_padding_mask: non-positive dimension");
+    int64_t total = (int64_t)B * N * H * W;
+    key_padding_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        img_hw, B * N, pad_h, pad_w, H, W, mask);
+    return after_launch("petr_key_padding_mask");
+}
+
+extern "C" int petr_frustum_features(const float* img2lidar, const uint8_t* masks, int B, int N,
+                                     int H, int W, int D, int pad_h, int pad_w, int lid,
+                                     float depth_start, float bin_size, const float* h_range_lo,
+                                     const float* h_range_span, void* feat, int feat_dtype,
+                                     uint8_t* coords_mask, float* coords3d, void* stream) {
+    PETR_REQUIRE(img2lidar && feat && h_range_lo && h_range_span, PETR_E_BADARG,
+                 "petr_frustum_features: null pointer");
+    PETR_REQUIRE(B > 0 && N > 0 && H > 0 && W > 0 && D > 0, PETR_E_BADARG,
+                 "petr_frustum_features: non-positive dimension");
+    PETR_REQUIRE(feat_dtype == PETR_DTYPE_F32 || feat_dtype == PETR_DTYPE_BF16, PETR_E_BADARG,
+                 "petr_frustum_features: bad dtype %d", feat_dtype);
+    FrustumParams p;
+    p.B = B; p.N = N; p.H = H; p.W = W; p.D = D; p.pad_h = pad_h; p.pad_w = pad_w; p.lid = lid;
+    p.depth_start = depth_start; p.bin_size = bin_size;
+    for (int i = 0; i < 3; ++i) { p.lo[i] = h_range_lo[i]; p.span[i] = h_range_span[i]; }
+    int64_t T = (int64_t)B * N * H * W;
+    unsigned grid = (unsigned)((T + 7) / 8);
+    if (feat_dtype == PETR_DTYPE_F32)
+        frustum_features_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            p, img2lidar, masks, (float*)feat, coords_mask, coords3d);
+    else
+        frustum_features_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            p, img2lidar, masks, (__nv_bfloat16*)feat, coords_mask, coords3d);
+    return after_launch("petr_frustum_features");
+}
+
+extern "C" int petr_sine3d_features(const uint8_t* mask, const float* dim_t, int B, int N, int H,
+                                    int W, int num_feats, int normalize, float scale, float eps,
+                                    float offset, void* out, int out_dtype, void* stream) {
+    PETR_REQUIRE(mask && dim_t && out, PETR_E_BADARG, "petr_sine3d_features: null pointer");
+    PETR_REQUIRE(B > 0 && N > 0 && H > 0 && W > 0 && num_feats > 0 && (num_feats % 2) == 0,
+                 PETR_E_BADARG, "petr_sine3d_features: bad dimension");
+    size_t smem = (size_t)(3 * W + num_feats) * sizeof(float);
+    PETR_REQUIRE(smem <= 48 * 1024, PETR_E_SHAPE, "petr_sine3d_features: W too large");
+    unsigned grid = (unsigned)(B * N * H);
+    if (out_dtype == PETR_DTYPE_F32)
+        sine3d_features_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(
+            mask, dim_t, B, N, H, W, num_feats, normalize, scale, eps, offset, (float*)out);
+    else if (out_dtype == PETR_DTYPE_BF16)
+        sine3d_features_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(
+            mask, dim_t, B, N, H, W, num_feats, normalize, scale, eps, offset, (__nv_bfloat16*)out);
+    else
+        return fail(PETR_E_BADARG, "petr_sine3d_features: bad dtype %d", out_dtype);
+    return after_launch("petr_sine3d_features");
+}
+
+extern "C" int petr_pos2posemb3d(const float* ref, const float* dim_t, int Q, int num_feats,
+                                 float* out, void* stream) {
+    PETR_REQUIRE(ref && dim_t && out, PETR_E_BADARG, "petr_pos2posemb3d: null pointer");
+    PETR_REQUIRE(Q > 0 && num_feats > 0, PETR_E_BADARG, "petr_pos2posemb3d: bad dimension");
+    int total = Q * 3 * num_feats;
+    pos2posemb3d_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ref, dim_t, Q, num_feats, out);
+    return after_launch("petr_pos2posemb3d");
+}
+
+extern "C" int petr_gemm_f32(const float* A, int lda, int a_layout, int hw, const float* A2,
+                             int a2_rows, const float* W, const float* bias, const float* residual,
+                             const float* gate, int act, float* C, void* C_bf16, int ldc, int M,
+                             int N, int K, void* stream) {
+    PETR_REQUIRE(A && W && (C || C_bf16), PETR_E_BADARG, "petr_gemm_f32: null pointer");
+    PETR_REQUIRE(M > 0 && N > 0 && K > 0 && ldc >= N, PETR_E_BADARG, "petr_gemm_f32: bad dimension");
+    PETR_REQUIRE(a_layout == PETR_A_ROWMAJOR || a_layout == PETR_A_NCHW, PETR_E_BADARG,
+                 "petr_gemm_f32: bad a_layout");
+    if (a_layout == PETR_A_NCHW)
+        PETR_REQUIRE(hw > 0 && M % hw == 0 && !A2, PETR_E_SHAPE, "petr_gemm_f32: NCHW needs M %% hw == 0, no A2");
+    else
+        PETR_REQUIRE(lda >= K, PETR_E_BADARG, "petr_gemm_f32: lda < K");
+    if (A2) PETR_REQUIRE(a2_rows > 0, PETR_E_BADARG, "petr_gemm_f32: a2_rows <= 0");
+    if (act == PETR_ACT_SIGMOID_GATE) PETR_REQUIRE(gate, PETR_E_BADARG, "petr_gemm_f32: gate is null");
+    GemmParams p{A, lda, a_layout, hw, A2, a2_rows, W, bias, residual, gate, act, C,
+                 (__nv_bfloat16*)C_bf16, ldc, M, N, K};
+    dim3 grid((M + GBM - 1) / GBM, (N + GBN - 1) / GBN);
+    gemm_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    return after_launch("petr_gemm_f32");
+}
+
+extern "C" int petr_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V,
+                                  int ldv, const uint8_t* key_mask, float* O, int ldo, int B, int Lq,
+                                  int Lk, int heads, int head_dim, float scale, void* stream) {
+    PETR_REQUIRE(Q && K && V && O, PETR_E_BADARG, "petr_attention_f32: null pointer");
+    PETR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0, PETR_E_BADARG, "petr_attention_f32: bad dimension");
+    PETR_REQUIRE(head_dim == 32, PETR_E_SHAPE, "petr_attention_f32: head_dim must be 32, got %d", head_dim);
+    PETR_REQUIRE((ldk & 3) == 0 && (ldv & 3) == 0 && aligned16(K) && aligned16(V), PETR_E_ALIGN,
+                 "petr_attention_f32: K/V rows must be 16-byte aligned");
+    dim3 grid((Lq + ATT_THREADS - 1) / ATT_THREADS, heads, B);
+    attention_f32_kernel<<<grid, ATT_THREADS, 0, (cudaStream_t)stream>>>(
+        Q, ldq, K, ldk, V, ldv, key_mask, O, ldo, Lq, Lk, scale * 1.4426950408889634f);
+    return after_launch("petr_attention_f32");
+}
+
+extern "C" int petr_layernorm_f32(const float* X, const float* gamma, const float* beta, float* Y,
+                                  int rows, int E, float eps, int relu, int nan_to_num, void* stream) {
+    PETR_REQUIRE(X && gamma && beta && Y, PETR_E_BADARG, "petr_layernorm_f32: null pointer");
+    PETR_REQUIRE(rows > 0 && E > 0, PETR_E_BADARG, "petr_layernorm_f32: bad dimension");
+    dim3 grid((rows + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+#define PETR_LN_CASE(PER) case PER * 32: \
+        layernorm_f32_kernel<PER><<<grid, 256, 0, st>>>(X, gamma, beta, Y, rows, eps, relu, nan_to_num); break;
+    switch (E) {
+        PETR_LN_CASE(1) PETR_LN_CASE(2) PETR_LN_CASE(4) PETR_LN_CASE(8)
+        PETR_LN_CASE(16) PETR_LN_CASE(32) PETR_LN_CASE(64)
+        default:
+            return fail(PETR_E_SHAPE, "petr_layernorm_f32: E must be 32 * 2^k <= 2048, got %d", E);
+    }
+#undef PETR_LN_CASE
+    return after_launch("petr_layernorm_f32");
+}
+
+extern "C" int petr_decode_boxes(float* reg, const float* ref, const float* h_pc_range,
+                                 const float* time_div, int L, int B, int Q, int code_size, void* stream) {
+    PETR_REQUIRE(reg && ref && h_pc_range, PETR_E_BADARG, "petr_decode_boxes: null pointer");
+    PETR_REQUIRE(L > 0 && B > 0 && Q > 0 && code_size >= 5, PETR_E_BADARG, "petr_decode_boxes: bad dimension");
+    DecodeParams dp;
+    for (int i = 0; i < 6; ++i) dp.pc[i] = h_pc_range[i];
+    int64_t rows = (int64_t)L * B * Q;
+    decode_boxes_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reg, ref, dp, time_div, rows, B, Q, code_size);
+    return after_launch("petr_decode_boxes");
+}

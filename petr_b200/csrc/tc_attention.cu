@@ -1,0 +1,413 @@
+// Flash cross-attention on tcgen05 (petr_transformer.py:357-362, one decoder layer):
+//   S = Q K^T (TMEM, fp32) -> online softmax in registers (one thread per query row, exp2 domain,
+//   lazy rescaling) -> P (bf16, shared memory, UMMA K-major 128B-swizzled) -> O += P V (TMEM).
+// No (B*heads, Lq, Lk) score tensor ever exists; K and V tiles stream through a TMA/mbarrier ring.
+//
+// CTA = one (batch, head, 128-query tile, key split).  Warp 0: TMA producer.  Warp 1: TMEM
+// allocator + single-thread tcgen05.mma issuer.  Warps 2-5: softmax / correction / epilogue, thread
+// r owns query row r (TMEM lane r).  S is double buffered in TMEM and P in shared memory, so
+// QK^T of tile j+1 runs on the tensor core while the softmax warps work on tile j.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <math.h>
+
+namespace petr {
+namespace {
+
+using namespace tc;
+
+constexpr int QT = 128;            // query rows per CTA
+constexpr int KT = 128;            // keys per tile
+constexpr int HD = 32;             // head dim
+constexpr int KV_STAGES = 4;
+constexpr int Q_BYTES = QT * HD * 2;            // 8 KB
+constexpr int K_BYTES = KT * HD * 2;            // 8 KB
+constexpr int V_BYTES = KT * HD * 2;            // 8 KB
+constexpr int P_BYTES = QT * KT * 2;            // 32 KB
+constexpr int OFF_Q = 0;
+constexpr int OFF_KV = OFF_Q + Q_BYTES;
+constexpr int OFF_P = OFF_KV + KV_STAGES * (K_BYTES + V_BYTES);
+constexpr int OFF_BIAS = OFF_P + 2 * P_BYTES;
+constexpr int OFF_BAR = OFF_BIAS + 2 * KT * 4;
+constexpr int ATT_SMEM = OFF_BAR + 256 + 1024;
+constexpr int ATT_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256;
+constexpr float RESCALE_TH = 8.0f;  // lazy rescale threshold (log2 domain): p <= 2^8
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct AttParams {
+    const uint8_t* key_mask;   // [B, Lk] or null
+    float* O; int ldo;         // normalised output (nsplit == 1)
+    float* partial;            // [nsplit][rows*32 O | rows*2 (m,l)], rows = B*heads*Lq
+    int B, Lq, Lk, heads, nsplit, tiles_total, write_partial;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, AttParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* q_full = bars;                        // 1
+    uint64_t* kv_full = bars + 1;                   // KV_STAGES
+    uint64_t* kv_empty = kv_full + KV_STAGES;       // KV_STAGES
+    uint64_t* s_full = kv_empty + KV_STAGES;        // 2
+    uint64_t* s_free = s_full + 2;                  // 2
+    uint64_t* p_ready = s_free + 2;                 // 2
+    uint64_t* pv_done = p_ready + 2;                // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+    float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qtile = blockIdx.x;
+    const int bh = blockIdx.y;                      // b * heads + h
+    const int split = blockIdx.z;
+    const int b = bh / p.heads, h = bh - b * p.heads;
+    // key tiles of this split: [t_begin, t_end)
+    const int per = (p.tiles_total + p.nsplit - 1) / p.nsplit;
+    const int t_begin = split * per;
+    const int t_end = min(p.tiles_total, t_begin + per);
+    const int ntiles = max(0, t_end - t_begin);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(q_full, 1);
+            for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128);
+                mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, TMEM_COLS);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            if (ntiles > 0) {
+                mbar_arrive_expect_tx(q_full, Q_BYTES);
+                tma_load_3d(smem + OFF_Q, &tmQ, q_full, 0, qtile * QT, bh);
+            }
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % KV_STAGES;
+                const uint32_t ph = (j / KV_STAGES) & 1;
+                mbar_wait(&kv_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
+                uint8_t* kd = smem + OFF_KV + s * (K_BYTES + V_BYTES);
+                const int key0 = (t_begin + j) * KT;
+                tma_load_3d(kd, &tmK, &kv_full[s], 0, key0, bh);
+                tma_load_3d(kd + K_BYTES, &tmV, &kv_full[s], 0, key0, bh);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0 && ntiles > 0) {
+            constexpr uint32_t idesc_qk = make_idesc(QT, KT, 1, 0, 0);     // S[128x128] = Q K^T
+            constexpr uint32_t idesc_pv = make_idesc(QT, HD, 1, 0, 1);     // O[128x32] += P V (V MN-major)
+            const uint32_t q_addr = smem_u32(smem + OFF_Q);
+            auto issue_qk = [&](int t) {
+                const int s = t % KV_STAGES;
+                mbar_wait(&kv_full[s], (t / KV_STAGES) & 1);
+                mbar_wait(&s_free[t & 1], ((t >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t k_addr = smem_u32(smem + OFF_KV + s * (K_BYTES + V_BYTES));
+                const uint32_t d = tmem_base + ((t & 1) ? TM_S1 : TM_S0);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {
+                    uint64_t ad = make_smem_desc(q_addr + k * 32, 16, 512, LAYOUT_SW64);
+                    uint64_t bd = make_smem_desc(k_addr + k * 32, 16, 512, LAYOUT_SW64);
+                    umma_f16_ss(d, ad, bd, idesc_qk, k ? 1u : 0u);
+                }
+                umma_commit(&s_full[t & 1]);
+            };
+            mbar_wait(q_full, 0);
+            issue_qk(0);
+            for (int j = 0; j < ntiles; ++j) {
+                if (j + 1 < ntiles) issue_qk(j + 1);
+                const int s = j % KV_STAGES;
+                mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+                tcgen05_fence_after();
+                const uint32_t p_addr = smem_u32(smem + OFF_P + (j & 1) * P_BYTES);
+                const uint32_t v_addr = smem_u32(smem + OFF_KV + s * (K_BYTES + V_BYTES) + K_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < KT / 16; ++kk) {
+                    // P: two 64-key K-atoms of 16 KB; 32 B per 16-key step inside an atom
+                    uint64_t ad = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+                    // V: [key][32 dims] MN-major, 64B-swizzled; 8-key groups are 512 B apart
+                    uint64_t bd = make_smem_desc(v_addr + kk * 1024, 512, 512, LAYOUT_SW64);
+                    umma_f16_ss(tmem_base + TM_O, ad, bd, idesc_pv, (j | kk) ? 1u : 0u);
+                }
+                umma_commit(&kv_empty[s]);
+                umma_commit(&pv_done[j & 1]);
+            }
+        }
+    } else {
+        // ---------------- softmax / correction / epilogue: thread <-> query row ----------------
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int sm_tid = row;                              // 0..127 within the softmax group
+        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        float m_use = -INFINITY, l = 0.f;
+        const bool use_mask = (p.key_mask != nullptr);
+        for (int j = 0; j < ntiles; ++j) {
+            const int bsel = j & 1;
+            const uint32_t u = (j >> 1) & 1;
+            const int key0 = (t_begin + j) * KT;
+            const bool need_bias = use_mask || (key0 + KT > p.Lk);
+            if (need_bias) {
+                const int key = key0 + sm_tid;
+                bool dead = key >= p.Lk;
+                if (!dead && use_mask) dead = p.key_mask[(int64_t)b * p.Lk + key] != 0;
+                sbias[bsel * KT + sm_tid] = dead ? -INFINITY : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            mbar_wait(&s_full[bsel], u);
+            tcgen05_fence_after();
+            uint32_t sr[128];
+            const uint32_t s_addr = tmem_base + lane_off + (bsel ? TM_S1 : TM_S0);
+            tmem_ld_x32(s_addr, sr);
+            tmem_ld_x32(s_addr + 32, sr + 32);
+            tmem_ld_x32(s_addr + 64, sr + 64);
+            tmem_ld_x32(s_addr + 96, sr + 96);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(&s_free[bsel]);
+            float* sv = reinterpret_cast<float*>(sr);
+            if (need_bias) {
+                const float* bb = sbias + bsel * KT;
+#pragma unroll
+                for (int i = 0; i < 128; ++i) sv[i] += bb[i];
+            }
+            float mx = sv[0];
+#pragma unroll
+            for (int i = 1; i < 128; ++i) mx = fmaxf(mx, sv[i]);
+            // lazy rescale: only move the reference max when it grew by more than RESCALE_TH
+            bool grow = mx > m_use + RESCALE_TH;             // (-inf + 8 = -inf) -> true on first finite max
+            float alpha = 1.f;
+            if (grow) {
+                alpha = ex2(m_use - mx);                     // m_use = -inf -> 0
+                m_use = mx;
+                l *= alpha;
+            }
+            const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
+            float lsum = 0.f;
+            uint32_t pk[64];
+#pragma unroll
+            for (int i = 0; i < 128; i += 2) {
+                float p0 = ex2(sv[i] - m_eff), p1 = ex2(sv[i + 1] - m_eff);
+                lsum += p0 + p1;
+                pk[i >> 1] = pack_bf16x2(p0, p1);
+            }
+            l += lsum;
+            // P[bsel] is free once PV(j-2) has retired
+            mbar_wait(&pv_done[bsel], u ^ 1);
+            uint8_t* prow = smem + OFF_P + bsel * P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                uint8_t* dst = prow + (c >> 3) * 16384 + (((c & 7) ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
+            // correction: O *= alpha (needs PV(j-1) retired); warp-uniform decision
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {
+                mbar_wait(&pv_done[bsel ^ 1], ((j - 1) >> 1) & 1);
+                tcgen05_fence_after();
+                uint32_t orr[32];
+                tmem_ld_x32(tmem_base + lane_off + TM_O, orr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+                tmem_st_x32(tmem_base + lane_off + TM_O, orr);
+                tmem_st_wait();
+            }
+            fence_proxy_async_smem();
+            tcgen05_fence_before();
+            mbar_arrive(&p_ready[bsel]);
+        }
+        // ---------------- epilogue ----------------
+        const int q = qtile * QT + row;
+        float o[32];
+        if (ntiles > 0) {
+            const int jl = ntiles - 1;
+            mbar_wait(&pv_done[jl & 1], (jl >> 1) & 1);
+            tcgen05_fence_after();
+            uint32_t orr[32];
+            tmem_ld_x32(tmem_base + lane_off + TM_O, orr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(orr[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = 0.f;
+        }
+        if (q < p.Lq) {
+            if (p.write_partial) {
+                const int64_t prow_i = (int64_t)bh * p.Lq + q;
+                const int64_t rows = (int64_t)p.B * p.heads * p.Lq;
+                float* pbase = p.partial + (int64_t)split * rows * 34;
+                float* po = pbase + prow_i * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(po + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                float* pm = pbase + rows * 32 + prow_i * 2;
+                pm[0] = m_use; pm[1] = l;
+            } else {
+                const float inv = 1.f / l;          // l == 0 (all keys masked) -> NaN like torch
+                float* op = p.O + ((int64_t)b * p.Lq + q) * p.ldo + h * HD;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(op + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// merge partial (O, m, l) over parts; thread per (row, 4 dims)
+__global__ void attention_merge_kernel(const float* __restrict__ part, int nparts, float* __restrict__ O,
+                                       int ldo, int B, int Lq, int heads) {
+    const int64_t rows = (int64_t)B * heads * Lq;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * 8) return;
+    const int64_t r = idx >> 3;
+    const int d4 = (int)(idx & 7) * 4;
+    const int64_t part_stride = rows * 34;
+    float m = -INFINITY;
+    for (int pz = 0; pz < nparts; ++pz) m = fmaxf(m, part[pz * part_stride + rows * 32 + r * 2]);
+    float den = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int pz = 0; pz < nparts; ++pz) {
+        const float* base = part + pz * part_stride;
+        float mp = base[rows * 32 + r * 2], lp = base[rows * 32 + r * 2 + 1];
+        float w = (mp == -INFINITY) ? 0.f : exp2f(mp - m);
+        den += w * lp;
+        float4 o = *reinterpret_cast<const float4*>(base + r * 32 + d4);
+        acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
+    }
+    const float inv = 1.f / den;                     // den == 0 -> NaN (all keys masked)
+    const int q = (int)(r % Lq);
+    const int bh = (int)(r / Lq);
+    const int b = bh / heads, h = bh % heads;
+    float* op = O + ((int64_t)b * Lq + q) * ldo + h * 32 + d4;
+    *reinterpret_cast<float4*>(op) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+}
+
+// fp32 Q [B*Lq, heads*32] -> bf16 [B, heads, Lq, 32], scaled (head_dim^-1/2 * log2 e)
+__global__ void pack_q_kernel(const float* __restrict__ Q, int ldq, __nv_bfloat16* __restrict__ out,
+                              int B, int Lq, int heads, float scale) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // over B*Lq*heads*16 pairs
+    const int64_t total = (int64_t)B * Lq * heads * 16;
+    if (idx >= total) return;
+    const int d2 = (int)(idx & 15) * 2;
+    const int h = (int)((idx >> 4) % heads);
+    const int64_t bq = idx / (16 * heads);
+    const int q = (int)(bq % Lq);
+    const int b = (int)(bq / Lq);
+    const float* src = Q + bq * ldq + h * 32 + d2;
+    __nv_bfloat162 v = __floats2bfloat162_rn(src[0] * scale, src[1] * scale);
+    *reinterpret_cast<__nv_bfloat162*>(out + (((int64_t)b * heads + h) * Lq + q) * 32 + d2) = v;
+}
+
+}  // namespace
+}  // namespace petr
+
+using namespace petr;
+
+extern "C" int64_t petr_attention_partial_floats(int B, int Lq, int heads) {
+    return (int64_t)B * heads * Lq * 34;
+}
+
+extern "C" int petr_pack_q_bf16(const float* Q, int ldq, void* out, int B, int Lq, int heads,
+                                float scale, void* stream) {
+    PETR_REQUIRE(Q && out, PETR_E_BADARG, "petr_pack_q_bf16: null pointer");
+    PETR_REQUIRE(B > 0 && Lq > 0 && heads > 0 && ldq >= heads * 32, PETR_E_BADARG, "petr_pack_q_bf16: bad dimension");
+    int64_t total = (int64_t)B * Lq * heads * 16;
+    pack_q_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        Q, ldq, (__nv_bfloat16*)out, B, Lq, heads, scale);
+    return after_launch("petr_pack_q_bf16");
+}
+
+extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const void* Vh,
+                                         const uint8_t* key_mask, float* O, int ldo, float* partial,
+                                         int B, int Lq, int Lk, int heads, int nsplit,
+                                         int write_partial, void* stream) {
+    PETR_REQUIRE(Qs && Kh && Vh, PETR_E_BADARG, "petr_cross_attention_bf16: null pointer");
+    PETR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0 && nsplit > 0, PETR_E_BADARG,
+                 "petr_cross_attention_bf16: bad dimension");
+    const bool part = write_partial || nsplit > 1;
+    if (part) PETR_REQUIRE(partial, PETR_E_BADARG, "petr_cross_attention_bf16: partial buffer required");
+    if (!write_partial) PETR_REQUIRE(O && ldo >= heads * 32 && (ldo % 4) == 0 && aligned16(O), PETR_E_ALIGN,
+                                     "petr_cross_attention_bf16: O must be 16-byte aligned, ldo %% 4 == 0");
+    PETR_REQUIRE(aligned16(Qs) && aligned16(Kh) && aligned16(Vh), PETR_E_ALIGN,
+                 "petr_cross_attention_bf16: Q/K/V must be 16-byte aligned");
+    const int tiles = (Lk + KT - 1) / KT;
+    if (nsplit > tiles) nsplit = tiles;
+    CUtensorMap tmQ, tmK, tmV;
+    {
+        uint64_t d[3] = {HD, (uint64_t)Lq, (uint64_t)B * heads};
+        uint64_t s[2] = {HD * 2, (uint64_t)Lq * HD * 2};
+        uint32_t box[3] = {HD, QT, 1};
+        int rc = tmap::encode(&tmQ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Qs, d, s, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+    }
+    {
+        uint64_t d[3] = {HD, (uint64_t)Lk, (uint64_t)B * heads};
+        uint64_t s[2] = {HD * 2, (uint64_t)Lk * HD * 2};
+        uint32_t box[3] = {HD, KT, 1};
+        int rc = tmap::encode(&tmK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Kh, d, s, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+        rc = tmap::encode(&tmV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Vh, d, s, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+    }
+    cudaError_t e = cudaFuncSetAttribute(cross_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e != cudaSuccess) return fail((int)e, "petr_cross_attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    AttParams p{};
+    p.key_mask = key_mask; p.O = O; p.ldo = ldo;
+    const int64_t rows = (int64_t)B * heads * Lq;
+    p.partial = partial;
+    p.B = B; p.Lq = Lq; p.Lk = Lk; p.heads = heads; p.nsplit = nsplit; p.tiles_total = tiles;
+    p.write_partial = part ? 1 : 0;
+    dim3 grid((Lq + QT - 1) / QT, B * heads, nsplit);
+    cross_attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    int rc = after_launch("petr_cross_attention_bf16");
+    if (rc) return rc;
+    if (part && !write_partial) {
+        // on-GPU split-KV: merge right away
+        int64_t total = rows * 8;
+        attention_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            partial, nsplit, O, ldo, B, Lq, heads);
+        return after_launch("petr_attention_merge");
+    }
+    return 0;
+}
+
+extern "C" int petr_attention_merge(const float* partial, int nparts, float* O, int ldo, int B, int Lq,
+                                    int heads, void* stream) {
+    PETR_REQUIRE(partial && O, PETR_E_BADARG, "petr_attention_merge: null pointer");
+    PETR_REQUIRE(nparts > 0 && B > 0 && Lq > 0 && heads > 0 && ldo >= heads * 32 && (ldo % 4) == 0, PETR_E_BADARG,
+                 "petr_attention_merge: bad dimension");
+    int64_t total = (int64_t)B * heads * Lq * 8;
+    attention_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        partial, nparts, O, ldo, B, Lq, heads);
+    return after_launch("petr_attention_merge");
+}

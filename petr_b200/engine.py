@@ -1,0 +1,319 @@
+"""Head engine: packs a head's parameters once per device and runs the whole hot path
+(PETRHead.forward petr_head.py:366-468 / PETRv2Head.forward petrv2_head.py:429-540) as a
+sequence of libpetr_b200.so kernel launches on the current CUDA stream.
+
+Internal layouts (chosen once):
+  * image tokens ("keys") are token-major: row t = ((b*N + n)*H + h)*W + w, 256 channels
+    contiguous -- the order petr_transformer.py:90 flattens to, but batch-first.
+  * query-side activations are (B*Lq, 256) rows, row = b*Lq + q.
+Two precision paths, both CUDA-only:
+  * 'fp32'  -- every GEMM/attention in fp32 (the 1e-5 position-embedding parity path);
+  * 'bf16'  -- the Lk-side work (position/adapt MLPs, K/V projection, QK^T, PV) on tcgen05
+               tensor cores with bf16 operands and fp32 accumulation; query-side GEMMs,
+               residual stream, LayerNorm, softmax statistics and branches stay fp32.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID_GATE
+
+
+# ------------------------------------------------------------------------------------------
+# host-side img_metas ingestion (vectorised; SURVEY.md hard part 7)
+# ------------------------------------------------------------------------------------------
+def img2lidar_from_metas(img_metas: Sequence[dict]) -> np.ndarray:
+    """float64 batched inverse of lidar2img, rounded once to fp32 (petr_head.py:308-315).
+    A batched np.linalg.inv on the stacked (B,N,4,4) array is bit-identical to the reference's
+    per-view loop."""
+    l2i = np.asarray([np.asarray(m["lidar2img"], dtype=np.float64) for m in img_metas])
+    return np.linalg.inv(l2i).astype(np.float32)
+
+
+def img_hw_from_metas(img_metas: Sequence[dict], N: int) -> np.ndarray:
+    out = np.empty((len(img_metas), N, 2), dtype=np.int32)
+    for b, m in enumerate(img_metas):
+        shp = np.asarray(m["img_shape"])[:N]
+        out[b] = shp[:, :2]
+    return out
+
+
+def mean_time_stamp(img_metas: Sequence[dict]) -> torch.Tensor:
+    """petrv2_head.py:499-505 on the host in fp32 (tiny)."""
+    ts = torch.tensor(np.asarray([np.asarray(m["timestamp"]) for m in img_metas]), dtype=torch.float32)
+    ts = ts.view(len(img_metas), -1, 6)
+    return (ts[:, 1, :] - ts[:, 0, :]).mean(-1)
+
+
+def _h2d(arr, device) -> torch.Tensor:
+    t = torch.from_numpy(np.ascontiguousarray(arr)) if isinstance(arr, np.ndarray) else arr
+    return t.pin_memory().to(device, non_blocking=True)
+
+
+def sine_dim_t(num_feats: int, temperature: float) -> torch.Tensor:
+    """positional_encoding.py:81-83 / petr_head.py:34-35, evaluated with the same torch ops."""
+    dim_t = torch.arange(num_feats, dtype=torch.float32)
+    return temperature ** (2 * (dim_t // 2) / num_feats)
+
+
+class HeadSpec:
+    """Static description of a head, read from the module's ctor arguments."""
+
+    def __init__(self, head):
+        self.E = head.embed_dims
+        self.heads = head.transformer.decoder.layers[0].attentions[1].num_heads
+        self.L = len(head.transformer.decoder.layers)
+        self.Lq = head.num_query
+        self.D = head.depth_num
+        self.lid = bool(head.LID)
+        self.depth_start = float(head.depth_start)
+        self.position_range = [float(v) for v in head.position_range]
+        self.pc_range = [float(v) for v in head.pc_range]
+        self.num_reg_fcs = head.num_reg_fcs
+        self.code_size = head.code_size
+        self.cls_out = head.cls_out_channels
+        self.with_position = head.with_position
+        self.with_multiview = head.with_multiview
+        self.with_fpe = getattr(head, "with_fpe", False)
+        self.with_time = getattr(head, "with_time", False)
+        self.with_multi = getattr(head, "with_multi", False)
+        self.shared_branches = head.cls_branches[0] is head.cls_branches[-1]
+        pe = head.positional_encoding
+        self.sine = dict(num_feats=pe.num_feats, temperature=pe.temperature, normalize=pe.normalize,
+                         scale=pe.scale, eps=pe.eps, offset=pe.offset)
+        if self.lid:
+            self.bin_size = (self.position_range[3] - self.depth_start) / (self.D * (1 + self.D))
+        else:
+            self.bin_size = (self.position_range[3] - self.depth_start) / self.D
+
+
+class HeadEngine:
+    def __init__(self, head):
+        self.spec = HeadSpec(head)
+        self._head = head
+        self._packed: Dict[torch.device, dict] = {}
+
+    # -------------------------------------------------------------------------------------
+    def invalidate(self):
+        self._packed.clear()
+
+    def packed(self, device) -> dict:
+        device = torch.device(device)
+        if device not in self._packed:
+            self._packed[device] = self._pack(device)
+        return self._packed[device]
+
+    def _pack(self, device) -> dict:
+        s = self.spec
+        sd = {k: v.detach().to(device=device, dtype=torch.float32).contiguous()
+              for k, v in self._head.state_dict().items()}
+        E = s.E
+        P = dict(sd=sd)
+        P["in_w"] = sd["input_proj.weight"].reshape(E, -1).contiguous()
+        P["in_b"] = sd["input_proj.bias"]
+        if s.with_position:
+            P["pe_w1"] = sd["position_encoder.0.weight"].reshape(4 * E, -1).contiguous()
+            P["pe_b1"] = sd["position_encoder.0.bias"]
+            P["pe_w2"] = sd["position_encoder.2.weight"].reshape(E, -1).contiguous()
+            P["pe_b2"] = sd["position_encoder.2.bias"]
+        P["ad_w1"] = sd["adapt_pos3d.0.weight"].flatten(1).contiguous()
+        P["ad_b1"] = sd["adapt_pos3d.0.bias"]
+        P["ad_w2"] = sd["adapt_pos3d.2.weight"].flatten(1).contiguous()
+        P["ad_b2"] = sd["adapt_pos3d.2.bias"]
+        if s.with_fpe:
+            P["fpe_wr"] = sd["fpe.conv_reduce.weight"].flatten(1).contiguous()
+            P["fpe_br"] = sd["fpe.conv_reduce.bias"]
+            P["fpe_we"] = sd["fpe.conv_expand.weight"].flatten(1).contiguous()
+            P["fpe_be"] = sd["fpe.conv_expand.bias"]
+        layers = []
+        for l in range(s.L):
+            p = f"transformer.decoder.layers.{l}."
+            layers.append(dict(
+                sa_in_w=sd[p + "attentions.0.attn.in_proj_weight"], sa_in_b=sd[p + "attentions.0.attn.in_proj_bias"],
+                sa_out_w=sd[p + "attentions.0.attn.out_proj.weight"], sa_out_b=sd[p + "attentions.0.attn.out_proj.bias"],
+                ca_in_w=sd[p + "attentions.1.attn.in_proj_weight"], ca_in_b=sd[p + "attentions.1.attn.in_proj_bias"],
+                ca_out_w=sd[p + "attentions.1.attn.out_proj.weight"], ca_out_b=sd[p + "attentions.1.attn.out_proj.bias"],
+                f1_w=sd[p + "ffns.0.layers.0.0.weight"], f1_b=sd[p + "ffns.0.layers.0.0.bias"],
+                f2_w=sd[p + "ffns.0.layers.1.weight"], f2_b=sd[p + "ffns.0.layers.1.bias"],
+                ln=[(sd[p + f"norms.{i}.weight"], sd[p + f"norms.{i}.bias"]) for i in range(3)]))
+        P["layers"] = layers
+        P["post_norm"] = (sd["transformer.decoder.post_norm.weight"], sd["transformer.decoder.post_norm.bias"])
+        P["ref"] = sd["reference_points.weight"]
+        P["dim_t_sine"] = sine_dim_t(s.sine["num_feats"], s.sine["temperature"]).to(device)
+        P["dim_t_query"] = sine_dim_t(128, 10000).to(device)
+        if s.with_multi:
+            for l in range(s.L):
+                p = f"reg_branches.{l}."
+                P[f"task_w0_{l}"] = torch.cat([sd[p + f"task_heads.{t}.0.weight"] for t in range(5)], 0).contiguous()
+                P[f"task_b0_{l}"] = torch.cat([sd[p + f"task_heads.{t}.0.bias"] for t in range(5)], 0).contiguous()
+        return P
+
+    # -------------------------------------------------------------------------------------
+    # pieces
+    # -------------------------------------------------------------------------------------
+    def masks(self, img_metas, B, N, H, W, device) -> torch.Tensor:
+        pad_h, pad_w = img_metas[0]["pad_shape"][0][:2]
+        img_hw = _h2d(img_hw_from_metas(img_metas, N), device)
+        return ops.key_padding_mask(img_hw, pad_h, pad_w, H, W)
+
+    def frustum(self, img_metas, B, N, H, W, device, masks=None, dtype=torch.float32,
+                want_mask=True, want_coords=False):
+        s = self.spec
+        pad_h, pad_w = img_metas[0]["pad_shape"][0][:2]
+        i2l = _h2d(img2lidar_from_metas(img_metas), device)
+        assert i2l.shape[:2] == (B, N), f"lidar2img has {i2l.shape[:2]}, features have {(B, N)}"
+        return ops.frustum_features(i2l, masks, H, W, s.D, pad_h, pad_w, s.lid, s.depth_start,
+                                    s.bin_size, s.position_range, dtype, want_mask, want_coords)
+
+    def position_embedding_tokens(self, P, img_metas, B, N, H, W, device, masks):
+        """fp32 path of position_embeding (petr_head.py:286-334): (T,256) tokens + coords_mask."""
+        feat, cmask, _ = self.frustum(img_metas, B, N, H, W, device, masks)
+        h = ops.gemm_f32(feat, P["pe_w1"], P["pe_b1"], act=ACT_RELU)
+        pos = ops.gemm_f32(h, P["pe_w2"], P["pe_b2"])
+        return pos, cmask
+
+    def query_embeds(self, P) -> torch.Tensor:
+        sd = P["sd"]
+        qe = ops.pos2posemb3d(P["ref"], P["dim_t_query"])
+        h = ops.gemm_f32(qe, sd["query_embedding.0.weight"], sd["query_embedding.0.bias"], act=ACT_RELU)
+        return ops.gemm_f32(h, sd["query_embedding.2.weight"], sd["query_embedding.2.bias"])
+
+    # one decoder layer, fp32 path ---------------------------------------------------------
+    def _self_attn(self, X, qpos, lw, B):
+        s = self.spec
+        E = s.E
+        qk = ops.gemm_f32(X, lw["sa_in_w"][:2 * E], lw["sa_in_b"][:2 * E], A2=qpos)
+        v = ops.gemm_f32(X, lw["sa_in_w"][2 * E:], lw["sa_in_b"][2 * E:])
+        o = ops.attention_f32(qk[:, :E], qk[:, E:], v, None, B, s.Lq, s.Lq, s.heads)
+        y = ops.gemm_f32(o, lw["sa_out_w"], lw["sa_out_b"], residual=X)
+        return ops.layernorm(y, *lw["ln"][0], out=y)
+
+    def _cross_attn_f32(self, X, qpos, mem, pos, kmask, lw, B, Lk):
+        s = self.spec
+        E = s.E
+        q = ops.gemm_f32(X, lw["ca_in_w"][:E], lw["ca_in_b"][:E], A2=qpos)
+        k = ops.gemm_f32(mem, lw["ca_in_w"][E:2 * E], lw["ca_in_b"][E:2 * E], A2=pos)
+        v = ops.gemm_f32(mem, lw["ca_in_w"][2 * E:], lw["ca_in_b"][2 * E:])
+        o = ops.attention_f32(q, k, v, kmask, B, s.Lq, Lk, s.heads)
+        y = ops.gemm_f32(o, lw["ca_out_w"], lw["ca_out_b"], residual=X)
+        return ops.layernorm(y, *lw["ln"][1], out=y)
+
+    def _ffn(self, X, lw):
+        h = ops.gemm_f32(X, lw["f1_w"], lw["f1_b"], act=ACT_RELU)
+        y = ops.gemm_f32(h, lw["f2_w"], lw["f2_b"], residual=X)
+        return ops.layernorm(y, *lw["ln"][2], out=y)
+
+    # branches -----------------------------------------------------------------------------
+    def _cls_branch(self, sd, p, x):
+        s = self.spec
+        for i in range(s.num_reg_fcs):
+            x = ops.gemm_f32(x, sd[f"{p}{3 * i}.weight"], sd[f"{p}{3 * i}.bias"])
+            x = ops.layernorm(x, sd[f"{p}{3 * i + 1}.weight"], sd[f"{p}{3 * i + 1}.bias"], relu=True, out=x)
+        j = 3 * s.num_reg_fcs
+        return ops.gemm_f32(x, sd[f"{p}{j}.weight"], sd[f"{p}{j}.bias"])
+
+    def _reg_branch(self, P, l, p, x):
+        s = self.spec
+        sd = P["sd"]
+        if s.with_multi:
+            for i in range(s.num_reg_fcs):
+                x = ops.gemm_f32(x, sd[f"{p}reg_branch.{3 * i}.weight"], sd[f"{p}reg_branch.{3 * i}.bias"], act=ACT_RELU)
+            h = ops.gemm_f32(x, P[f"task_w0_{l}"], P[f"task_b0_{l}"], act=ACT_RELU)      # (rows, 5E)
+            out = torch.empty((x.shape[0], s.code_size), dtype=torch.float32, device=x.device)
+            c0 = 0
+            for t in range(5):
+                w = sd[f"{p}task_heads.{t}.2.weight"]
+                ops.gemm_f32(h[:, t * s.E:(t + 1) * s.E], w, sd[f"{p}task_heads.{t}.2.bias"],
+                             out=out[:, c0:c0 + w.shape[0]])
+                c0 += w.shape[0]
+            return out
+        for i in range(s.num_reg_fcs):
+            x = ops.gemm_f32(x, sd[f"{p}{2 * i}.weight"], sd[f"{p}{2 * i}.bias"], act=ACT_RELU)
+        j = 2 * s.num_reg_fcs
+        return ops.gemm_f32(x, sd[f"{p}{j}.weight"], sd[f"{p}{j}.bias"])
+
+    def branches(self, P, outs_dec: torch.Tensor, B: int, time_div=None):
+        """outs_dec (L, B*Lq, E) -> all_cls_scores (L,B,Lq,C), all_bbox_preds (L,B,Lq,code)."""
+        s = self.spec
+        sd = P["sd"]
+        L = outs_dec.shape[0]
+        if s.shared_branches:
+            flat = outs_dec.reshape(L * B * s.Lq, s.E)
+            cls = self._cls_branch(sd, "cls_branches.0.", flat)
+            reg = self._reg_branch(P, 0, "reg_branches.0.", flat)
+        else:
+            cls = torch.empty((L * B * s.Lq, s.cls_out), dtype=torch.float32, device=outs_dec.device)
+            reg = torch.empty((L * B * s.Lq, s.code_size), dtype=torch.float32, device=outs_dec.device)
+            n = B * s.Lq
+            for l in range(L):
+                cls[l * n:(l + 1) * n] = self._cls_branch(sd, f"cls_branches.{l}.", outs_dec[l])
+                reg[l * n:(l + 1) * n] = self._reg_branch(P, l, f"reg_branches.{l}.", outs_dec[l])
+        ops.decode_boxes(reg, P["ref"], s.pc_range, time_div, L, B, s.Lq)
+        return cls.view(L, B, s.Lq, s.cls_out), reg.view(L, B, s.Lq, s.code_size)
+
+    # -------------------------------------------------------------------------------------
+    # whole head
+    # -------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, img_metas: List[dict], precision: str = "bf16",
+                taps: Optional[dict] = None) -> dict:
+        if not x.is_cuda:
+            raise RuntimeError("petr_b200: features must be CUDA tensors (no CPU fallback)")
+        if precision == "bf16":
+            from .engine_tc import forward_tc
+            return forward_tc(self, x, img_metas, taps)
+        if precision != "fp32":
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        s = self.spec
+        if not s.with_multiview:
+            raise NotImplementedError("petr_b200 implements with_multiview=True (all shipped configs)")
+        x = x.float().contiguous()
+        B, N, Cin, H, W = x.shape
+        dev = x.device
+        Lk = N * H * W
+        P = self.packed(dev)
+        masks = self.masks(img_metas, B, N, H, W, dev)
+        mem = ops.gemm_f32(x, P["in_w"], P["in_b"], nchw_hw=H * W)                  # (T,E)
+        sf = ops.sine3d_features(masks, P["dim_t_sine"], **_sine_args(s))
+        h2 = ops.gemm_f32(sf, P["ad_w1"], P["ad_b1"], act=ACT_RELU)
+        if s.with_position:
+            pos, _ = self.position_embedding_tokens(P, img_metas, B, N, H, W, dev, masks)
+            if taps is not None:
+                taps["coords_position_embeding"] = pos.clone()
+            if s.with_fpe:
+                se = ops.gemm_f32(mem, P["fpe_wr"], P["fpe_br"], act=ACT_RELU)
+                pos = ops.gemm_f32(se, P["fpe_we"], P["fpe_be"], act=ACT_SIGMOID_GATE, gate=pos)
+            pos = ops.gemm_f32(h2, P["ad_w2"], P["ad_b2"], residual=pos)
+        else:
+            pos = ops.gemm_f32(h2, P["ad_w2"], P["ad_b2"])
+        qpos = self.query_embeds(P)
+        kmask = masks.view(B, Lk)
+        X = torch.zeros((B * s.Lq, s.E), dtype=torch.float32, device=dev)
+        outs = torch.empty((s.L, B * s.Lq, s.E), dtype=torch.float32, device=dev)
+        if taps is not None:
+            taps.update(masks=masks, memory=mem, pos_embed=pos, query_embeds=qpos, layers=[])
+        for l, lw in enumerate(P["layers"]):
+            X = self._self_attn(X, qpos, lw, B)
+            X = self._cross_attn_f32(X, qpos, mem, pos, kmask, lw, B, Lk)
+            X = self._ffn(X, lw)
+            ops.layernorm(X, *P["post_norm"], nan_to_num=True, out=outs[l])
+            if taps is not None:
+                taps["layers"].append(X.clone())
+        time_div = None
+        if s.with_time:
+            time_div = _h2d(mean_time_stamp(img_metas), dev)
+        cls, box = self.branches(P, outs, B, time_div)
+        if taps is not None:
+            taps["outs_dec"] = outs.view(s.L, B, s.Lq, s.E)
+        return dict(all_cls_scores=cls, all_bbox_preds=box, enc_cls_scores=None, enc_bbox_preds=None)
+
+
+def _sine_args(s: HeadSpec) -> dict:
+    a = s.sine
+    return dict(num_feats=a["num_feats"], normalize=a["normalize"], scale=a["scale"],
+                eps=a["eps"], offset=a["offset"])

@@ -1,0 +1,250 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/petr_b200.h).
+
+PyTorch is used for device memory and streams only; every computation is a kernel of
+libpetr_b200.so launched on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, host_floats, ptr, stream_ptr
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_SIGMOID_GATE = 0, 1, 2
+A_ROWMAJOR, A_NCHW = 0, 1
+
+
+def _cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"petr_b200: {name} must be a CUDA tensor (no CPU fallback)")
+
+
+def _dt(dtype):
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError(f"petr_b200: unsupported dtype {dtype}")
+
+
+def key_padding_mask(img_hw: torch.Tensor, pad_h: int, pad_w: int, H: int, W: int) -> torch.Tensor:
+    """img_hw int32 (B,N,2) on device -> uint8 (B,N,H,W); petr_head.py:383-394."""
+    _cuda(img_hw, "img_hw")
+    B, N, _ = img_hw.shape
+    out = torch.empty((B, N, H, W), dtype=torch.uint8, device=img_hw.device)
+    call("petr_key_padding_mask", ptr(img_hw), B, N, int(pad_h), int(pad_w), H, W, ptr(out),
+         stream_ptr(img_hw.device))
+    return out
+
+
+def frustum_features(img2lidar: torch.Tensor, masks: Optional[torch.Tensor], H: int, W: int, D: int,
+                     pad_h: int, pad_w: int, lid: bool, depth_start: float, bin_size: float,
+                     position_range, dtype=torch.float32, want_mask=True, want_coords=False):
+    """petr_head.py:286-331.  Returns (feat (T,3D), coords_mask uint8 (B,N,H,W) | None,
+    coords3d (B,N,H,W,D,3) | None)."""
+    _cuda(img2lidar, "img2lidar")
+    B, N = img2lidar.shape[:2]
+    dev = img2lidar.device
+    T = B * N * H * W
+    feat = torch.empty((T, 3 * D), dtype=dtype, device=dev)
+    cmask = torch.empty((B, N, H, W), dtype=torch.uint8, device=dev) if want_mask else None
+    c3 = torch.empty((B, N, H, W, D, 3), dtype=torch.float32, device=dev) if want_coords else None
+    pr = [float(v) for v in position_range]
+    lo = host_floats(pr[:3])
+    span = host_floats([pr[3] - pr[0], pr[4] - pr[1], pr[5] - pr[2]])
+    call("petr_frustum_features", ptr(img2lidar), ptr(masks), B, N, H, W, D, int(pad_h), int(pad_w),
+         int(bool(lid)), float(depth_start), float(bin_size), lo, span, ptr(feat), _dt(dtype),
+         ptr(cmask), ptr(c3), stream_ptr(dev))
+    return feat, cmask, c3
+
+
+def sine3d_features(mask: torch.Tensor, dim_t: torch.Tensor, num_feats: int, normalize: bool,
+                    scale: float, eps: float, offset: float, dtype=torch.float32) -> torch.Tensor:
+    """positional_encoding.py:58-100.  mask uint8 (B,N,H,W) -> (T, 3*num_feats)."""
+    _cuda(mask, "mask")
+    B, N, H, W = mask.shape
+    out = torch.empty((B * N * H * W, 3 * num_feats), dtype=dtype, device=mask.device)
+    call("petr_sine3d_features", ptr(mask), ptr(dim_t), B, N, H, W, num_feats, int(bool(normalize)),
+         float(scale), float(eps), float(offset), ptr(out), _dt(dtype), stream_ptr(mask.device))
+    return out
+
+
+def pos2posemb3d(ref: torch.Tensor, dim_t: torch.Tensor) -> torch.Tensor:
+    """petr_head.py:31-43.  ref (Q,3) fp32 -> (Q, 3*F)."""
+    _cuda(ref, "ref")
+    Q, Fn = ref.shape[0], dim_t.numel()
+    out = torch.empty((Q, 3 * Fn), dtype=torch.float32, device=ref.device)
+    call("petr_pos2posemb3d", ptr(ref), ptr(dim_t), Q, Fn, ptr(out), stream_ptr(ref.device))
+    return out
+
+
+def gemm_f32(A: torch.Tensor, W: torch.Tensor, bias=None, *, A2=None, residual=None, gate=None,
+             act=ACT_NONE, out=None, out_bf16=None, nchw_hw: int = 0, M: Optional[int] = None,
+             want_f32: bool = True) -> torch.Tensor:
+    """C = epi((A + A2[m % rows]) @ W.T + bias) + residual, fp32 accumulate.
+
+    A: (M,K) with unit inner stride, or (when nchw_hw > 0) a contiguous (G,K,h,w) map read as
+    M = G*h*w rows.  W: (N,K) contiguous."""
+    _cuda(A, "A")
+    N, K = W.shape[0], W[0].numel()
+    assert W.is_contiguous()
+    if nchw_hw > 0:
+        assert A.is_contiguous()
+        M = A.numel() // K
+        lda, layout = K, A_NCHW
+    else:
+        assert A.dim() == 2 and A.stride(1) == 1 and A.shape[1] == K
+        M = A.shape[0] if M is None else M
+        lda, layout = A.stride(0), A_ROWMAJOR
+    a2_rows = 0
+    if A2 is not None:
+        assert A2.dim() == 2 and A2.stride(1) == 1 and A2.stride(0) == lda and A2.shape[1] == K
+        a2_rows = A2.shape[0]
+    if out is None and want_f32:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    ref_t = out if out is not None else out_bf16
+    assert ref_t.stride(-1) == 1
+    ldc = ref_t.stride(0)
+    for t in (residual, gate, out_bf16):
+        if t is not None:
+            assert t.stride(0) == ldc and t.stride(1) == 1
+    call("petr_gemm_f32", ptr(A), lda, layout, int(nchw_hw), ptr(A2), a2_rows, ptr(W), ptr(bias),
+         ptr(residual), ptr(gate), act, ptr(out), ptr(out_bf16), ldc, M, N, K, stream_ptr(A.device))
+    return out if out is not None else out_bf16
+
+
+def attention_f32(Q, K, V, key_mask, B: int, Lq: int, Lk: int, heads: int, out=None) -> torch.Tensor:
+    """softmax(Q K^T / sqrt(d) + mask) V; Q rows b*Lq+q, K/V rows b*Lk+k, head_dim 32."""
+    _cuda(Q, "Q")
+    d = 32
+    E = heads * d
+    if out is None:
+        out = torch.empty((B * Lq, E), dtype=torch.float32, device=Q.device)
+    call("petr_attention_f32", ptr(Q), Q.stride(0), ptr(K), K.stride(0), ptr(V), V.stride(0),
+         ptr(key_mask), ptr(out), out.stride(0), B, Lq, Lk, heads, d, 1.0 / math.sqrt(d),
+         stream_ptr(Q.device))
+    return out
+
+
+def layernorm(X, gamma, beta, eps=1e-5, relu=False, nan_to_num=False, out=None) -> torch.Tensor:
+    _cuda(X, "X")
+    assert X.is_contiguous()
+    E = X.shape[-1]
+    rows = X.numel() // E
+    if out is None:
+        out = torch.empty_like(X)
+    call("petr_layernorm_f32", ptr(X), ptr(gamma), ptr(beta), ptr(out), rows, E, float(eps),
+         int(relu), int(nan_to_num), stream_ptr(X.device))
+    return out
+
+
+def decode_boxes(reg: torch.Tensor, ref: torch.Tensor, pc_range, time_div, L: int, B: int, Q: int):
+    """In place on reg (L*B*Q, code_size); petr_head.py:440-460."""
+    _cuda(reg, "reg")
+    assert reg.is_contiguous()
+    call("petr_decode_boxes", ptr(reg), ptr(ref), host_floats(list(pc_range)), ptr(time_div),
+         L, B, Q, reg.shape[-1], stream_ptr(reg.device))
+    return reg
+
+
+def launch_count() -> int:
+    return _lib.launch_count()
+
+
+def reset_launch_count():
+    _lib.reset_launch_count()
+
+
+# ---- tcgen05 tier ---------------------------------------------------------------------------
+OUT_F32, OUT_BF16, OUT_HEADSPLIT = 0, 1, 2
+
+
+def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, act=ACT_NONE,
+                 out=None, out_dtype=torch.float32, headsplit_Lk: int = 0) -> torch.Tensor:
+    """C = epi(A @ W.T + bias) (+ residual) on tcgen05; A (M,K) bf16, W (N,K) bf16, K % 64 == 0.
+    headsplit_Lk > 0: bf16 output in the [N/256][B][8][Lk][32] K/V layout."""
+    _cuda(A, "A")
+    assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
+    assert A.dim() == 2 and A.stride(1) == 1 and W.dim() == 2 and W.stride(1) == 1
+    M, K = A.shape
+    N = W.shape[0]
+    if headsplit_Lk > 0:
+        B = M // headsplit_Lk
+        if out is None:
+            out = torch.empty((N // 256, B, 8, headsplit_Lk, 32), dtype=torch.bfloat16, device=A.device)
+        mode, ldc = OUT_HEADSPLIT, 0
+    else:
+        if out is None:
+            out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+        mode = OUT_F32 if out.dtype == torch.float32 else OUT_BF16
+        ldc = out.stride(0)
+        if residual is not None:
+            assert residual.dtype == torch.float32 and residual.stride(0) == ldc
+    call("petr_gemm_bf16_tc", ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), ptr(residual), act,
+         ptr(out), ldc, mode, M, N, K, int(headsplit_Lk), stream_ptr(A.device))
+    return out
+
+
+def pack_q_bf16(Q: torch.Tensor, B: int, Lq: int, heads: int, out=None) -> torch.Tensor:
+    """fp32 (B*Lq, heads*32) -> bf16 (B, heads, Lq, 32) scaled by 32^-1/2 * log2(e)."""
+    _cuda(Q, "Q")
+    if out is None:
+        out = torch.empty((B, heads, Lq, 32), dtype=torch.bfloat16, device=Q.device)
+    scale = (1.0 / math.sqrt(32.0)) * 1.4426950408889634
+    call("petr_pack_q_bf16", ptr(Q), Q.stride(0), ptr(out), B, Lq, heads, scale, stream_ptr(Q.device))
+    return out
+
+
+def attention_partial_floats(B: int, Lq: int, heads: int) -> int:
+    return int(_lib.lib().petr_attention_partial_floats(B, Lq, heads))
+
+
+# Optional live kernel timing (bench.py roofline): name -> list of (start, end) CUDA events
+# recorded on the launching stream around the named launches.
+KERNEL_TIMERS = None
+
+
+class _Timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if KERNEL_TIMERS is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+
+    def __exit__(self, *a):
+        if KERNEL_TIMERS is not None:
+            self.ev[1].record()
+            KERNEL_TIMERS.setdefault(self.name, []).append(self.ev)
+
+
+def cross_attention_bf16(Qs, Kh, Vh, key_mask, B: int, Lq: int, Lk: int, heads: int, nsplit: int = 1,
+                         out=None, partial=None, write_partial: bool = False):
+    """Flash cross-attention on tcgen05.  Returns O fp32 (B*Lq, heads*32), or the partial
+    buffer when write_partial."""
+    _cuda(Qs, "Qs")
+    nsplit = max(1, min(int(nsplit), (Lk + 127) // 128))
+    if (nsplit > 1 or write_partial) and partial is None:
+        partial = torch.empty((nsplit * attention_partial_floats(B, Lq, heads),), dtype=torch.float32,
+                              device=Qs.device)
+    if not write_partial and out is None:
+        out = torch.empty((B * Lq, heads * 32), dtype=torch.float32, device=Qs.device)
+    with _Timed("cross_attention_bf16"):
+        call("petr_cross_attention_bf16", ptr(Qs), ptr(Kh), ptr(Vh), ptr(key_mask), ptr(out),
+             out.stride(0) if out is not None else 0, ptr(partial), B, Lq, Lk, heads, nsplit,
+             int(write_partial), stream_ptr(Qs.device))
+    return partial if write_partial else out
+
+
+def attention_merge(partial: torch.Tensor, nparts: int, B: int, Lq: int, heads: int, out=None):
+    _cuda(partial, "partial")
+    if out is None:
+        out = torch.empty((B * Lq, heads * 32), dtype=torch.float32, device=partial.device)
+    call("petr_attention_merge", ptr(partial), nparts, ptr(out), out.stride(0), B, Lq, heads,
+         stream_ptr(partial.device))
+    return out

@@ -73,3 +73,45 @@ def sharpen_state_dict(sd: dict, qk_scale: float = 8.0) -> dict:
             E = out[k].shape[1]
             out[k][:2 * E] *= qk_scale
     return out
+
+
+def random_state_dict(shapes: dict, seed: int = 0) -> dict:
+    """Deterministic random weights for a head, generated key by key in sorted order from a
+    seeded CPU generator (so the build container and the GPU box produce identical weights
+    without shipping a 44 MB checkpoint).  Scales follow the reference's init_weights()
+    (xavier-uniform matrices, reference_points ~ U(0,1), petr_head.py:276-284) but with non-zero
+    biases and non-unit LayerNorm gains so every parameter matters in parity tests."""
+    g = torch.Generator(device='cpu').manual_seed(3000 + seed)
+    out = {}
+    for k in sorted(shapes):
+        if k.startswith('_'):
+            continue
+        shp = tuple(shapes[k])
+        if k == 'code_weights':
+            out[k] = torch.ones(shp)
+        elif k == 'reference_points.weight':
+            out[k] = torch.rand(shp, generator=g)
+        elif len(shp) >= 2:
+            fan_out, fan_in = shp[0], int(np.prod(shp[1:]))
+            a = math.sqrt(6.0 / (fan_in + fan_out))
+            out[k] = (torch.rand(shp, generator=g) * 2 - 1) * a
+        elif 'norm' in k and k.endswith('weight') or (k.split('.')[-2] in ('1', '4') and
+                                                      k.startswith('cls_branches') and k.endswith('weight')):
+            out[k] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        else:
+            out[k] = 0.05 * torch.randn(shp, generator=g)
+    # aliased (shared) branches of PETRHead must stay identical across the six copies
+    for k in list(out):
+        for br in ('cls_branches.', 'reg_branches.'):
+            if k.startswith(br) and shapes.get('_shared_branches', False):
+                rest = k.split('.', 2)[2]
+                out[k] = out[f'{br}0.{rest}']
+    return out
+
+
+def head_state_dict(head, seed: int = 0) -> dict:
+    """random_state_dict for a built head module (reference or petr_b200)."""
+    shapes = {k: tuple(v.shape) for k, v in head.state_dict().items()}
+    shared = head.cls_branches[0] is head.cls_branches[-1]
+    sd = random_state_dict(dict(shapes, _shared_branches=shared) if shared else shapes, seed)
+    return sd

@@ -1,0 +1,272 @@
+"""GPU parity tests of every C-ABI kernel against the CPU oracle / a plain fp32 evaluation.
+Integer-class results (masks, frustum grid/depth/transform, coords_mask) must be bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import petr_oracle as po
+from petr_b200 import engine, ops, synth
+from petr_b200.configs import WORKLOADS
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _metas_rand_shapes(wl, B, seed, pad):
+    rng = np.random.RandomState(seed)
+    metas = synth.make_img_metas(wl, B, seed, pad_shape=pad)
+    for m in metas:
+        m["img_shape"] = [(int(rng.randint(1, pad[0] + 1)), int(rng.randint(1, pad[1] + 1)), 3)
+                          for _ in range(wl.num_cams)]
+    return metas
+
+
+@pytest.mark.parametrize("H,W,pad", [(4, 10, (64, 160)), (58, 100, (928, 1600)), (20, 50, (320, 800)),
+                                     (16, 44, (512, 1408)), (7, 13, (100, 333)), (40, 100, (640, 1600))])
+def test_key_padding_mask_bit_exact(H, W, pad):
+    wl = WORKLOADS["tiny"]
+    metas = _metas_rand_shapes(wl, 3, 5, pad)
+    metas[0]["img_shape"] = [(pad[0], pad[1], 3)] * wl.num_cams
+    metas[1]["img_shape"][0] = (0, 0, 3)
+    ref = po.key_padding_masks(metas, 3, wl.num_cams, H, W)
+    img_hw = torch.from_numpy(engine.img_hw_from_metas(metas, wl.num_cams)).to(DEV)
+    got = ops.key_padding_mask(img_hw, pad[0], pad[1], H, W)
+    assert torch.equal(got.cpu().bool(), ref)
+    from petr_b200.engine_tc import any_key_masked
+    assert any_key_masked(metas, wl.num_cams, H, W) == bool(ref.any())
+    full = synth.make_img_metas(wl, 2, 0, img_shape=pad, pad_shape=pad)
+    assert any_key_masked(full, wl.num_cams, H, W) is False
+
+
+@pytest.mark.parametrize("wn,B,pr", [("tiny", 2, None), ("vov-p4-800x320", 1, None),
+                                     ("tiny", 2, (-20.0, -20.0, -2.0, 20.0, 20.0, 2.0)),
+                                     ("r50-c5-1408x512", 1, None)])
+def test_frustum_bit_exact(wn, B, pr):
+    wl = WORKLOADS[wn]
+    pr = pr or (-61.2, -61.2, -10.0, 61.2, 61.2, 10.0)
+    metas = synth.make_img_metas(wl, B, 7)
+    N, H, W, D = wl.num_cams, wl.feat_h, wl.feat_w, 64
+    masks = torch.zeros(B, N, H, W, dtype=torch.bool)
+    masks[0, 0, 0, :3] = True
+    feat_ref, cmask_ref, c3_ref = po.position_features(metas, B, N, H, W, masks, 64, 1.0, pr, True)
+    i2l = torch.from_numpy(engine.img2lidar_from_metas(metas)).to(DEV)
+    assert torch.equal(i2l.cpu(), po.img2lidar_matrices(metas))
+    bin_size = (pr[3] - 1.0) / (64 * 65)
+    feat, cmask, c3 = ops.frustum_features(i2l, masks.to(DEV).to(torch.uint8), H, W, D, wl.img_h, wl.img_w,
+                                           True, 1.0, bin_size, pr, want_mask=True, want_coords=True)
+    c3_ref = c3_ref.permute(0, 1, 3, 2, 4, 5).contiguous()            # (B,N,W,H,D,3) -> (B,N,H,W,D,3)
+    assert torch.equal(c3.cpu(), c3_ref), "frustum transform / normalisation must be bit-exact"
+    assert torch.equal(cmask.cpu().bool(), cmask_ref)
+    fr = feat_ref.view(B * N, 3 * D, H * W).permute(0, 2, 1).reshape(-1, 3 * D)
+    assert (feat.cpu() - fr).abs().max() <= 4e-6                      # logf vs torch.log: <= 2 ulp at 11.5
+    featb, _, _ = ops.frustum_features(i2l, None, H, W, D, wl.img_h, wl.img_w, True, 1.0, bin_size, pr,
+                                       dtype=torch.bfloat16, want_mask=False)
+    assert (featb.float().cpu() - fr).abs().max() <= 0.05
+
+
+def test_frustum_no_lid():
+    wl = WORKLOADS["tiny"]
+    metas = synth.make_img_metas(wl, 1, 3)
+    pr = (-61.2, -61.2, -10.0, 61.2, 61.2, 10.0)
+    _, cm_ref, c3_ref = po.position_features(metas, 1, 2, 4, 10, None, 16, 1.0, pr, False)
+    i2l = torch.from_numpy(engine.img2lidar_from_metas(metas)).to(DEV)
+    _, cm, c3 = ops.frustum_features(i2l, None, 4, 10, 16, 64, 160, False, 1.0, (pr[3] - 1.0) / 16, pr,
+                                     want_mask=True, want_coords=True)
+    assert torch.equal(c3.cpu(), c3_ref.permute(0, 1, 3, 2, 4, 5).contiguous())
+    assert torch.equal(cm.cpu().bool(), cm_ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 4, 10), (1, 6, 20, 50), (1, 12, 5, 7)])
+@pytest.mark.parametrize("normalize", [True, False])
+def test_sine3d_features(shape, normalize):
+    g = torch.Generator().manual_seed(1)
+    mask = torch.rand(shape, generator=g) < 0.2
+    mask[0, 0] = False
+    ref = po.sine_positional_encoding_3d(mask, 128, normalize=normalize)
+    B, N, H, W = shape
+    ref = ref.permute(0, 1, 3, 4, 2).reshape(-1, 384)
+    dim_t = engine.sine_dim_t(128, 10000).to(DEV)
+    got = ops.sine3d_features(mask.to(DEV).to(torch.uint8), dim_t, 128, normalize, 2 * math.pi, 1e-6, 0.0)
+    assert (got.cpu() - ref).abs().max() <= (2e-6 if normalize else 2e-4)
+
+
+def test_pos2posemb3d():
+    ref_pts = torch.rand(900, 3, generator=torch.Generator().manual_seed(0))
+    ref = po.pos2posemb3d(ref_pts)
+    got = ops.pos2posemb3d(ref_pts.to(DEV), engine.sine_dim_t(128, 10000).to(DEV))
+    assert (got.cpu() - ref).abs().max() <= 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(900, 256, 256), (128, 64, 16), (1000, 10, 256), (333, 1024, 192),
+                                   (4224, 256, 2048), (77, 130, 100)])
+def test_gemm_f32(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    A2 = torch.randn(7, K, generator=g).to(DEV)
+    ref = (A.double() @ W.double().T + b.double()).float()
+    assert (ops.gemm_f32(A, W, b) - ref).abs().max() <= 2e-5
+    ref2 = torch.relu(((A + A2[torch.arange(M, device=DEV) % 7]).double() @ W.double().T + b.double())).float() + res
+    out_b = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    got2 = ops.gemm_f32(A, W, b, A2=A2, residual=res, act=ops.ACT_RELU, out_bf16=out_b)
+    assert (got2 - ref2).abs().max() <= 3e-5
+    assert (out_b.float() - ref2).abs().max() <= 0.05
+    gate = torch.randn(M, N, generator=g).to(DEV)
+    ref3 = gate * torch.sigmoid(ref)
+    assert (ops.gemm_f32(A, W, b, gate=gate, act=ops.ACT_SIGMOID_GATE) - ref3).abs().max() <= 2e-5
+    # strided views (packed in-proj slices) and strided output columns
+    big = torch.zeros(M, N + 6, device=DEV)
+    ops.gemm_f32(A, W, b, out=big[:, 3:3 + N])
+    assert (big[:, 3:3 + N] - ref).abs().max() <= 2e-5 and big[:, :3].abs().max() == 0
+
+
+def test_gemm_f32_nchw():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 64, 4, 10, generator=g).to(DEV)
+    w = torch.randn(256, 64, 1, 1, generator=g).to(DEV) * 0.1
+    b = torch.randn(256, generator=g).to(DEV)
+    ref = torch.nn.functional.conv2d(x.cpu(), w.cpu(), b.cpu()).permute(0, 2, 3, 1).reshape(-1, 256)
+    got = ops.gemm_f32(x, w.reshape(256, 64).contiguous(), b, nchw_hw=40)
+    assert (got.cpu() - ref).abs().max() <= 2e-5
+
+
+def _attn_ref(Q, K, V, mask, B, Lq, Lk, heads):
+    q = Q.double().view(B, Lq, heads, 32).transpose(1, 2)
+    k = K.double().view(B, Lk, heads, 32).transpose(1, 2)
+    v = V.double().view(B, Lk, heads, 32).transpose(1, 2)
+    s = q @ k.transpose(-1, -2) / math.sqrt(32)
+    if mask is not None:
+        s = s.masked_fill(mask.bool()[:, None, None, :], float("-inf"))
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * Lq, heads * 32).float()
+
+
+@pytest.mark.parametrize("B,Lq,Lk,scale", [(2, 64, 80, 1.0), (1, 900, 900, 1.0), (2, 100, 333, 6.0)])
+def test_attention_f32(B, Lq, Lk, scale):
+    g = torch.Generator().manual_seed(Lk)
+    Q = (torch.randn(B * Lq, 256, generator=g) * scale).to(DEV)
+    K = (torch.randn(B * Lk, 256, generator=g) * scale).to(DEV)
+    V = torch.randn(B * Lk, 256, generator=g).to(DEV)
+    mask = (torch.rand(B, Lk, generator=g) < 0.3).to(DEV).to(torch.uint8)
+    mask[0, :70] = 1
+    for m in (None, mask):
+        got = ops.attention_f32(Q, K, V, m, B, Lq, Lk, 8)
+        assert (got - _attn_ref(Q, K, V, m, B, Lq, Lk, 8)).abs().max() <= 2e-5
+    mask[B - 1] = 1                                               # fully masked sample -> NaN like torch
+    got = ops.attention_f32(Q, K, V, mask, B, Lq, Lk, 8)
+    assert torch.isnan(got[(B - 1) * Lq:]).all()
+
+
+def test_layernorm_and_decode():
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(1000, 256, generator=g).to(DEV) * 3 + 1
+    gm, bt = torch.randn(256, generator=g).to(DEV), torch.randn(256, generator=g).to(DEV)
+    ref = torch.nn.functional.layer_norm(X, (256,), gm, bt, 1e-5)
+    assert (ops.layernorm(X, gm, bt) - ref).abs().max() <= 1e-5
+    assert (ops.layernorm(X, gm, bt, relu=True) - torch.relu(ref)).abs().max() <= 1e-5
+    Xn = X.clone()
+    Xn[5] = float("nan")
+    out = ops.layernorm(Xn, gm, bt, nan_to_num=True)
+    assert out[5].abs().max() == 0 and (out[6] - ref[6]).abs().max() <= 1e-5
+    L, B, Q = 2, 3, 50
+    reg = torch.randn(L * B * Q, 10, generator=g).to(DEV)
+    refp = torch.rand(Q, 3, generator=g).to(DEV)
+    td = torch.tensor([0.5, 0.25, 1.0], device=DEV)
+    pc = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+    exp = reg.clone().view(L, B, Q, 10)
+    r = po.inverse_sigmoid(refp.cpu()).to(DEV)
+    exp[..., 0:2] = (exp[..., 0:2] + r[:, 0:2]).sigmoid()
+    exp[..., 4:5] = (exp[..., 4:5] + r[:, 2:3]).sigmoid()
+    exp[..., 8:] = exp[..., 8:] / td[None, :, None, None]
+    exp[..., 0] = exp[..., 0] * 102.4 - 51.2
+    exp[..., 1] = exp[..., 1] * 102.4 - 51.2
+    exp[..., 4] = exp[..., 4] * 8.0 - 5.0
+    got = ops.decode_boxes(reg.clone(), refp, pc, td, L, B, Q).view(L, B, Q, 10)
+    assert (got - exp).abs().max() <= 2e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 tier
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 256), (1000, 1024, 192), (4224, 256, 1024),
+                                   (333, 1536, 256), (130, 100, 384)])
+def test_gemm_bf16_tc(M, N, K):
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).to(torch.bfloat16)
+    b = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    ref = (A.double() @ W.double().T + b.double()).float()
+    got = ops.gemm_bf16_tc(A, W, b)
+    assert (got - ref).abs().max() <= 2e-4, "tcgen05 GEMM (fp32 out)"
+    got = ops.gemm_bf16_tc(A, W, b, residual=res, act=ops.ACT_RELU)
+    assert (got - (torch.relu(ref) + res)).abs().max() <= 2e-4
+    gb = ops.gemm_bf16_tc(A, W, b, act=ops.ACT_RELU, out_dtype=torch.bfloat16)
+    assert (gb.float() - torch.relu(ref)).abs().max() <= 0.05
+
+
+def test_gemm_bf16_tc_headsplit():
+    B, Lk, K = 2, 200, 256
+    g = torch.Generator().manual_seed(9)
+    A = torch.randn(B * Lk, K, generator=g).to(DEV).to(torch.bfloat16)
+    W = (torch.randn(512, K, generator=g) / 16).to(DEV).to(torch.bfloat16)
+    b = torch.randn(512, generator=g).to(DEV)
+    ref = (A.double() @ W.double().T + b.double()).float()                # (B*Lk, 512)
+    ref = ref.view(B, Lk, 2, 8, 32).permute(2, 0, 3, 1, 4)                # (L,B,heads,Lk,32)
+    got = ops.gemm_bf16_tc(A, W, b, headsplit_Lk=Lk)
+    assert got.shape == (2, B, 8, Lk, 32)
+    assert (got.float() - ref).abs().max() <= 0.05
+
+
+def _flash_inputs(B, Lq, Lk, qscale, seed):
+    g = torch.Generator().manual_seed(seed)
+    q = (torch.randn(B * Lq, 256, generator=g) * qscale).to(DEV)
+    Kh = torch.randn(B, 8, Lk, 32, generator=g).to(DEV).to(torch.bfloat16)
+    Vh = torch.randn(B, 8, Lk, 32, generator=g).to(DEV).to(torch.bfloat16)
+    qs = ops.pack_q_bf16(q, B, Lq, 8)
+    # fp64 evaluation on the bf16-rounded operands (scale already folded into qs, exp2 domain)
+    s = qs.double() @ Kh.double().transpose(-1, -2) * math.log(2.0)
+    return qs, Kh, Vh, s
+
+
+@pytest.mark.parametrize("B,Lq,Lk,qscale,nsplit", [
+    (1, 128, 128, 1.0, 1), (1, 128, 256, 1.0, 1), (2, 900, 1000, 1.0, 1), (1, 900, 6000, 1.0, 1),
+    (1, 900, 6000, 1.0, 3), (2, 64, 333, 8.0, 2), (1, 900, 4224, 12.0, 1), (1, 200, 1500, 1.0, 5)])
+def test_cross_attention_bf16(B, Lq, Lk, qscale, nsplit):
+    qs, Kh, Vh, s = _flash_inputs(B, Lq, Lk, qscale, Lk + nsplit)
+    ref = (torch.softmax(s, -1) @ Vh.double()).transpose(1, 2).reshape(B * Lq, 256).float()
+    got = ops.cross_attention_bf16(qs, Kh, Vh, None, B, Lq, Lk, 8, nsplit)
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), f"flash attention error {err}"
+    assert err <= 1.5e-2, f"flash attention error {err}"
+
+
+def test_cross_attention_bf16_masks_and_merge():
+    B, Lq, Lk = 3, 100, 700
+    qs, Kh, Vh, s = _flash_inputs(B, Lq, Lk, 4.0, 5)
+    g = torch.Generator().manual_seed(1)
+    mask = (torch.rand(B, Lk, generator=g) < 0.4).to(DEV)
+    mask[0, 128:384] = True                      # two fully masked key tiles
+    mask[0, :128] = True                         # ... including the first one
+    mask[2] = True                               # fully masked sample
+    sm = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(sm, -1) @ Vh.double()).transpose(1, 2).reshape(B * Lq, 256).float()
+    m8 = mask.to(torch.uint8)
+    for ns in (1, 3):
+        got = ops.cross_attention_bf16(qs, Kh, Vh, m8, B, Lq, Lk, 8, ns)
+        assert torch.isnan(got[2 * Lq:]).all()
+        assert (got[:2 * Lq] - ref[:2 * Lq]).abs().max() <= 1e-2
+    # key-split across "ranks": two halves computed separately, partials concatenated, merged
+    half = 384
+    parts = []
+    for lo, hi in ((0, half), (half, Lk)):
+        parts.append(ops.cross_attention_bf16(qs, Kh[:, :, lo:hi].contiguous(), Vh[:, :, lo:hi].contiguous(),
+                                              m8[:, lo:hi].contiguous(), B, Lq, hi - lo, 8, 1,
+                                              write_partial=True))
+    merged = ops.attention_merge(torch.cat(parts), 2, B, Lq, 8)
+    assert (merged[:2 * Lq] - ref[:2 * Lq]).abs().max() <= 1e-2
+    assert torch.isnan(merged[2 * Lq:]).all()
