@@ -257,21 +257,15 @@ class HeadEngine:
         return cls.view(L, B, s.Lq, s.cls_out), reg.view(L, B, s.Lq, s.code_size)
 
     # -------------------------------------------------------------------------------------
-    # whole head
+    # key side / decoder layer / whole head
     # -------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def forward(self, x: torch.Tensor, img_metas: List[dict], precision: str = "bf16",
-                taps: Optional[dict] = None) -> dict:
-        if not x.is_cuda:
-            raise RuntimeError("petr_b200: features must be CUDA tensors (no CPU fallback)")
+    def key_side(self, x: torch.Tensor, img_metas: List[dict], precision: str, taps=None) -> dict:
+        """Everything that depends on the image tokens (petr_head.py:381-402 and the K/V side of
+        petr_transformer.py:341-344).  Returns the per-forward key-side state."""
         if precision == "bf16":
-            from .engine_tc import forward_tc
-            return forward_tc(self, x, img_metas, taps)
-        if precision != "fp32":
-            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+            from .engine_tc import key_side_tc
+            return key_side_tc(self, x, img_metas, taps)
         s = self.spec
-        if not s.with_multiview:
-            raise NotImplementedError("petr_b200 implements with_multiview=True (all shipped configs)")
         x = x.float().contiguous()
         B, N, Cin, H, W = x.shape
         dev = x.device
@@ -291,16 +285,44 @@ class HeadEngine:
             pos = ops.gemm_f32(h2, P["ad_w2"], P["ad_b2"], residual=pos)
         else:
             pos = ops.gemm_f32(h2, P["ad_w2"], P["ad_b2"])
+        if taps is not None:
+            taps.update(masks=masks, memory=mem, pos_embed=pos)
+        return dict(precision="fp32", B=B, Lk=Lk, mem=mem, pos=pos, kmask=masks.view(B, Lk))
+
+    def decoder_layer(self, P, l: int, X: torch.Tensor, qpos: torch.Tensor, ks: dict) -> torch.Tensor:
+        """One PETRTransformerDecoderLayer (self_attn, norm, cross_attn, norm, ffn, norm) on
+        (B*Lq, E) rows; petr_transformer.py:185-224 via mmcv BaseTransformerLayer."""
+        lw = P["layers"][l]
+        B = ks["B"]
+        X = self._self_attn(X, qpos, lw, B)
+        if ks["precision"] == "fp32":
+            X = self._cross_attn_f32(X, qpos, ks["mem"], ks["pos"], ks["kmask"], lw, B, ks["Lk"])
+        else:
+            from .engine_tc import cross_attn_tc
+            X = cross_attn_tc(self, X, qpos, lw, l, ks)
+        return self._ffn(X, lw)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, img_metas: List[dict], precision: str = "bf16",
+                taps: Optional[dict] = None) -> dict:
+        if not x.is_cuda:
+            raise RuntimeError("petr_b200: features must be CUDA tensors (no CPU fallback)")
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        s = self.spec
+        if not s.with_multiview:
+            raise NotImplementedError("petr_b200 implements with_multiview=True (all shipped configs)")
+        dev = x.device
+        P = self.packed(dev)
+        ks = self.key_side(x, img_metas, precision, taps)
+        B = ks["B"]
         qpos = self.query_embeds(P)
-        kmask = masks.view(B, Lk)
         X = torch.zeros((B * s.Lq, s.E), dtype=torch.float32, device=dev)
         outs = torch.empty((s.L, B * s.Lq, s.E), dtype=torch.float32, device=dev)
         if taps is not None:
-            taps.update(masks=masks, memory=mem, pos_embed=pos, query_embeds=qpos, layers=[])
-        for l, lw in enumerate(P["layers"]):
-            X = self._self_attn(X, qpos, lw, B)
-            X = self._cross_attn_f32(X, qpos, mem, pos, kmask, lw, B, Lk)
-            X = self._ffn(X, lw)
+            taps.update(query_embeds=qpos, layers=[])
+        for l in range(s.L):
+            X = self.decoder_layer(P, l, X, qpos, ks)
             ops.layernorm(X, *P["post_norm"], nan_to_num=True, out=outs[l])
             if taps is not None:
                 taps["layers"].append(X.clone())

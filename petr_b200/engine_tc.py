@@ -76,7 +76,8 @@ def packed_tc(eng, device) -> dict:
 
 def key_side_tc(eng, x, img_metas, taps=None):
     """Everything that depends on the image tokens: masks, input_proj, position embedding,
-    K/V projection of all layers.  Returns (Kh, Vh (L,B,heads,Lk,32) bf16, kmask|None, B, Lk)."""
+    K/V projection of all layers.  Returns the key-side state: Kh, Vh (L,B,heads,Lk,32) bf16,
+    kmask (None when no key is padded), the split-KV plan."""
     s = eng.spec
     x = x.float().contiguous()
     B, N, Cin, H, W = x.shape
@@ -107,7 +108,14 @@ def key_side_tc(eng, x, img_metas, taps=None):
     if taps is not None:
         taps.update(masks=masks, memory=mem, kin=kin, Kh=Kh, Vh=Vh)
     kmask = masks.view(B, Lk) if has_mask else None
-    return Kh, Vh, kmask, B, Lk
+    if s.E != 256 or s.heads != 8:
+        raise NotImplementedError("tcgen05 path is specialised for embed_dims 256, 8 heads of 32")
+    nsplit = choose_nsplit(B, s.heads, s.Lq, Lk)
+    partial = None
+    if nsplit > 1:
+        partial = torch.empty((nsplit * ops.attention_partial_floats(B, s.Lq, s.heads),),
+                              dtype=torch.float32, device=dev)
+    return dict(precision="bf16", B=B, Lk=Lk, Kh=Kh, Vh=Vh, kmask=kmask, nsplit=nsplit, partial=partial)
 
 
 def _sine_args(s):
@@ -116,43 +124,16 @@ def _sine_args(s):
                 eps=a["eps"], offset=a["offset"])
 
 
-@torch.no_grad()
-def forward_tc(eng, x: torch.Tensor, img_metas: List[dict], taps: Optional[dict] = None) -> dict:
+def cross_attn_tc(eng, X, qpos, lw, l: int, ks: dict):
+    """Cross-attention block of decoder layer l on the tcgen05 path: fp32 Q projection ->
+    bf16 pack (scale folded) -> flash attention over the pre-projected K/V -> fp32 out-proj +
+    residual -> LayerNorm (petr_transformer.py:341-367)."""
     s = eng.spec
-    if not s.with_multiview:
-        raise NotImplementedError("petr_b200 implements with_multiview=True (all shipped configs)")
-    if s.E != 256 or s.heads != 8:
-        raise NotImplementedError("tcgen05 path is specialised for embed_dims 256, 8 heads of 32")
-    dev = x.device
-    P = eng.packed(dev)
-    Kh, Vh, kmask, B, Lk = key_side_tc(eng, x, img_metas, taps)
-    qpos = eng.query_embeds(P)
-    nsplit = choose_nsplit(B, s.heads, s.Lq, Lk)
-    X = torch.zeros((B * s.Lq, s.E), dtype=torch.float32, device=dev)
-    outs = torch.empty((s.L, B * s.Lq, s.E), dtype=torch.float32, device=dev)
-    partial = None
-    if nsplit > 1:
-        partial = torch.empty((nsplit * ops.attention_partial_floats(B, s.Lq, s.heads),),
-                              dtype=torch.float32, device=dev)
-    if taps is not None:
-        taps.update(query_embeds=qpos, layers=[])
     E = s.E
-    for l, lw in enumerate(P["layers"]):
-        X = eng._self_attn(X, qpos, lw, B)
-        q = ops.gemm_f32(X, lw["ca_in_w"][:E], lw["ca_in_b"][:E], A2=qpos)
-        qs = ops.pack_q_bf16(q, B, s.Lq, s.heads)
-        o = ops.cross_attention_bf16(qs, Kh[l], Vh[l], kmask, B, s.Lq, Lk, s.heads, nsplit, partial=partial)
-        y = ops.gemm_f32(o, lw["ca_out_w"], lw["ca_out_b"], residual=X)
-        X = ops.layernorm(y, *lw["ln"][1], out=y)
-        X = eng._ffn(X, lw)
-        ops.layernorm(X, *P["post_norm"], nan_to_num=True, out=outs[l])
-        if taps is not None:
-            taps["layers"].append(X.clone())
-    time_div = None
-    if s.with_time:
-        from .engine import _h2d, mean_time_stamp
-        time_div = _h2d(mean_time_stamp(img_metas), dev)
-    cls, box = eng.branches(P, outs, B, time_div)
-    if taps is not None:
-        taps["outs_dec"] = outs.view(s.L, B, s.Lq, s.E)
-    return dict(all_cls_scores=cls, all_bbox_preds=box, enc_cls_scores=None, enc_bbox_preds=None)
+    B, Lk = ks["B"], ks["Lk"]
+    q = ops.gemm_f32(X, lw["ca_in_w"][:E], lw["ca_in_b"][:E], A2=qpos)
+    qs = ops.pack_q_bf16(q, B, s.Lq, s.heads)
+    o = ops.cross_attention_bf16(qs, ks["Kh"][l], ks["Vh"][l], ks["kmask"], B, s.Lq, Lk, s.heads,
+                                 ks["nsplit"], partial=ks["partial"])
+    y = ops.gemm_f32(o, lw["ca_out_w"], lw["ca_out_b"], residual=X)
+    return ops.layernorm(y, *lw["ln"][1], out=y)

@@ -24,6 +24,13 @@ def _build(name):
     return case, wl, feats, metas, head.eval().to(DEV)
 
 
+# tiny_sharp (cross-attention Wq/Wk x8, features x4) is chaotic end to end: a 1e-6 relative input
+# perturbation moves the REFERENCE's own layer-5 outputs by 0.2-0.6, so whole-head comparisons
+# only make sense on its first layer; its deeper layers are checked teacher-forced below.
+def _layers_to_check(name):
+    return slice(0, 1) if name == "tiny_sharp" else slice(None)
+
+
 @pytest.mark.parametrize("name", list(cases.CASES))
 def test_head_fp32_path_matches_reference(name):
     case, wl, feats, metas, head = _build(name)
@@ -34,8 +41,9 @@ def test_head_fp32_path_matches_reference(name):
     assert ops.launch_count() > 50
     cls, box = out["all_cls_scores"].cpu().numpy(), out["all_bbox_preds"].cpu().numpy()
     assert cls.shape == g["all_cls_scores"].shape and box.shape == g["all_bbox_preds"].shape
-    assert np.abs(cls - g["all_cls_scores"]).max() <= 2e-3
-    assert np.abs(box - g["all_bbox_preds"]).max() <= 2e-3
+    sl = _layers_to_check(name)
+    assert np.abs(cls[sl] - g["all_cls_scores"][sl]).max() <= 2e-3
+    assert np.abs(box[sl] - g["all_bbox_preds"][sl]).max() <= 2e-3
     assert out["enc_cls_scores"] is None and out["enc_bbox_preds"] is None
 
 
@@ -47,8 +55,42 @@ def test_head_bf16_path_within_tolerance(name):
     out = head([feats.to(DEV)], metas)
     cls, box = out["all_cls_scores"].cpu().numpy(), out["all_bbox_preds"].cpu().numpy()
     assert np.isfinite(cls).all() and np.isfinite(box).all()
-    assert np.abs(cls - g["all_cls_scores"]).max() <= 2e-2, np.abs(cls - g["all_cls_scores"]).max()
-    assert np.abs(box - g["all_bbox_preds"]).max() <= 2e-2, np.abs(box - g["all_bbox_preds"]).max()
+    sl = _layers_to_check(name)
+    assert np.abs(cls[sl] - g["all_cls_scores"][sl]).max() <= 2e-2, np.abs(cls - g["all_cls_scores"]).max()
+    assert np.abs(box[sl] - g["all_bbox_preds"][sl]).max() <= 2e-2, np.abs(box - g["all_bbox_preds"]).max()
+
+
+@pytest.mark.parametrize("name", ["tiny_sharp", "tiny_padded", "tiny"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-3), ("bf16", 2e-2)])
+def test_decoder_layers_teacher_forced(name, precision, tol):
+    """Each decoder layer fed with the ORACLE's input to that layer (no error compounding), then
+    post_norm + branches: cls/box of every layer within tolerance even with peaked attention
+    (exercises online-softmax max tracking, rescaling, masked tiles, split-KV)."""
+    case, wl, feats, metas, head = _build(name)
+    sd = {k: v.cpu() for k, v in head.state_dict().items()}
+    taps = {}
+    with torch.no_grad():
+        ref = po.head_forward(sd, feats, metas, cases.oracle_cfg(case), taps)
+    eng = head.engine
+    P = eng.packed(DEV)
+    ks = eng.key_side(feats.to(DEV), metas, precision)
+    qpos = eng.query_embeds(P)
+    s = eng.spec
+    B = feats.shape[0]
+    outs = torch.empty((s.L, B * s.Lq, s.E), device=DEV)
+    for l in range(s.L):
+        if l == 0:
+            X = torch.zeros((B * s.Lq, s.E), device=DEV)
+        else:
+            X = taps["layers"][l - 1]["out"].transpose(0, 1).reshape(B * s.Lq, s.E).contiguous().to(DEV)
+        Y = eng.decoder_layer(P, l, X, qpos, ks)
+        yref = taps["layers"][l]["out"].transpose(0, 1).reshape(B * s.Lq, s.E)
+        ok = ~torch.isnan(yref).any(1)
+        assert (Y.cpu()[ok] - yref[ok]).abs().max() <= (5e-4 if precision == "fp32" else 5e-2), l
+        ops.layernorm(Y, *P["post_norm"], nan_to_num=True, out=outs[l])
+    cls, box = eng.branches(P, outs, B, None)
+    assert (cls.cpu() - ref["all_cls_scores"]).abs().max() <= tol
+    assert (box.cpu() - ref["all_bbox_preds"]).abs().max() <= tol
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))

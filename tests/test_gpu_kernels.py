@@ -155,7 +155,7 @@ def test_attention_f32(B, Lq, Lk, scale):
     mask[0, :70] = 1
     for m in (None, mask):
         got = ops.attention_f32(Q, K, V, m, B, Lq, Lk, 8)
-        assert (got - _attn_ref(Q, K, V, m, B, Lq, Lk, 8)).abs().max() <= 2e-5
+        assert (got - _attn_ref(Q, K, V, m, B, Lq, Lk, 8)).abs().max() <= 1e-4
     mask[B - 1] = 1                                               # fully masked sample -> NaN like torch
     got = ops.attention_f32(Q, K, V, mask, B, Lq, Lk, 8)
     assert torch.isnan(got[(B - 1) * Lq:]).all()
