@@ -109,15 +109,31 @@ int petr_gemm_f32(const float* A, int lda, int a_layout, int hw,
  * by petr_transformer.py:357-362 (packed projections are separate petr_gemm_* calls).
  * Q rows b*Lq+q (ldq), K/V rows b*Lk+k (ldk/ldv), head h occupies columns [h*head_dim, ...).
  * key_mask nullable uint8 [B,Lk], 1 = ignore.  A row whose keys are all masked yields NaN,
- * like the reference (zeroed later by nan_to_num, petr_head.py:435).  head_dim must be 32. */
+ * like the reference (zeroed later by nan_to_num, petr_head.py:435).  head_dim must be 32.
+ * O (fp32, nullable) and/or O_split (nullable: bf16 rows [hi | lo] of width 2*heads*head_dim, the
+ * A operand of a bf16x3 petr_gemm_bf16_tc) receive the result. */
 int petr_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
-                       const uint8_t* key_mask, float* O, int ldo,
+                       const uint8_t* key_mask, float* O, int ldo, void* O_split,
                        int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
 
 /* ---- nn.LayerNorm over the last dim (eps 1e-5 on this path), optional fused ReLU
  * (cls_branches, petr_head.py:226-231) and nan_to_num (petr_head.py:435).  Y may alias X. */
 int petr_layernorm_f32(const float* X, const float* gamma, const float* beta, float* Y,
                        int rows, int E, float eps, int relu, int nan_to_num, void* stream);
+
+/* Fused LayerNorm of the decoder residual stream (E = 256).  Optional outputs: Y = LN(X) fp32;
+ * split(Y) and split(Y + qpos[row % qpos_rows]) as bf16 [hi | lo] rows (bf16x3 GEMM inputs:
+ * query+query_pos of petr_transformer.py:341); Z = LN2(Y) with nan_to_num (the decoder's
+ * post_norm on a copy, petr_transformer.py:444 + petr_head.py:435) as fp32 and/or split bf16.
+ * relu != 0 applies ReLU to Y (cls_branches, petr_head.py:226-231). */
+int petr_layernorm_multi_f32(const float* X, const float* gamma, const float* beta, float eps,
+                             const float* qpos, int qpos_rows, float* Y, void* Y_split,
+                             void* Ypos_split, const float* gamma2, const float* beta2,
+                             float* Z, void* Z_split, int rows, int E, int relu, void* stream);
+
+/* fp32 rows -> bf16 [hi | lo] rows of width 2*E: split(relu?(X + add[row % add_rows])). */
+int petr_split_rows_bf16(const float* X, int ldx, const float* add, int add_rows, void* out,
+                         int rows, int E, int relu, void* stream);
 
 /* ---- a12: reference-point add, sigmoid and pc_range affine.  petr_head.py:440-460
  * (+ PETRv2 with_time petrv2_head.py:499-505,:520-521).  reg: fp32 [L*B*Q, code_size] in place.
@@ -128,16 +144,28 @@ int petr_decode_boxes(float* reg, const float* ref, const float* h_pc_range,
 
 /* ---- tcgen05 tier (sm_100a tensor cores, TMA-fed, TMEM accumulators) ----------------- */
 
-/* bf16 x bf16 -> fp32 GEMM on tcgen05:  C = epi(A[M,K] * W[N,K]^T + bias) (+ residual).
- * A, W: bf16 row-major, K % 64 == 0, 16-byte aligned rows.  out_mode selects the store:
+/* fp32 NCHW feature maps x[G][C][hw] -> bf16 token-major out[G*hw][C] (A operand of input_proj,
+ * petr_head.py:390). */
+int petr_nchw_to_tokens_bf16(const float* x, void* out, int G, int C, int hw, void* stream);
+
+/* bf16 x bf16 -> fp32 GEMM on tcgen05 (persistent, 128x256 tiles, TMA-fed, TMEM accumulators):
+ *   C = alpha * act(A[M,K] * W[N,K]^T + bias) (+ residual)
+ * A, W: bf16 row-major, K % 64 == 0, 16-byte aligned rows.  a_k_wrap (0 = K): A has only
+ * a_k_wrap columns and column k of the product reads A[:, k % a_k_wrap] -- with A = [hi | lo]
+ * (2K0 columns), W = [W_hi | W_hi | W_lo] (3K0 columns) and a_k_wrap = 2K0 this is the bf16x3
+ * product A_hi W_hi + A_lo W_hi + A_hi W_lo, accurate to ~2^-16 (fp32-class query-side GEMMs).
+ * out_mode selects the store:
  *   0: fp32 C[m*ldc+n];  1: bf16 C[m*ldc+n];
  *   2: bf16 head-split layout C[n / 256][b][(n % 256) / 32][key][32] with b = m / kv_Lk,
- *      key = m % kv_Lk -- the K/V layout petr_cross_attention_bf16 reads.
- * Used for the Lk-side work: K/V projection of all decoder layers in one launch
- * (petr_transformer.py:341-344,:357-360), position_encoder / adapt_pos3d MLPs. */
-int petr_gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias,
-                      const float* residual, int act, void* C, int ldc, int out_mode,
-                      int M, int N, int K, int kv_Lk, void* stream);
+ *      key = m % kv_Lk -- the Q/K/V layout petr_cross_attention_bf16 reads;
+ *   3: bf16 split C[m*2N + n] = hi, C[m*2N + N + n] = lo, plus (C2 nullable) fp32 C2[m*ldc+n].
+ * residual (nullable, fp32, ldc) is added after alpha.  Used for the K/V projection of all
+ * decoder layers in one launch (petr_transformer.py:341-344,:357-360), the position_encoder /
+ * adapt_pos3d MLPs, input_proj and the query-side projections / FFN. */
+int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const void* W, int ldw,
+                      const float* bias, const float* residual, int act, float alpha,
+                      void* C, void* C2, int ldc, int out_mode, int M, int N, int K,
+                      int kv_Lk, void* stream);
 
 /* fp32 Q [B*Lq, heads*32] (row stride ldq) -> bf16 [B, heads, Lq, 32] multiplied by `scale`
  * (head_dim^-1/2 * log2 e: the softmax of petr_cross_attention_bf16 runs in the exp2 domain). */
@@ -151,20 +179,21 @@ int petr_pack_q_bf16(const float* Q, int ldq, void* out, int B, int Lq, int head
  *   Vh : bf16 [B, heads, Lk, 32]
  *   key_mask nullable uint8 [B, Lk], 1 = ignore.
  * nsplit key splits run as separate CTAs (split-KV for small B).  write_partial == 0: O fp32
- * [B*Lq, heads*32] (row stride ldo) receives the normalised result (partials of nsplit > 1 are
+ * [B*Lq, heads*32] (row stride ldo, nullable) and/or O_split (bf16 [hi | lo] rows of width
+ * 2*heads*32, nullable) receive the normalised result (partials of nsplit > 1 are
  * merged internally; `partial` is then the scratch, petr_attention_partial_floats * nsplit).
  * write_partial == 1: only the un-normalised partials (O, m, l) are written to `partial`
  * (layout below) for a later petr_attention_merge -- the key-split-across-GPUs path. */
 int petr_cross_attention_bf16(const void* Qs, const void* Kh, const void* Vh,
-                              const uint8_t* key_mask, float* O, int ldo, float* partial,
-                              int B, int Lq, int Lk, int heads, int nsplit, int write_partial,
-                              void* stream);
+                              const uint8_t* key_mask, float* O, int ldo, void* O_split,
+                              float* partial, int B, int Lq, int Lk, int heads, int nsplit,
+                              int write_partial, void* stream);
 
 /* Merge `nparts` partial attention results (on-GPU split-KV or key-split across GPUs after an
  * all-gather):  m = max m_r;  O = sum e^{m_r-m} O_r / sum e^{m_r-m} l_r.
  * partial: fp32 [nparts][ rows*32 (O) | rows*2 (m, l) ], rows = B*heads*Lq ordered (b, head, q);
  * m is in the log2 domain. */
-int petr_attention_merge(const float* partial, int nparts, float* O, int ldo,
+int petr_attention_merge(const float* partial, int nparts, float* O, int ldo, void* O_split,
                          int B, int Lq, int heads, void* stream);
 
 int64_t petr_attention_partial_floats(int B, int Lq, int heads);

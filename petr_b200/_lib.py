@@ -28,13 +28,16 @@ SIGNATURES = {
     "petr_sine3d_features": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _I, _P]),
     "petr_pos2posemb3d": (c_int, [_P, _P, _I, _I, _P, _P]),
     "petr_gemm_f32": (c_int, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
-    "petr_attention_f32": (c_int, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "petr_attention_f32": (c_int, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "petr_layernorm_multi_f32": (c_int, [_P, _P, _P, _F, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "petr_split_rows_bf16": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "petr_nchw_to_tokens_bf16": (c_int, [_P, _P, _I, _I, _I, _P]),
     "petr_layernorm_f32": (c_int, [_P, _P, _P, _P, _I, _I, _F, _I, _I, _P]),
     "petr_decode_boxes": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "petr_gemm_bf16_tc": (c_int, [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "petr_gemm_bf16_tc": (c_int, [_P, _I, _I, _P, _I, _P, _P, _I, _F, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "petr_pack_q_bf16": (c_int, [_P, _I, _P, _I, _I, _I, _F, _P]),
-    "petr_cross_attention_bf16": (c_int, [_P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "petr_attention_merge": (c_int, [_P, _I, _P, _I, _I, _I, _I, _P]),
+    "petr_cross_attention_bf16": (c_int, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "petr_attention_merge": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
     "petr_attention_partial_floats": (c_int64, [_I, _I, _I]),
 }
 

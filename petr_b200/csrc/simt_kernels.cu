@@ -369,7 +369,8 @@ constexpr int ATT_THREADS = 64, ATT_KT = 64;
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk,
                      const float* __restrict__ V, int ldv, const uint8_t* __restrict__ key_mask,
-                     float* __restrict__ O, int ldo, int Lq, int Lk, float scale_log2) {
+                     float* __restrict__ O, int ldo, __nv_bfloat16* __restrict__ O_split, int E,
+                     int Lq, int Lk, float scale_log2) {
     __shared__ __align__(16) float sK[ATT_KT][32];
     __shared__ __align__(16) float sV[ATT_KT][32];
     __shared__ float sBias[ATT_KT];
@@ -439,9 +440,22 @@ attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restri
     }
     if (live) {
         float inv = 1.f / l;                           // l == 0 (all keys masked) -> NaN, as torch
-        float* op = O + ((int64_t)b * Lq + q) * ldo + head * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) op[i] = o[i] * inv;
+        for (int i = 0; i < 32; ++i) o[i] *= inv;
+        if (O) {
+            float* op = O + ((int64_t)b * Lq + q) * ldo + head * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) op[i] = o[i];
+        }
+        if (O_split) {                                 // bf16 [hi | lo] rows of width 2E (bf16x3 GEMM input)
+            __nv_bfloat16* sp = O_split + ((int64_t)b * Lq + q) * (2 * E) + head * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                __nv_bfloat16 hi = __float2bfloat16_rn(o[i]);
+                sp[i] = hi;
+                sp[E + i] = __float2bfloat16_rn(o[i] - __bfloat162float(hi));
+            }
+        }
     }
 }
 
@@ -482,6 +496,91 @@ layernorm_f32_kernel(const float* __restrict__ X, const float* __restrict__ gamm
         }
         y[c] = r;
     }
+}
+
+// Fused LayerNorm for the decoder residual stream (E = 256, one warp per row): optional outputs
+//   Y fp32, split(Y) and split(Y + qpos[row % qpos_rows]) as bf16 [hi | lo] rows (inputs of the
+//   bf16x3 tensor-core GEMMs), and a second LayerNorm Z = LN2(Y) (the decoder's post_norm on a
+//   copy, petr_transformer.py:444) with nan_to_num (petr_head.py:435) as fp32 and split bf16.
+struct LnMultiParams {
+    const float* X; const float* gamma; const float* beta; float eps;
+    const float* qpos; int qpos_rows;
+    float* Y; __nv_bfloat16* Y_split; __nv_bfloat16* Ypos_split;
+    const float* gamma2; const float* beta2; float* Z; __nv_bfloat16* Z_split;
+    int rows; int relu;
+};
+
+__device__ __forceinline__ void store_split_elem(__nv_bfloat16* base, int E, int c, float v) {
+    __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    base[c] = hi;
+    base[E + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_multi_kernel(LnMultiParams p) {
+    constexpr int PER = 8, E = 256;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= p.rows) return;
+    const float* x = p.X + (int64_t)row * E;
+    float v[PER], y[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] = x[lane + 32 * i]; s += v[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    float mean = s / (float)E, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q += d * d; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    float rstd = rsqrtf(q / (float)E + p.eps);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int c = lane + 32 * i;
+        y[i] = (v[i] - mean) * rstd * p.gamma[c] + p.beta[c];
+        if (p.relu) y[i] = fmaxf(y[i], 0.f);
+        if (p.Y) p.Y[(int64_t)row * E + c] = y[i];
+        if (p.Y_split) store_split_elem(p.Y_split + (int64_t)row * 2 * E, E, c, y[i]);
+        if (p.Ypos_split)
+            store_split_elem(p.Ypos_split + (int64_t)row * 2 * E, E, c,
+                             y[i] + p.qpos[(int64_t)(row % p.qpos_rows) * E + c]);
+    }
+    if (p.gamma2) {
+        s = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) s += y[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        mean = s / (float)E; q = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { float d = y[i] - mean; q += d * d; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        rstd = rsqrtf(q / (float)E + p.eps);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            int c = lane + 32 * i;
+            float r = (y[i] - mean) * rstd * p.gamma2[c] + p.beta2[c];
+            if (isnan(r)) r = 0.f;
+            else if (isinf(r)) r = r > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+            if (p.Z) p.Z[(int64_t)row * E + c] = r;
+            if (p.Z_split) store_split_elem(p.Z_split + (int64_t)row * 2 * E, E, c, r);
+        }
+    }
+}
+
+// fp32 rows -> bf16 [hi | lo] rows, optionally adding a broadcast row table first, with optional
+// ReLU (E arbitrary): split(relu(X + add[row % add_rows]))
+__global__ void split_rows_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ add,
+                                  int add_rows, __nv_bfloat16* __restrict__ out, int64_t rows, int E, int relu) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * E) return;
+    int64_t r = i / E;
+    int c = (int)(i - r * E);
+    float v = X[r * ldx + c];
+    if (add) v += add[(r % add_rows) * (int64_t)E + c];
+    if (relu) v = fmaxf(v, 0.f);
+    store_split_elem(out + r * 2 * E, E, c, v);
 }
 
 // a12: reference add + sigmoid + pc_range affine (petr_head.py:440-460)
@@ -604,16 +703,17 @@ extern "C" int petr_gemm_f32(const float* A, int lda, int a_layout, int hw, cons
 }
 
 extern "C" int petr_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V,
-                                  int ldv, const uint8_t* key_mask, float* O, int ldo, int B, int Lq,
-                                  int Lk, int heads, int head_dim, float scale, void* stream) {
-    PETR_REQUIRE(Q && K && V && O, PETR_E_BADARG, "petr_attention_f32: null pointer");
+                                  int ldv, const uint8_t* key_mask, float* O, int ldo, void* O_split,
+                                  int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream) {
+    PETR_REQUIRE(Q && K && V && (O || O_split), PETR_E_BADARG, "petr_attention_f32: null pointer");
     PETR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0, PETR_E_BADARG, "petr_attention_f32: bad dimension");
     PETR_REQUIRE(head_dim == 32, PETR_E_SHAPE, "petr_attention_f32: head_dim must be 32, got %d", head_dim);
     PETR_REQUIRE((ldk & 3) == 0 && (ldv & 3) == 0 && aligned16(K) && aligned16(V), PETR_E_ALIGN,
                  "petr_attention_f32: K/V rows must be 16-byte aligned");
     dim3 grid((Lq + ATT_THREADS - 1) / ATT_THREADS, heads, B);
     attention_f32_kernel<<<grid, ATT_THREADS, 0, (cudaStream_t)stream>>>(
-        Q, ldq, K, ldk, V, ldv, key_mask, O, ldo, Lq, Lk, scale * 1.4426950408889634f);
+        Q, ldq, K, ldk, V, ldv, key_mask, O, ldo, (__nv_bfloat16*)O_split, heads * 32, Lq, Lk,
+        scale * 1.4426950408889634f);
     return after_launch("petr_attention_f32");
 }
 
@@ -645,4 +745,31 @@ extern "C" int petr_decode_boxes(float* reg, const float* ref, const float* h_pc
     decode_boxes_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reg, ref, dp, time_div, rows, B, Q, code_size);
     return after_launch("petr_decode_boxes");
+}
+
+extern "C" int petr_layernorm_multi_f32(const float* X, const float* gamma, const float* beta, float eps,
+                                        const float* qpos, int qpos_rows, float* Y, void* Y_split,
+                                        void* Ypos_split, const float* gamma2, const float* beta2,
+                                        float* Z, void* Z_split, int rows, int E, int relu, void* stream) {
+    PETR_REQUIRE(X && gamma && beta, PETR_E_BADARG, "petr_layernorm_multi_f32: null pointer");
+    PETR_REQUIRE(rows > 0, PETR_E_BADARG, "petr_layernorm_multi_f32: bad dimension");
+    PETR_REQUIRE(E == 256, PETR_E_SHAPE, "petr_layernorm_multi_f32: E must be 256, got %d", E);
+    if (Ypos_split) PETR_REQUIRE(qpos && qpos_rows > 0, PETR_E_BADARG, "petr_layernorm_multi_f32: qpos required");
+    if (Z || Z_split) PETR_REQUIRE(gamma2 && beta2, PETR_E_BADARG, "petr_layernorm_multi_f32: gamma2/beta2 required");
+    LnMultiParams p{X, gamma, beta, eps, qpos, qpos_rows, Y, (__nv_bfloat16*)Y_split,
+                    (__nv_bfloat16*)Ypos_split, (Z || Z_split) ? gamma2 : nullptr, beta2, Z,
+                    (__nv_bfloat16*)Z_split, rows, relu};
+    layernorm_multi_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p);
+    return after_launch("petr_layernorm_multi_f32");
+}
+
+extern "C" int petr_split_rows_bf16(const float* X, int ldx, const float* add, int add_rows, void* out,
+                                    int rows, int E, int relu, void* stream) {
+    PETR_REQUIRE(X && out, PETR_E_BADARG, "petr_split_rows_bf16: null pointer");
+    PETR_REQUIRE(rows > 0 && E > 0 && ldx >= E, PETR_E_BADARG, "petr_split_rows_bf16: bad dimension");
+    if (add) PETR_REQUIRE(add_rows > 0, PETR_E_BADARG, "petr_split_rows_bf16: add_rows <= 0");
+    int64_t total = (int64_t)rows * E;
+    split_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        X, ldx, add, add_rows, (__nv_bfloat16*)out, rows, E, relu);
+    return after_launch("petr_split_rows_bf16");
 }

@@ -43,7 +43,8 @@ __device__ __forceinline__ float ex2(float x) {
 
 struct AttParams {
     const uint8_t* key_mask;   // [B, Lk] or null
-    float* O; int ldo;         // normalised output (nsplit == 1)
+    float* O; int ldo;         // normalised output (nsplit == 1), nullable
+    __nv_bfloat16* O_split;    // bf16 [hi | lo] rows of width 2*heads*32, nullable
     float* partial;            // [nsplit][rows*32 O | rows*2 (m,l)], rows = B*heads*Lq
     int B, Lq, Lk, heads, nsplit, tiles_total, write_partial;
 };
@@ -267,10 +268,31 @@ cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
                 pm[0] = m_use; pm[1] = l;
             } else {
                 const float inv = 1.f / l;          // l == 0 (all keys masked) -> NaN like torch
-                float* op = p.O + ((int64_t)b * p.Lq + q) * p.ldo + h * HD;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(op + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+                for (int i = 0; i < 32; ++i) o[i] *= inv;
+                if (p.O) {
+                    float* op = p.O + ((int64_t)b * p.Lq + q) * p.ldo + h * HD;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4*>(op + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                }
+                if (p.O_split) {
+                    const int E = p.heads * HD;
+                    __nv_bfloat16* sp = p.O_split + ((int64_t)b * p.Lq + q) * (2 * E) + h * HD;
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float h0 = __bfloat162float(__float2bfloat16_rn(o[i]));
+                        float h1 = __bfloat162float(__float2bfloat16_rn(o[i + 1]));
+                        hi[i >> 1] = pack_bf16x2(h0, h1);
+                        lo[i >> 1] = pack_bf16x2(o[i] - h0, o[i + 1] - h1);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        *reinterpret_cast<uint4*>(sp + 2 * i) = make_uint4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]);
+                        *reinterpret_cast<uint4*>(sp + E + 2 * i) = make_uint4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
+                    }
+                }
             }
         }
         tcgen05_fence_before();
@@ -285,7 +307,7 @@ cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 
 // merge partial (O, m, l) over parts; thread per (row, 4 dims)
 __global__ void attention_merge_kernel(const float* __restrict__ part, int nparts, float* __restrict__ O,
-                                       int ldo, int B, int Lq, int heads) {
+                                       int ldo, __nv_bfloat16* __restrict__ O_split, int B, int Lq, int heads) {
     const int64_t rows = (int64_t)B * heads * Lq;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * 8) return;
@@ -308,8 +330,16 @@ __global__ void attention_merge_kernel(const float* __restrict__ part, int npart
     const int q = (int)(r % Lq);
     const int bh = (int)(r / Lq);
     const int b = bh / heads, h = bh % heads;
-    float* op = O + ((int64_t)b * Lq + q) * ldo + h * 32 + d4;
-    *reinterpret_cast<float4*>(op) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    if (O) *reinterpret_cast<float4*>(O + ((int64_t)b * Lq + q) * ldo + h * 32 + d4) = acc;
+    if (O_split) {
+        const int E = heads * 32;
+        __nv_bfloat16* sp = O_split + ((int64_t)b * Lq + q) * (2 * E) + h * 32 + d4;
+        float h0 = __bfloat162float(__float2bfloat16_rn(acc.x)), h1 = __bfloat162float(__float2bfloat16_rn(acc.y));
+        float h2 = __bfloat162float(__float2bfloat16_rn(acc.z)), h3 = __bfloat162float(__float2bfloat16_rn(acc.w));
+        *reinterpret_cast<uint2*>(sp) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+        *reinterpret_cast<uint2*>(sp + E) = make_uint2(pack_bf16x2(acc.x - h0, acc.y - h1), pack_bf16x2(acc.z - h2, acc.w - h3));
+    }
 }
 
 // fp32 Q [B*Lq, heads*32] -> bf16 [B, heads, Lq, 32], scaled (head_dim^-1/2 * log2 e)
@@ -348,16 +378,20 @@ extern "C" int petr_pack_q_bf16(const float* Q, int ldq, void* out, int B, int L
 }
 
 extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const void* Vh,
-                                         const uint8_t* key_mask, float* O, int ldo, float* partial,
-                                         int B, int Lq, int Lk, int heads, int nsplit,
+                                         const uint8_t* key_mask, float* O, int ldo, void* O_split,
+                                         float* partial, int B, int Lq, int Lk, int heads, int nsplit,
                                          int write_partial, void* stream) {
     PETR_REQUIRE(Qs && Kh && Vh, PETR_E_BADARG, "petr_cross_attention_bf16: null pointer");
     PETR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0 && nsplit > 0, PETR_E_BADARG,
                  "petr_cross_attention_bf16: bad dimension");
     const bool part = write_partial || nsplit > 1;
     if (part) PETR_REQUIRE(partial, PETR_E_BADARG, "petr_cross_attention_bf16: partial buffer required");
-    if (!write_partial) PETR_REQUIRE(O && ldo >= heads * 32 && (ldo % 4) == 0 && aligned16(O), PETR_E_ALIGN,
-                                     "petr_cross_attention_bf16: O must be 16-byte aligned, ldo %% 4 == 0");
+    if (!write_partial) {
+        PETR_REQUIRE(O || O_split, PETR_E_BADARG, "petr_cross_attention_bf16: O or O_split required");
+        if (O) PETR_REQUIRE(ldo >= heads * 32 && (ldo % 4) == 0 && aligned16(O), PETR_E_ALIGN,
+                            "petr_cross_attention_bf16: O must be 16-byte aligned, ldo %% 4 == 0");
+        if (O_split) PETR_REQUIRE(aligned16(O_split), PETR_E_ALIGN, "petr_cross_attention_bf16: O_split alignment");
+    }
     PETR_REQUIRE(aligned16(Qs) && aligned16(Kh) && aligned16(Vh), PETR_E_ALIGN,
                  "petr_cross_attention_bf16: Q/K/V must be 16-byte aligned");
     const int tiles = (Lk + KT - 1) / KT;
@@ -382,7 +416,7 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
     cudaError_t e = cudaFuncSetAttribute(cross_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (e != cudaSuccess) return fail((int)e, "petr_cross_attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     AttParams p{};
-    p.key_mask = key_mask; p.O = O; p.ldo = ldo;
+    p.key_mask = key_mask; p.O = O; p.ldo = ldo; p.O_split = (__nv_bfloat16*)O_split;
     const int64_t rows = (int64_t)B * heads * Lq;
     p.partial = partial;
     p.B = B; p.Lq = Lq; p.Lk = Lk; p.heads = heads; p.nsplit = nsplit; p.tiles_total = tiles;
@@ -395,19 +429,19 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
         // on-GPU split-KV: merge right away
         int64_t total = rows * 8;
         attention_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            partial, nsplit, O, ldo, B, Lq, heads);
+            partial, nsplit, O, ldo, (__nv_bfloat16*)O_split, B, Lq, heads);
         return after_launch("petr_attention_merge");
     }
     return 0;
 }
 
-extern "C" int petr_attention_merge(const float* partial, int nparts, float* O, int ldo, int B, int Lq,
-                                    int heads, void* stream) {
-    PETR_REQUIRE(partial && O, PETR_E_BADARG, "petr_attention_merge: null pointer");
-    PETR_REQUIRE(nparts > 0 && B > 0 && Lq > 0 && heads > 0 && ldo >= heads * 32 && (ldo % 4) == 0, PETR_E_BADARG,
-                 "petr_attention_merge: bad dimension");
+extern "C" int petr_attention_merge(const float* partial, int nparts, float* O, int ldo, void* O_split,
+                                    int B, int Lq, int heads, void* stream) {
+    PETR_REQUIRE(partial && (O || O_split), PETR_E_BADARG, "petr_attention_merge: null pointer");
+    PETR_REQUIRE(nparts > 0 && B > 0 && Lq > 0 && heads > 0, PETR_E_BADARG, "petr_attention_merge: bad dimension");
+    if (O) PETR_REQUIRE(ldo >= heads * 32 && (ldo % 4) == 0, PETR_E_BADARG, "petr_attention_merge: bad ldo");
     int64_t total = (int64_t)B * heads * Lq * 8;
     attention_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        partial, nparts, O, ldo, B, Lq, heads);
+        partial, nparts, O, ldo, (__nv_bfloat16*)O_split, B, Lq, heads);
     return after_launch("petr_attention_merge");
 }

@@ -1,12 +1,15 @@
-// tcgen05 GEMM: C[M,N] = epi(A[M,K] . W[N,K]^T + bias) (+ residual), bf16 operands, fp32
-// accumulation in TMEM.  Lk-side work of the PETR head: K/V projection of all decoder layers,
-// position_encoder / adapt_pos3d MLPs (petr_head.py:249-267, petr_transformer.py:341-360).
+// tcgen05 GEMM: C[M,N] = alpha * epi(A[M,K] . W[N,K]^T + bias) (+ residual), bf16 operands, fp32
+// accumulation in TMEM.  Used for the Lk-side work of the PETR head (K/V projection of all decoder
+// layers, position_encoder / adapt_pos3d MLPs; petr_head.py:249-267, petr_transformer.py:341-360)
+// and, through the bf16x3 split (A = [hi|lo|hi], W = [hi|hi|lo] concatenated along K), for the
+// fp32-class query-side projections / FFN.
 //
-// CTA = one 128 x 128 output tile.  Warp 0: TMA producer (A and W tiles, 128B-swizzled, 3-stage
-// mbarrier ring).  Warp 1: TMEM allocator + single-thread tcgen05.mma issuer.  Warps 2-5:
-// epilogue (tcgen05.ld 32x32b -> registers -> bias/act/residual -> global).  ~97 KB of shared
-// memory and 128 TMEM columns per CTA, so two CTAs are resident per SM and one CTA's epilogue
-// overlaps the other's main loop.
+// Persistent kernel, one CTA per SM, 128 x 256 output tiles (n fastest so an A tile is reused from
+// L2 by neighbouring CTAs).  Warp 0: TMA producer (128B-swizzled tiles, 4-stage mbarrier ring).
+// Warp 1: TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128x256x16).  Warps 2-5:
+// epilogue (tcgen05.ld 32x32b -> registers -> bias/act/residual -> global).  The fp32 accumulator
+// is double buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop
+// of tile i+1.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <mutex>
@@ -48,30 +51,43 @@ namespace {
 
 using namespace tc;
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;
+constexpr int STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;                 // 48 KB
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int GEMM_THREADS = 192;
 
 struct EpiParams {
-    const float* bias; const float* residual; int act; void* C; int ldc; int out_mode;
-    int M, N, K; int kv_Lk; int kv_B; int kv_E;
+    const float* bias; const float* residual; int act; float alpha;
+    void* C; void* C2; int ldc; int out_mode;
+    int M, N, K; int a_k_wrap; int kv_Lk; int kv_B; int kv_E;
+    int tiles_m, tiles_n;
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS)
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* cp, const float* v) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        uint4 t;
+        t.x = pack_bf16x2(v[j], v[j + 1]); t.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        t.z = pack_bf16x2(v[j + 4], v[j + 5]); t.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(cp + j) = t;
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     EpiParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* acc_full = empty_bar + STAGES;      // 2
+    uint64_t* acc_empty = acc_full + 2;           // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int num_k = p.K / BK;
+    const int num_tiles = p.tiles_m * p.tiles_n;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -80,11 +96,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-            mbar_init(accum_bar, 1);
+            for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, BN);
+        tmem_alloc(tmem_slot, 512);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -93,114 +109,169 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                uint8_t* a = smem + s * STAGE_BYTES;
-                tma_load_2d(a, &tmA, &full_bar[s], kb * BK, m0);
-                tma_load_2d(a + TILE_A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+            uint32_t it = 0;                                   // global k-block counter of this CTA
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    uint8_t* a = smem + s * STAGE_BYTES;
+                    int ka = kb * BK;
+                    if (ka >= p.a_k_wrap) ka -= p.a_k_wrap;      // A = [hi | lo | hi] without a third copy
+                    tma_load_2d(a, &tmA, &full_bar[s], ka, m0);
+                    tma_load_2d(a + TILE_A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BM, BN, 1, 0, 0);
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+                const uint32_t buf = tcount & 1;
+                mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1) ^ 1);   // epilogue drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-                const uint32_t b_addr = a_addr + TILE_A_BYTES;
+                const uint32_t d = tmem_base + buf * BN;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + TILE_A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024, LAYOUT_SW128);
-                    uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024, LAYOUT_SW128);
-                    umma_f16_ss(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024, LAYOUT_SW128);
+                        uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024, LAYOUT_SW128);
+                        umma_f16_ss(d, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);                  // smem stage free when these retire
                 }
-                umma_commit(&empty_bar[s]);      // frees the smem stage when these MMAs retire
+                umma_commit(&acc_full[buf]);
             }
-            umma_commit(accum_bar);              // accumulator complete
         }
     } else {
         // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        const int m = m0 + row;
-        mbar_wait(accum_bar, 0);
-        tcgen05_fence_after();
-        int kv_b = 0, kv_key = 0;
-        if (p.out_mode == 2 && m < p.M) { kv_b = m / p.kv_Lk; kv_key = m - kv_b * p.kv_Lk; }
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+            const uint32_t buf = tcount & 1;
+            const int m = m0 + row;
+            mbar_wait(&acc_full[buf], (tcount >> 1) & 1);
+            tcgen05_fence_after();
+            int kv_b = 0, kv_key = 0;
+            if (p.out_mode == 2 && m < p.M) { kv_b = m / p.kv_Lk; kv_key = m - kv_b * p.kv_Lk; }
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, r);
-            tmem_ld_wait();
-            const int nb = n0 + c * 32;
-            if (m >= p.M || nb >= p.N) continue;
-            float v[32];
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c * 32, r);
+                tmem_ld_wait();
+                const int nb = n0 + c * 32;
+                if (m >= p.M || nb >= p.N) continue;
+                const bool full = (nb + 32 <= p.N);
+                float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                v[j] = __uint_as_float(r[j]);
-                if (p.bias && nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
-                if (p.act == PETR_ACT_RELU) v[j] = fmaxf(v[j], 0.f);
-            }
-            const bool full = (nb + 32 <= p.N);
-            if (p.residual) {
-                const float* rp = p.residual + (int64_t)m * p.ldc + nb;
-                if (full && ((p.ldc & 3) == 0)) {
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias) {
+                    if (full) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 t = *reinterpret_cast<const float4*>(rp + j);
-                        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+                            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
                     }
-                } else {
-                    for (int j = 0; j < 32 && nb + j < p.N; ++j) v[j] += rp[j];
                 }
-            }
-            if (p.out_mode == 0) {
-                float* cp = reinterpret_cast<float*>(p.C) + (int64_t)m * p.ldc + nb;
-                if (full && ((p.ldc & 3) == 0)) {
+                if (p.act == PETR_ACT_RELU) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-                    for (int j = 0; j < 32 && nb + j < p.N; ++j) cp[j] = v[j];
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
-            } else {
-                __nv_bfloat16* cp;
-                bool vec;
+                if (p.alpha != 1.f) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+                }
+                if (p.residual) {
+                    const float* rp = p.residual + (int64_t)m * p.ldc + nb;
+                    if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 t = *reinterpret_cast<const float4*>(rp + j);
+                            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (nb + j < p.N) v[j] += rp[j];
+                    }
+                }
+                if (p.out_mode == 0 || (p.out_mode == 3 && p.C2)) {
+                    float* cp = reinterpret_cast<float*>(p.out_mode == 0 ? p.C : p.C2) + (int64_t)m * p.ldc + nb;
+                    if (full && ((p.ldc & 3) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (nb + j < p.N) cp[j] = v[j];
+                    }
+                }
                 if (p.out_mode == 1) {
-                    cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m * p.ldc + nb;
-                    vec = full && ((p.ldc & 7) == 0);
-                } else {
+                    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m * p.ldc + nb;
+                    if (full && ((p.ldc & 7) == 0)) store_bf16x32(cp, v);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (nb + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
+                    }
+                } else if (p.out_mode == 2) {
                     // head-split layout [n / E][b][head][key][32]; a 32-column chunk is one head
                     const int l = nb / p.kv_E, h = (nb % p.kv_E) >> 5;
-                    cp = reinterpret_cast<__nv_bfloat16*>(p.C) +
-                         ((((int64_t)l * p.kv_B + kv_b) * (p.kv_E >> 5) + h) * p.kv_Lk + kv_key) * 32;
-                    vec = true;
-                }
-                if (vec) {
+                    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) +
+                        ((((int64_t)l * p.kv_B + kv_b) * (p.kv_E >> 5) + h) * p.kv_Lk + kv_key) * 32;
+                    store_bf16x32(cp, v);
+                } else if (p.out_mode == 3) {
+                    // bf16 split [hi | lo] for the bf16x3 GEMMs: row m, hi at [nb], lo at [N + nb]
+                    float lo[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 t;
-                        t.x = pack_bf16x2(v[j], v[j + 1]); t.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                        t.z = pack_bf16x2(v[j + 4], v[j + 5]); t.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                        *reinterpret_cast<uint4*>(cp + j) = t;
+                    for (int j = 0; j < 32; ++j) {
+                        float hi = __bfloat162float(__float2bfloat16_rn(v[j]));
+                        lo[j] = v[j] - hi;
                     }
-                } else {
-                    for (int j = 0; j < 32 && nb + j < p.N; ++j) cp[j] = __float2bfloat16_rn(v[j]);
+                    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m * (2 * p.N) + nb;
+                    store_bf16x32(cp, v);
+                    store_bf16x32(cp + p.N, lo);
                 }
             }
+            tcgen05_fence_before();
+            mbar_arrive(&acc_empty[buf]);
         }
-        tcgen05_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
         __syncwarp();
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// fp32 NCHW feature maps (G, C, hw) -> bf16 token-major (G*hw, C): A operand of input_proj
+__global__ void __launch_bounds__(256)
+nchw_to_tokens_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int hw) {
+    __shared__ float tile[32][33];
+    const int g = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const float* xg = x + (int64_t)g * C * hw;
+    for (int i = ty; i < 32; i += 8) {
+        int c = c0 + i, pp = p0 + tx;
+        tile[i][tx] = (c < C && pp < hw) ? xg[(int64_t)c * hw + pp] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int pp = p0 + i, c = c0 + tx;
+        if (pp < hw && c < C) out[((int64_t)g * hw + pp) * C + c] = __float2bfloat16_rn(tile[tx][i]);
     }
 }
 
@@ -209,42 +280,61 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 using namespace petr;
 
-extern "C" int petr_gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, const float* bias,
-                                 const float* residual, int act, void* C, int ldc, int out_mode,
-                                 int M, int N, int K, int kv_Lk, void* stream) {
+extern "C" int petr_nchw_to_tokens_bf16(const float* x, void* out, int G, int C, int hw, void* stream) {
+    PETR_REQUIRE(x && out, PETR_E_BADARG, "petr_nchw_to_tokens_bf16: null pointer");
+    PETR_REQUIRE(G > 0 && C > 0 && hw > 0 && G <= 65535, PETR_E_BADARG, "petr_nchw_to_tokens_bf16: bad dimension");
+    dim3 grid((hw + 31) / 32, (C + 31) / 32, G);
+    nchw_to_tokens_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, C, hw);
+    return after_launch("petr_nchw_to_tokens_bf16");
+}
+
+extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const void* W, int ldw,
+                                 const float* bias, const float* residual, int act, float alpha,
+                                 void* C, void* C2, int ldc, int out_mode, int M, int N, int K,
+                                 int kv_Lk, void* stream) {
     PETR_REQUIRE(A && W && C, PETR_E_BADARG, "petr_gemm_bf16_tc: null pointer");
     PETR_REQUIRE(M > 0 && N > 0 && K > 0, PETR_E_BADARG, "petr_gemm_bf16_tc: bad dimension");
     PETR_REQUIRE(K % BK == 0, PETR_E_SHAPE, "petr_gemm_bf16_tc: K must be a multiple of 64, got %d", K);
-    PETR_REQUIRE(lda >= K && ldw >= K && (lda % 8) == 0 && (ldw % 8) == 0 && aligned16(A) && aligned16(W),
+    if (a_k_wrap <= 0) a_k_wrap = K;
+    PETR_REQUIRE(a_k_wrap % BK == 0 && a_k_wrap <= K && K - a_k_wrap <= a_k_wrap, PETR_E_SHAPE,
+                 "petr_gemm_bf16_tc: a_k_wrap must be a multiple of 64 with K/2 <= a_k_wrap <= K");
+    PETR_REQUIRE(lda >= a_k_wrap && ldw >= K && (lda % 8) == 0 && (ldw % 8) == 0 && aligned16(A) && aligned16(W),
                  PETR_E_ALIGN, "petr_gemm_bf16_tc: A/W rows must be 16-byte aligned");
     PETR_REQUIRE(act == PETR_ACT_NONE || act == PETR_ACT_RELU, PETR_E_BADARG, "petr_gemm_bf16_tc: bad act");
-    PETR_REQUIRE(out_mode >= 0 && out_mode <= 2, PETR_E_BADARG, "petr_gemm_bf16_tc: bad out_mode");
+    PETR_REQUIRE(out_mode >= 0 && out_mode <= 3, PETR_E_BADARG, "petr_gemm_bf16_tc: bad out_mode");
     EpiParams p{};
-    p.bias = bias; p.residual = residual; p.act = act; p.C = C; p.ldc = ldc; p.out_mode = out_mode;
-    p.M = M; p.N = N; p.K = K;
+    p.bias = bias; p.residual = residual; p.act = act; p.alpha = alpha;
+    p.C = C; p.C2 = C2; p.ldc = ldc; p.out_mode = out_mode;
+    p.M = M; p.N = N; p.K = K; p.a_k_wrap = a_k_wrap;
+    if (bias) PETR_REQUIRE(aligned16(bias), PETR_E_ALIGN, "petr_gemm_bf16_tc: bias must be 16-byte aligned");
     if (out_mode == 2) {
         PETR_REQUIRE(kv_Lk > 0 && M % kv_Lk == 0 && N % 256 == 0 && !residual, PETR_E_SHAPE,
                      "petr_gemm_bf16_tc: head-split output needs M %% Lk == 0, N %% 256 == 0, no residual");
         p.kv_Lk = kv_Lk; p.kv_B = M / kv_Lk; p.kv_E = 256;
         PETR_REQUIRE(aligned16(C), PETR_E_ALIGN, "petr_gemm_bf16_tc: C must be 16-byte aligned");
+    } else if (out_mode == 3) {
+        PETR_REQUIRE(N % 32 == 0 && aligned16(C), PETR_E_SHAPE, "petr_gemm_bf16_tc: split output needs N %% 32 == 0");
+        if (C2 || residual) PETR_REQUIRE(ldc >= N, PETR_E_BADARG, "petr_gemm_bf16_tc: ldc < N");
     } else {
         PETR_REQUIRE(ldc >= N, PETR_E_BADARG, "petr_gemm_bf16_tc: ldc < N");
     }
     CUtensorMap tmA, tmB;
-    uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)lda * 2};
+    uint64_t dA[2] = {(uint64_t)a_k_wrap, (uint64_t)M}, sA[1] = {(uint64_t)lda * 2};
     uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)ldw * 2};
     uint32_t boxA[2] = {BK, BM}, boxB[2] = {BK, BN};
     int rc = tmap::encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, dA, sA, boxA, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = tmap::encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, dB, sB, boxB, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-        if (e != cudaSuccess) return fail((int)e, "petr_gemm_bf16_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
-    dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    if (e != cudaSuccess) return fail((int)e, "petr_gemm_bf16_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    p.tiles_m = (M + BM - 1) / BM;
+    p.tiles_n = (N + BN - 1) / BN;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int tiles = p.tiles_m * p.tiles_n;
+    int grid = tiles < sms ? tiles : sms;
     gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, p);
     return after_launch("petr_gemm_bf16_tc");
 }

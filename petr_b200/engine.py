@@ -295,11 +295,8 @@ class HeadEngine:
         lw = P["layers"][l]
         B = ks["B"]
         X = self._self_attn(X, qpos, lw, B)
-        if ks["precision"] == "fp32":
-            X = self._cross_attn_f32(X, qpos, ks["mem"], ks["pos"], ks["kmask"], lw, B, ks["Lk"])
-        else:
-            from .engine_tc import cross_attn_tc
-            X = cross_attn_tc(self, X, qpos, lw, l, ks)
+        assert ks["precision"] == "fp32", "the bf16 path runs engine_tc.decoder_layer_tc"
+        X = self._cross_attn_f32(X, qpos, ks["mem"], ks["pos"], ks["kmask"], lw, B, ks["Lk"])
         return self._ffn(X, lw)
 
     @torch.no_grad()
@@ -317,19 +314,27 @@ class HeadEngine:
         ks = self.key_side(x, img_metas, precision, taps)
         B = ks["B"]
         qpos = self.query_embeds(P)
-        X = torch.zeros((B * s.Lq, s.E), dtype=torch.float32, device=dev)
-        outs = torch.empty((s.L, B * s.Lq, s.E), dtype=torch.float32, device=dev)
+        time_div = _h2d(mean_time_stamp(img_metas), dev) if s.with_time else None
         if taps is not None:
             taps.update(query_embeds=qpos, layers=[])
-        for l in range(s.L):
-            X = self.decoder_layer(P, l, X, qpos, ks)
-            ops.layernorm(X, *P["post_norm"], nan_to_num=True, out=outs[l])
-            if taps is not None:
-                taps["layers"].append(X.clone())
-        time_div = None
-        if s.with_time:
-            time_div = _h2d(mean_time_stamp(img_metas), dev)
-        cls, box = self.branches(P, outs, B, time_div)
+        if precision == "bf16":
+            from . import engine_tc as tc
+            st = tc.initial_state(self, B, qpos, dev)
+            for l in range(s.L):
+                st = tc.decoder_layer_tc(self, P, l, st, qpos, ks, last=(l == s.L - 1))
+                if taps is not None:
+                    taps["layers"].append(st["X"].clone())
+            outs = st["outs"]
+            cls, box = tc.branches_tc(self, P, outs, st["outs_split"], B, time_div)
+        else:
+            X = torch.zeros((B * s.Lq, s.E), dtype=torch.float32, device=dev)
+            outs = torch.empty((s.L, B * s.Lq, s.E), dtype=torch.float32, device=dev)
+            for l in range(s.L):
+                X = self.decoder_layer(P, l, X, qpos, ks)
+                ops.layernorm(X, *P["post_norm"], nan_to_num=True, out=outs[l])
+                if taps is not None:
+                    taps["layers"].append(X.clone())
+            cls, box = self.branches(P, outs, B, time_div)
         if taps is not None:
             taps["outs_dec"] = outs.view(s.L, B, s.Lq, s.E)
         return dict(all_cls_scores=cls, all_bbox_preds=box, enc_cls_scores=None, enc_bbox_preds=None)

@@ -54,13 +54,18 @@ def choose_nsplit(B: int, heads: int, Lq: int, Lk: int) -> int:
 
 
 def packed_tc(eng, device) -> dict:
+    """bf16 weight copies for the tensor-core path: plain bf16 for the Lk-side GEMMs, [hi|hi|lo]
+    (ops.x3_weight) for the fp32-class query-side GEMMs."""
     P = eng.packed(device)
     if "tc" in P:
         return P["tc"]
     s = eng.spec
+    sd = P["sd"]
     E = s.E
     bf = torch.bfloat16
+    x3 = ops.x3_weight
     T = dict()
+    T["in_w"] = P["in_w"].to(bf).contiguous()
     if s.with_position:
         T["pe_w1"] = P["pe_w1"].to(bf).contiguous()
         T["pe_w2"] = P["pe_w2"].to(bf).contiguous()
@@ -70,6 +75,24 @@ def packed_tc(eng, device) -> dict:
     T["bk"] = torch.cat([lw["ca_in_b"][E:2 * E] for lw in P["layers"]], 0).contiguous()
     T["wv"] = torch.cat([lw["ca_in_w"][2 * E:] for lw in P["layers"]], 0).to(bf).contiguous()
     T["bv"] = torch.cat([lw["ca_in_b"][2 * E:] for lw in P["layers"]], 0).contiguous()
+    T["layers"] = []
+    for lw in P["layers"]:
+        T["layers"].append(dict(
+            sa_qk=x3(lw["sa_in_w"][:2 * E]), sa_qk_b=lw["sa_in_b"][:2 * E].contiguous(),
+            sa_v=x3(lw["sa_in_w"][2 * E:]), sa_v_b=lw["sa_in_b"][2 * E:].contiguous(),
+            sa_out=x3(lw["sa_out_w"]), ca_q=x3(lw["ca_in_w"][:E]), ca_q_b=lw["ca_in_b"][:E].contiguous(),
+            ca_out=x3(lw["ca_out_w"]), f1=x3(lw["f1_w"]), f2=x3(lw["f2_w"])))
+    nb = 1 if s.shared_branches else s.L
+    T["branches"] = []
+    for l in range(nb):
+        c, r = f"cls_branches.{l}.", f"reg_branches.{l}."
+        d = dict(cls=[x3(sd[f"{c}{3 * i}.weight"]) for i in range(s.num_reg_fcs)])
+        if s.with_multi:
+            d["reg"] = [x3(sd[f"{r}reg_branch.{3 * i}.weight"]) for i in range(s.num_reg_fcs)]
+            d["task0"] = x3(P[f"task_w0_{l}"])
+        else:
+            d["reg"] = [x3(sd[f"{r}{2 * i}.weight"]) for i in range(s.num_reg_fcs)]
+        T["branches"].append(d)
     P["tc"] = T
     return T
 
@@ -79,37 +102,44 @@ def key_side_tc(eng, x, img_metas, taps=None):
     K/V projection of all layers.  Returns the key-side state: Kh, Vh (L,B,heads,Lk,32) bf16,
     kmask (None when no key is padded), the split-KV plan."""
     s = eng.spec
+    if s.E != 256 or s.heads != 8:
+        raise NotImplementedError("tcgen05 path is specialised for embed_dims 256, 8 heads of 32")
     x = x.float().contiguous()
     B, N, Cin, H, W = x.shape
+    if Cin % 64 != 0:
+        raise NotImplementedError("tcgen05 path needs in_channels % 64 == 0")
     dev = x.device
     Lk = N * H * W
+    E = s.E
     P = eng.packed(dev)
     T = packed_tc(eng, dev)
     masks = eng.masks(img_metas, B, N, H, W, dev)
     has_mask = any_key_masked(img_metas, N, H, W)
-    vin = torch.empty((B * Lk, s.E), dtype=torch.bfloat16, device=dev)
-    mem = ops.gemm_f32(x, P["in_w"], P["in_b"], nchw_hw=H * W, out_bf16=vin)
+    # input_proj (petr_head.py:390): fp32 NCHW -> bf16 tokens -> tcgen05 GEMM; mem kept in fp32 (for
+    # the K input mem + pos) and as bf16 [hi | lo] whose hi half is the V-projection operand
+    xt = ops.nchw_to_tokens_bf16(x.view(B * N, Cin, H, W))
+    mem = torch.empty((B * Lk, E), dtype=torch.float32, device=dev)
+    mem_split = ops.gemm_bf16_tc(xt, T["in_w"], P["in_b"], split_out=True, out_f32=mem, name="gemm_input_proj")
+    vin = mem_split[:, :E]
     sf = ops.sine3d_features(masks, P["dim_t_sine"], dtype=torch.bfloat16, **_sine_args(s))
-    h2 = ops.gemm_bf16_tc(sf, T["ad_w1"], P["ad_b1"], act=ACT_RELU, out_dtype=torch.bfloat16)
+    h2 = ops.gemm_bf16_tc(sf, T["ad_w1"], P["ad_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_adapt1")
     if s.with_position:
         feat, _, _ = eng.frustum(img_metas, B, N, H, W, dev, None, torch.bfloat16, want_mask=False)
-        h1 = ops.gemm_bf16_tc(feat, T["pe_w1"], P["pe_b1"], act=ACT_RELU, out_dtype=torch.bfloat16)
+        h1 = ops.gemm_bf16_tc(feat, T["pe_w1"], P["pe_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_pe1")
         if s.with_fpe:
-            pos = ops.gemm_bf16_tc(h1, T["pe_w2"], P["pe_b2"])
+            pos = ops.gemm_bf16_tc(h1, T["pe_w2"], P["pe_b2"], name="gemm_pe2")
             se = ops.gemm_f32(mem, P["fpe_wr"], P["fpe_br"], act=ACT_RELU)
             pos = ops.gemm_f32(se, P["fpe_we"], P["fpe_be"], act=ACT_SIGMOID_GATE, gate=pos, residual=mem)
         else:
-            pos = ops.gemm_bf16_tc(h1, T["pe_w2"], P["pe_b2"], residual=mem)      # mem + position MLP
+            pos = ops.gemm_bf16_tc(h1, T["pe_w2"], P["pe_b2"], residual=mem, name="gemm_pe2")   # mem + position MLP
     else:
         pos = mem
-    kin = ops.gemm_bf16_tc(h2, T["ad_w2"], P["ad_b2"], residual=pos, out_dtype=torch.bfloat16)
-    Kh = ops.gemm_bf16_tc(kin, T["wk"], T["bk"], headsplit_Lk=Lk)
-    Vh = ops.gemm_bf16_tc(vin, T["wv"], T["bv"], headsplit_Lk=Lk)
+    kin = ops.gemm_bf16_tc(h2, T["ad_w2"], P["ad_b2"], residual=pos, out_dtype=torch.bfloat16, name="gemm_adapt2")
+    Kh = ops.gemm_bf16_tc(kin, T["wk"], T["bk"], headsplit_Lk=Lk, name="gemm_kproj")
+    Vh = ops.gemm_bf16_tc(vin, T["wv"], T["bv"], headsplit_Lk=Lk, name="gemm_vproj")
     if taps is not None:
         taps.update(masks=masks, memory=mem, kin=kin, Kh=Kh, Vh=Vh)
     kmask = masks.view(B, Lk) if has_mask else None
-    if s.E != 256 or s.heads != 8:
-        raise NotImplementedError("tcgen05 path is specialised for embed_dims 256, 8 heads of 32")
     nsplit = choose_nsplit(B, s.heads, s.Lq, Lk)
     partial = None
     if nsplit > 1:
@@ -124,16 +154,117 @@ def _sine_args(s):
                 eps=a["eps"], offset=a["offset"])
 
 
-def cross_attn_tc(eng, X, qpos, lw, l: int, ks: dict):
-    """Cross-attention block of decoder layer l on the tcgen05 path: fp32 Q projection ->
-    bf16 pack (scale folded) -> flash attention over the pre-projected K/V -> fp32 out-proj +
-    residual -> LayerNorm (petr_transformer.py:341-367)."""
+Q_SCALE = (1.0 / 32.0 ** 0.5) * 1.4426950408889634          # head_dim^-1/2 * log2(e)
+
+
+def decoder_layer_tc(eng, P, l: int, st: dict, qpos, ks: dict, last: bool) -> dict:
+    """One decoder layer on the tensor-core path.  `st` carries the residual stream in the forms
+    the next GEMMs need: X fp32 (R,E), Xs = split(X), Xps = split(X + query_pos) (bf16 [hi|lo]).
+    Every projection / FFN GEMM is a bf16x3 tcgen05 GEMM (fp32-class accuracy); the self-attention
+    core is the fp32 kernel; the cross-attention core is the bf16 flash kernel."""
     s = eng.spec
+    E, R, B = s.E, st["X"].shape[0], ks["B"]
+    lw = P["layers"][l]
+    tw = packed_tc(eng, st["X"].device)["layers"][l]
+    dev = st["X"].device
+    g = ops.gemm_bf16_tc
+    # ---- self-attention (mmcv MultiheadAttention; q = k = X + qpos, v = X) ----
+    qk = g(st["Xps"], tw["sa_qk"], tw["sa_qk_b"], x3=True, name="gemm_q_side")
+    v = g(st["Xs"], tw["sa_v"], tw["sa_v_b"], x3=True, name="gemm_q_side")
+    o_s = torch.empty((R, 2 * E), dtype=torch.bfloat16, device=dev)
+    ops.attention_f32(qk[:, :E], qk[:, E:], v, None, B, s.Lq, s.Lq, s.heads, out_split=o_s, want_f32=False)
+    y = g(o_s, tw["sa_out"], lw["sa_out_b"], residual=st["X"], x3=True, name="gemm_q_side")
+    X1 = torch.empty_like(y)
+    X1ps = torch.empty((R, 2 * E), dtype=torch.bfloat16, device=dev)
+    ops.layernorm_multi(y, *lw["ln"][0], qpos=qpos, Y=X1, Ypos_split=X1ps)
+    # ---- cross-attention (PETRMultiheadAttention) ----
+    qs = g(X1ps, tw["ca_q"], tw["ca_q_b"], x3=True, alpha=Q_SCALE, headsplit_Lk=s.Lq, name="gemm_q_side")
+    ops.cross_attention_bf16(qs[0], ks["Kh"][l], ks["Vh"][l], ks["kmask"], B, s.Lq, ks["Lk"], s.heads,
+                             ks["nsplit"], partial=ks["partial"], out_split=o_s, want_f32=False)
+    y = g(o_s, tw["ca_out"], lw["ca_out_b"], residual=X1, x3=True, name="gemm_q_side")
+    X2 = torch.empty_like(y)
+    X2s = torch.empty((R, 2 * E), dtype=torch.bfloat16, device=dev)
+    ops.layernorm_multi(y, *lw["ln"][1], Y=X2, Y_split=X2s)
+    # ---- FFN ----
+    hs = g(X2s, tw["f1"], lw["f1_b"], act=ACT_RELU, x3=True, split_out=True, name="gemm_q_side")
+    y = g(hs, tw["f2"], lw["f2_b"], residual=X2, x3=True, name="gemm_q_side")
+    X3 = torch.empty_like(y)
+    X3s = torch.empty((R, 2 * E), dtype=torch.bfloat16, device=dev)
+    X3ps = None if last else torch.empty((R, 2 * E), dtype=torch.bfloat16, device=dev)
+    ops.layernorm_multi(y, *lw["ln"][2], qpos=None if last else qpos, Y=X3, Y_split=X3s, Ypos_split=X3ps,
+                        gamma2=P["post_norm"][0], beta2=P["post_norm"][1], Z=st["outs"][l],
+                        Z_split=st["outs_split"][l])
+    return dict(X=X3, Xs=X3s, Xps=X3ps, outs=st["outs"], outs_split=st["outs_split"])
+
+
+def branches_tc(eng, P, outs, outs_split, B: int, time_div=None):
+    """cls / reg branches on the tensor-core path: the 256x256 layers are bf16x3 tcgen05 GEMMs on
+    the split post_norm outputs, the final 256 -> 10 layers and the box decode stay fp32 kernels
+    (petr_head.py:440-460)."""
+    s = eng.spec
+    sd = P["sd"]
+    L = outs.shape[0]
+    R = B * s.Lq
     E = s.E
-    B, Lk = ks["B"], ks["Lk"]
-    q = ops.gemm_f32(X, lw["ca_in_w"][:E], lw["ca_in_b"][:E], A2=qpos)
-    qs = ops.pack_q_bf16(q, B, s.Lq, s.heads)
-    o = ops.cross_attention_bf16(qs, ks["Kh"][l], ks["Vh"][l], ks["kmask"], B, s.Lq, Lk, s.heads,
-                                 ks["nsplit"], partial=ks["partial"])
-    y = ops.gemm_f32(o, lw["ca_out_w"], lw["ca_out_b"], residual=X)
-    return ops.layernorm(y, *lw["ln"][1], out=y)
+    T = packed_tc(eng, outs.device)
+    g = ops.gemm_bf16_tc
+    dev = outs.device
+    cls = torch.empty((L * R, s.cls_out), dtype=torch.float32, device=dev)
+    reg = torch.empty((L * R, s.code_size), dtype=torch.float32, device=dev)
+    groups = [(0, outs_split.view(L * R, 2 * E), slice(0, L * R))] if s.shared_branches else \
+        [(l, outs_split[l], slice(l * R, (l + 1) * R)) for l in range(L)]
+    for l, xs, rows in groups:
+        bw = T["branches"][0 if s.shared_branches else l]
+        c, r = f"cls_branches.{l}.", f"reg_branches.{l}."
+        n = xs.shape[0]
+        h = xs
+        yf = None
+        for i in range(s.num_reg_fcs):
+            y = g(h, bw["cls"][i], sd[f"{c}{3 * i}.bias"], x3=True, name="gemm_q_side")
+            h = torch.empty((n, 2 * E), dtype=torch.bfloat16, device=dev)
+            yf = torch.empty((n, E), dtype=torch.float32, device=dev)
+            ops.layernorm_multi(y, sd[f"{c}{3 * i + 1}.weight"], sd[f"{c}{3 * i + 1}.bias"], Y=yf, Y_split=h, relu=True)
+        j = 3 * s.num_reg_fcs
+        ops.gemm_f32(yf, sd[f"{c}{j}.weight"], sd[f"{c}{j}.bias"], out=cls[rows])
+        if s.with_multi:
+            h = xs
+            for i in range(s.num_reg_fcs):
+                h = g(h, bw["reg"][i], sd[f"{r}reg_branch.{3 * i}.bias"], act=ACT_RELU, x3=True, split_out=True,
+                      name="gemm_q_side")
+            t = g(h, bw["task0"], P[f"task_b0_{l}"], act=ACT_RELU, x3=True, name="gemm_q_side")      # (n, 5E) fp32
+            c0 = 0
+            for k in range(5):
+                w = sd[f"{r}task_heads.{k}.2.weight"]
+                ops.gemm_f32(t[:, k * E:(k + 1) * E], w, sd[f"{r}task_heads.{k}.2.bias"],
+                             out=reg[rows][:, c0:c0 + w.shape[0]])
+                c0 += w.shape[0]
+        else:
+            h = xs
+            for i in range(s.num_reg_fcs):
+                lastfc = i == s.num_reg_fcs - 1
+                if lastfc:
+                    h = g(h, bw["reg"][i], sd[f"{r}{2 * i}.bias"], act=ACT_RELU, x3=True, name="gemm_q_side")
+                else:
+                    h = g(h, bw["reg"][i], sd[f"{r}{2 * i}.bias"], act=ACT_RELU, x3=True, split_out=True,
+                          name="gemm_q_side")
+            j = 2 * s.num_reg_fcs
+            ops.gemm_f32(h, sd[f"{r}{j}.weight"], sd[f"{r}{j}.bias"], out=reg[rows])
+    ops.decode_boxes(reg, P["ref"], s.pc_range, time_div, L, B, s.Lq)
+    return cls.view(L, B, s.Lq, s.cls_out), reg.view(L, B, s.Lq, s.code_size)
+
+
+def initial_state(eng, B: int, qpos, dev) -> dict:
+    s = eng.spec
+    R = B * s.Lq
+    X = torch.zeros((R, s.E), dtype=torch.float32, device=dev)
+    Xs = torch.zeros((R, 2 * s.E), dtype=torch.bfloat16, device=dev)
+    Xps = ops.split_rows(X, add=qpos)
+    outs = torch.empty((s.L, R, s.E), dtype=torch.float32, device=dev)
+    outs_split = torch.empty((s.L, R, 2 * s.E), dtype=torch.bfloat16, device=dev)
+    return dict(X=X, Xs=Xs, Xps=Xps, outs=outs, outs_split=outs_split)
+
+
+def state_from_rows(eng, X, qpos, st_like: dict) -> dict:
+    """Teacher-forcing helper (tests): rebuild the split forms of an externally supplied X."""
+    return dict(X=X, Xs=ops.split_rows(X), Xps=ops.split_rows(X, add=qpos), outs=st_like["outs"],
+                outs_split=st_like["outs_split"])

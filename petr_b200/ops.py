@@ -18,6 +18,26 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID_GATE = 0, 1, 2
 A_ROWMAJOR, A_NCHW = 0, 1
 
 
+# Optional live kernel timing (bench.py roofline): name -> list of (start, end) CUDA events
+# recorded on the launching stream around the named launches.
+KERNEL_TIMERS = None
+
+
+class _Timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if KERNEL_TIMERS is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+
+    def __exit__(self, *a):
+        if KERNEL_TIMERS is not None:
+            self.ev[1].record()
+            KERNEL_TIMERS.setdefault(self.name, []).append(self.ev)
+
+
 def _cuda(t: torch.Tensor, name: str):
     if not t.is_cuda:
         raise RuntimeError(f"petr_b200: {name} must be a CUDA tensor (no CPU fallback)")
@@ -117,16 +137,51 @@ def gemm_f32(A: torch.Tensor, W: torch.Tensor, bias=None, *, A2=None, residual=N
     return out if out is not None else out_bf16
 
 
-def attention_f32(Q, K, V, key_mask, B: int, Lq: int, Lk: int, heads: int, out=None) -> torch.Tensor:
-    """softmax(Q K^T / sqrt(d) + mask) V; Q rows b*Lq+q, K/V rows b*Lk+k, head_dim 32."""
+def attention_f32(Q, K, V, key_mask, B: int, Lq: int, Lk: int, heads: int, out=None,
+                  out_split=None, want_f32: bool = True) -> torch.Tensor:
+    """softmax(Q K^T / sqrt(d) + mask) V; Q rows b*Lq+q, K/V rows b*Lk+k, head_dim 32.
+    out_split: optional bf16 (B*Lq, 2E) [hi | lo] copy of the result."""
     _cuda(Q, "Q")
     d = 32
     E = heads * d
-    if out is None:
+    if out is None and want_f32:
         out = torch.empty((B * Lq, E), dtype=torch.float32, device=Q.device)
-    call("petr_attention_f32", ptr(Q), Q.stride(0), ptr(K), K.stride(0), ptr(V), V.stride(0),
-         ptr(key_mask), ptr(out), out.stride(0), B, Lq, Lk, heads, d, 1.0 / math.sqrt(d),
-         stream_ptr(Q.device))
+    with _Timed("attention_f32"):
+        call("petr_attention_f32", ptr(Q), Q.stride(0), ptr(K), K.stride(0), ptr(V), V.stride(0),
+             ptr(key_mask), ptr(out), out.stride(0) if out is not None else 0, ptr(out_split),
+             B, Lq, Lk, heads, d, 1.0 / math.sqrt(d), stream_ptr(Q.device))
+    return out if out is not None else out_split
+
+
+def layernorm_multi(X, gamma, beta, *, eps=1e-5, qpos=None, Y=None, Y_split=None, Ypos_split=None,
+                    gamma2=None, beta2=None, Z=None, Z_split=None, relu=False):
+    """Fused LayerNorm with optional fp32 / split-bf16 / (+qpos) / second-LN outputs (E = 256)."""
+    _cuda(X, "X")
+    assert X.is_contiguous() and X.shape[-1] == 256
+    rows = X.numel() // 256
+    call("petr_layernorm_multi_f32", ptr(X), ptr(gamma), ptr(beta), float(eps), ptr(qpos),
+         qpos.shape[0] if qpos is not None else 0, ptr(Y), ptr(Y_split), ptr(Ypos_split),
+         ptr(gamma2), ptr(beta2), ptr(Z), ptr(Z_split), rows, 256, int(relu), stream_ptr(X.device))
+
+
+def split_rows(X, add=None, relu=False, out=None) -> torch.Tensor:
+    """fp32 (R,E) -> bf16 (R,2E) [hi | lo] of relu?(X + add[r % add_rows])."""
+    _cuda(X, "X")
+    R, E = X.shape
+    if out is None:
+        out = torch.empty((R, 2 * E), dtype=torch.bfloat16, device=X.device)
+    call("petr_split_rows_bf16", ptr(X), X.stride(0), ptr(add), add.shape[0] if add is not None else 0,
+         ptr(out), R, E, int(relu), stream_ptr(X.device))
+    return out
+
+
+def nchw_to_tokens_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 (G,C,h,w) contiguous -> bf16 (G*h*w, C)."""
+    _cuda(x, "x")
+    assert x.is_contiguous() and x.dim() == 4
+    G, C, h, w = x.shape
+    out = torch.empty((G * h * w, C), dtype=torch.bfloat16, device=x.device)
+    call("petr_nchw_to_tokens_bf16", ptr(x), ptr(out), G, C, h * w, stream_ptr(x.device))
     return out
 
 
@@ -163,29 +218,57 @@ def reset_launch_count():
 OUT_F32, OUT_BF16, OUT_HEADSPLIT = 0, 1, 2
 
 
+def x3_weight(W: torch.Tensor) -> torch.Tensor:
+    """fp32 (N,K) -> bf16 (N,3K) = [W_hi | W_hi | W_lo], the W operand of a bf16x3 GEMM."""
+    hi = W.to(torch.bfloat16)
+    lo = (W - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, hi, lo], 1).contiguous()
+
+
+OUT_SPLIT = 3
+
+
 def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, act=ACT_NONE,
-                 out=None, out_dtype=torch.float32, headsplit_Lk: int = 0) -> torch.Tensor:
-    """C = epi(A @ W.T + bias) (+ residual) on tcgen05; A (M,K) bf16, W (N,K) bf16, K % 64 == 0.
-    headsplit_Lk > 0: bf16 output in the [N/256][B][8][Lk][32] K/V layout."""
+                 alpha: float = 1.0, out=None, out_dtype=torch.float32, headsplit_Lk: int = 0,
+                 split_out: bool = False, out_f32=None, x3: bool = False, name: str = "gemm_bf16_tc"):
+    """C = alpha * act(A @ W.T + bias) (+ residual) on tcgen05; A (M,Ka) bf16, W (N,K) bf16.
+    x3: A is a split (M, 2*K0) [hi | lo] activation and W an x3_weight (N, 3*K0).
+    headsplit_Lk > 0: bf16 output in the [N/256][B][8][Lk][32] Q/K/V layout.
+    split_out: bf16 (M, 2N) [hi | lo] output (+ optional fp32 copy out_f32)."""
     _cuda(A, "A")
     assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
     assert A.dim() == 2 and A.stride(1) == 1 and W.dim() == 2 and W.stride(1) == 1
-    M, K = A.shape
-    N = W.shape[0]
+    M = A.shape[0]
+    N, K = W.shape
+    wrap = 0
+    if x3:
+        assert 3 * A.shape[1] == 2 * K, (A.shape, W.shape)
+        wrap = A.shape[1]
+    else:
+        assert A.shape[1] == K
+    C2 = None
     if headsplit_Lk > 0:
         B = M // headsplit_Lk
         if out is None:
             out = torch.empty((N // 256, B, 8, headsplit_Lk, 32), dtype=torch.bfloat16, device=A.device)
         mode, ldc = OUT_HEADSPLIT, 0
+    elif split_out:
+        if out is None:
+            out = torch.empty((M, 2 * N), dtype=torch.bfloat16, device=A.device)
+        mode = OUT_SPLIT
+        C2 = out_f32
+        ldc = C2.stride(0) if C2 is not None else (residual.stride(0) if residual is not None else N)
     else:
         if out is None:
             out = torch.empty((M, N), dtype=out_dtype, device=A.device)
         mode = OUT_F32 if out.dtype == torch.float32 else OUT_BF16
         ldc = out.stride(0)
-        if residual is not None:
-            assert residual.dtype == torch.float32 and residual.stride(0) == ldc
-    call("petr_gemm_bf16_tc", ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), ptr(residual), act,
-         ptr(out), ldc, mode, M, N, K, int(headsplit_Lk), stream_ptr(A.device))
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(0) == ldc and residual.stride(1) == 1
+    with _Timed(name):
+        call("petr_gemm_bf16_tc", ptr(A), A.stride(0), wrap, ptr(W), W.stride(0), ptr(bias), ptr(residual),
+             act, float(alpha), ptr(out), ptr(C2), ldc, mode, M, N, K, int(headsplit_Lk),
+             stream_ptr(A.device))
     return out
 
 
@@ -203,28 +286,9 @@ def attention_partial_floats(B: int, Lq: int, heads: int) -> int:
     return int(_lib.lib().petr_attention_partial_floats(B, Lq, heads))
 
 
-# Optional live kernel timing (bench.py roofline): name -> list of (start, end) CUDA events
-# recorded on the launching stream around the named launches.
-KERNEL_TIMERS = None
-
-
-class _Timed:
-    def __init__(self, name):
-        self.name = name
-
-    def __enter__(self):
-        if KERNEL_TIMERS is not None:
-            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            self.ev[0].record()
-
-    def __exit__(self, *a):
-        if KERNEL_TIMERS is not None:
-            self.ev[1].record()
-            KERNEL_TIMERS.setdefault(self.name, []).append(self.ev)
-
-
 def cross_attention_bf16(Qs, Kh, Vh, key_mask, B: int, Lq: int, Lk: int, heads: int, nsplit: int = 1,
-                         out=None, partial=None, write_partial: bool = False):
+                         out=None, partial=None, write_partial: bool = False, out_split=None,
+                         want_f32: bool = True):
     """Flash cross-attention on tcgen05.  Returns O fp32 (B*Lq, heads*32), or the partial
     buffer when write_partial."""
     _cuda(Qs, "Qs")
@@ -232,19 +296,22 @@ def cross_attention_bf16(Qs, Kh, Vh, key_mask, B: int, Lq: int, Lk: int, heads: 
     if (nsplit > 1 or write_partial) and partial is None:
         partial = torch.empty((nsplit * attention_partial_floats(B, Lq, heads),), dtype=torch.float32,
                               device=Qs.device)
-    if not write_partial and out is None:
+    if not write_partial and out is None and want_f32:
         out = torch.empty((B * Lq, heads * 32), dtype=torch.float32, device=Qs.device)
     with _Timed("cross_attention_bf16"):
         call("petr_cross_attention_bf16", ptr(Qs), ptr(Kh), ptr(Vh), ptr(key_mask), ptr(out),
-             out.stride(0) if out is not None else 0, ptr(partial), B, Lq, Lk, heads, nsplit,
-             int(write_partial), stream_ptr(Qs.device))
-    return partial if write_partial else out
+             out.stride(0) if out is not None else 0, ptr(out_split), ptr(partial), B, Lq, Lk, heads,
+             nsplit, int(write_partial), stream_ptr(Qs.device))
+    if write_partial:
+        return partial
+    return out if out is not None else out_split
 
 
-def attention_merge(partial: torch.Tensor, nparts: int, B: int, Lq: int, heads: int, out=None):
+def attention_merge(partial: torch.Tensor, nparts: int, B: int, Lq: int, heads: int, out=None,
+                    out_split=None, want_f32: bool = True):
     _cuda(partial, "partial")
-    if out is None:
+    if out is None and want_f32:
         out = torch.empty((B * Lq, heads * 32), dtype=torch.float32, device=partial.device)
-    call("petr_attention_merge", ptr(partial), nparts, ptr(out), out.stride(0), B, Lq, heads,
-         stream_ptr(partial.device))
-    return out
+    call("petr_attention_merge", ptr(partial), nparts, ptr(out), out.stride(0) if out is not None else 0,
+         ptr(out_split), B, Lq, heads, stream_ptr(partial.device))
+    return out if out is not None else out_split

@@ -77,18 +77,26 @@ def test_decoder_layers_teacher_forced(name, precision, tol):
     qpos = eng.query_embeds(P)
     s = eng.spec
     B = feats.shape[0]
-    outs = torch.empty((s.L, B * s.Lq, s.E), device=DEV)
+    from petr_b200 import engine_tc as tc
+    st0 = tc.initial_state(eng, B, qpos, DEV)
+    outs = st0["outs"]
     for l in range(s.L):
         if l == 0:
             X = torch.zeros((B * s.Lq, s.E), device=DEV)
         else:
             X = taps["layers"][l - 1]["out"].transpose(0, 1).reshape(B * s.Lq, s.E).contiguous().to(DEV)
-        Y = eng.decoder_layer(P, l, X, qpos, ks)
+        if precision == "fp32":
+            Y = eng.decoder_layer(P, l, X, qpos, ks)
+            ops.layernorm(Y, *P["post_norm"], nan_to_num=True, out=outs[l])
+        else:
+            Y = tc.decoder_layer_tc(eng, P, l, tc.state_from_rows(eng, X, qpos, st0), qpos, ks, last=False)["X"]
         yref = taps["layers"][l]["out"].transpose(0, 1).reshape(B * s.Lq, s.E)
         ok = ~torch.isnan(yref).any(1)
         assert (Y.cpu()[ok] - yref[ok]).abs().max() <= (5e-4 if precision == "fp32" else 5e-2), l
-        ops.layernorm(Y, *P["post_norm"], nan_to_num=True, out=outs[l])
-    cls, box = eng.branches(P, outs, B, None)
+    if precision == "fp32":
+        cls, box = eng.branches(P, outs, B, None)
+    else:
+        cls, box = tc.branches_tc(eng, P, outs, st0["outs_split"], B, None)
     assert (cls.cpu() - ref["all_cls_scores"]).abs().max() <= tol
     assert (box.cpu() - ref["all_bbox_preds"]).abs().max() <= tol
 

@@ -209,6 +209,81 @@ def test_gemm_bf16_tc(M, N, K):
     assert (gb.float() - torch.relu(ref)).abs().max() <= 0.05
 
 
+@pytest.mark.parametrize("M,N,K0", [(900, 256, 256), (3600, 2048, 256), (1000, 256, 2048), (130, 512, 192)])
+def test_gemm_bf16x3_fp32_class(M, N, K0):
+    """A = [hi | lo], W = [hi | hi | lo]: the bf16x3 product must be fp32-class (~2^-16)."""
+    g = torch.Generator().manual_seed(M + N + K0)
+    A = torch.randn(M, K0, generator=g).to(DEV)
+    W = (torch.randn(N, K0, generator=g) / math.sqrt(K0)).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    ref = (A.double() @ W.double().T + b.double()).float()
+    As = ops.split_rows(A)
+    assert (As[:, :K0].float() + As[:, K0:].float() - A).abs().max() <= 2e-5 * A.abs().max()
+    W3 = ops.x3_weight(W)
+    got = ops.gemm_bf16_tc(As, W3, b, x3=True)
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max() <= 4e-5 * scale, (got - ref).abs().max()
+    # relu + residual + split output with fp32 copy
+    f32 = torch.empty(M, N, device=DEV)
+    sp = ops.gemm_bf16_tc(As, W3, b, x3=True, act=ops.ACT_RELU, residual=res, split_out=True, out_f32=f32)
+    ref2 = torch.relu(ref) + res
+    assert (f32 - ref2).abs().max() <= 4e-5 * scale
+    assert (sp[:, :N].float() + sp[:, N:].float() - ref2).abs().max() <= 6e-5 * scale
+    # alpha + head-split (the Q projection form)
+    if N == 256 and M % 100 == 0:
+        hs = ops.gemm_bf16_tc(As, W3, b, x3=True, alpha=0.25, headsplit_Lk=100)
+        refh = (0.25 * ref).view(M // 100, 100, 8, 32).permute(0, 2, 1, 3)
+        assert (hs[0].float() - refh).abs().max() <= 0.02 * max(1.0, 0.25 * scale)
+
+
+def test_layernorm_multi_split_rows_nchw():
+    g = torch.Generator().manual_seed(2)
+    R, E, Lq = 700, 256, 100
+    X = (torch.randn(R, E, generator=g) * 2 + 0.5).to(DEV)
+    qpos = torch.randn(Lq, E, generator=g).to(DEV)
+    g1, b1, g2, b2 = (torch.randn(E, generator=g).to(DEV) for _ in range(4))
+    Y = torch.empty(R, E, device=DEV); Z = torch.empty(R, E, device=DEV)
+    Ys, Yps, Zs = (torch.empty(R, 2 * E, dtype=torch.bfloat16, device=DEV) for _ in range(3))
+    Xn = X.clone(); Xn[3] = float("nan")
+    ops.layernorm_multi(Xn, g1, b1, qpos=qpos, Y=Y, Y_split=Ys, Ypos_split=Yps, gamma2=g2, beta2=b2, Z=Z, Z_split=Zs)
+    yref = torch.nn.functional.layer_norm(X, (E,), g1, b1, 1e-5)
+    zref = torch.nn.functional.layer_norm(yref, (E,), g2, b2, 1e-5)
+    ok = torch.ones(R, dtype=torch.bool, device=DEV); ok[3] = False
+    assert (Y[ok] - yref[ok]).abs().max() <= 2e-5 and (Z[ok] - zref[ok]).abs().max() <= 5e-5
+    assert torch.isnan(Y[3]).all() and Z[3].abs().max() == 0 and Zs[3].float().abs().max() == 0
+    yp = yref + qpos[torch.arange(R, device=DEV) % Lq]
+    for sp, r in ((Ys, yref), (Yps, yp), (Zs, zref)):
+        assert (sp[ok][:, :E].float() + sp[ok][:, E:].float() - r[ok]).abs().max() <= 1e-4
+    ops.layernorm_multi(X, g1, b1, Y=Y, relu=True)
+    assert (Y - torch.relu(yref)).abs().max() <= 2e-5
+    sp = ops.split_rows(X, add=qpos, relu=True)
+    r = torch.relu(X + qpos[torch.arange(R, device=DEV) % Lq])
+    assert (sp[:, :E].float() + sp[:, E:].float() - r).abs().max() <= 1e-4
+    x = torch.randn(5, 70, 6, 11, generator=g).to(DEV)
+    t = ops.nchw_to_tokens_bf16(x)
+    assert torch.equal(t, x.permute(0, 2, 3, 1).reshape(-1, 70).to(torch.bfloat16))
+
+
+def test_attention_split_outputs():
+    B, Lq, Lk = 2, 100, 260
+    g = torch.Generator().manual_seed(4)
+    Q = torch.randn(B * Lq, 256, generator=g).to(DEV)
+    K = torch.randn(B * Lk, 256, generator=g).to(DEV)
+    V = torch.randn(B * Lk, 256, generator=g).to(DEV)
+    ref = _attn_ref(Q, K, V, None, B, Lq, Lk, 8)
+    sp = torch.empty(B * Lq, 512, dtype=torch.bfloat16, device=DEV)
+    ops.attention_f32(Q, K, V, None, B, Lq, Lk, 8, out_split=sp, want_f32=False)
+    assert (sp[:, :256].float() + sp[:, 256:].float() - ref).abs().max() <= 1e-4
+    qs, Kh, Vh, s = _flash_inputs(B, Lq, Lk, 2.0, 3)
+    ref = (torch.softmax(s, -1) @ Vh.double()).transpose(1, 2).reshape(B * Lq, 256).float()
+    for ns in (1, 2):
+        f32 = torch.empty(B * Lq, 256, device=DEV)
+        ops.cross_attention_bf16(qs, Kh, Vh, None, B, Lq, Lk, 8, ns, out=f32, out_split=sp)
+        assert (f32 - ref).abs().max() <= 1e-2
+        assert (sp[:, :256].float() + sp[:, 256:].float() - f32).abs().max() <= 1e-4
+
+
 def test_gemm_bf16_tc_headsplit():
     B, Lk, K = 2, 200, 256
     g = torch.Generator().manual_seed(9)
