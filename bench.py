@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-samples", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print per-op CUDA-event times to stderr")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -197,7 +198,6 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ops.KERNEL_TIMERS = {}
     ops.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -209,8 +209,15 @@ def main():
     launches = ops.launch_count()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    timers = ops.KERNEL_TIMERS
-    ops.KERNEL_TIMERS = None
+    # second, separately timed pass with per-launch CUDA events (kept out of `value`: the event
+    # records add host overhead per launch)
+    from petr_b200 import _lib
+    _lib.TIMERS = {}
+    for _ in range(args.steps):
+        out = head([x_dev], metas)
+    torch.cuda.synchronize()
+    timers = _lib.TIMERS
+    _lib.TIMERS = None
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1000.0)
 
@@ -240,6 +247,11 @@ def main():
     # ---- roofline of the dominant kernel (flash cross-attention) ------------------------------
     peaks = load_peaks()
     roofline = None
+    breakdown = None
+    if timers:
+        breakdown = {k: dict(ms_per_step=float(sum(a.elapsed_time(b) for a, b in v)) / args.steps,
+                             launches_per_step=len(v) / args.steps) for k, v in timers.items()}
+        breakdown = dict(sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"]))
     if timers and timers.get("cross_attention_bf16"):
         evs = timers["cross_attention_bf16"]
         avg_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
@@ -272,6 +284,10 @@ def main():
                     e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=int(h2d),
                              d2h_bytes_per_step=int(d2h)),
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline, cpu_baseline=cpu)
+        if args.breakdown and breakdown:
+            sys.stderr.write("per-op breakdown (ms per step, CUDA events):\n")
+            for k, v in breakdown.items():
+                sys.stderr.write(f"  {k:32s} {v['ms_per_step']:9.3f} ms  x{v['launches_per_step']:.0f}\n")
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -83,8 +83,22 @@ def check(rc: int, name: str):
         raise RuntimeError(f"{name} failed with code {rc}: {msg}")
 
 
+# Optional live timing (bench.py roofline / --breakdown): when TIMERS is a dict, every C-ABI call
+# is bracketed by CUDA events recorded on torch's current stream; key = LABEL (set by the ops
+# wrapper for named GEMMs) or the entry-point name.
+TIMERS = None
+LABEL = None
+
+
 def call(name: str, *args):
+    if TIMERS is None:
+        check(getattr(lib(), name)(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(lib(), name)(*args), name)
+    e1.record()
+    TIMERS.setdefault(LABEL or name, []).append((e0, e1))
 
 
 def launch_count() -> int:

@@ -109,5 +109,8 @@ WORKLOADS = {
         # small shapes for fast tests (not BASELINE configs)
         Workload('tiny', 'PETRHead', 2, 64, 4, 10, 64, 160),
         Workload('tiny-v2', 'PETRv2Head', 12, 64, 4, 10, 64, 160),
+        # 1500-key shapes: small enough for the CPU oracle, enough keys for bf16 statistics
+        Workload('small', 'PETRHead', 6, 64, 10, 25, 160, 400),
+        Workload('small-v2', 'PETRv2Head', 12, 64, 5, 25, 80, 400),
     ]
 }

@@ -362,9 +362,11 @@ gemm_f32_kernel(GemmParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// fp32 flash-style attention, head_dim 32.  One thread per query row; keys staged in smem.
+// fp32 flash-style attention, head_dim 32.  A quad of 4 lanes owns one query row: lane `sub`
+// streams keys k = sub (mod 4) of every smem tile with its own online-softmax state (m, l, o[32]);
+// the four states are merged with warp shuffles at the end.  128 threads = 32 queries per block.
 // ------------------------------------------------------------------------------------------
-constexpr int ATT_THREADS = 64, ATT_KT = 64;
+constexpr int ATT_THREADS = 128, ATT_QPB = 32, ATT_KT = 64;
 
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk,
@@ -375,13 +377,19 @@ attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restri
     __shared__ __align__(16) float sV[ATT_KT][32];
     __shared__ float sBias[ATT_KT];
     const int head = blockIdx.y, b = blockIdx.z;
-    const int q = blockIdx.x * ATT_THREADS + threadIdx.x;
+    const int sub = threadIdx.x & 3;
+    const int q = blockIdx.x * ATT_QPB + (threadIdx.x >> 2);
     const bool live = q < Lq;
     float qv[32], o[32];
     {
         const float* qp = Q + ((int64_t)b * Lq + (live ? q : 0)) * ldq + head * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { qv[i] = qp[i] * scale_log2; o[i] = 0.f; }
+        for (int i = 0; i < 32; i += 4) {
+            float4 t = *reinterpret_cast<const float4*>(qp + i);
+            qv[i] = t.x * scale_log2; qv[i + 1] = t.y * scale_log2;
+            qv[i + 2] = t.z * scale_log2; qv[i + 3] = t.w * scale_log2;
+            o[i] = o[i + 1] = o[i + 2] = o[i + 3] = 0.f;
+        }
     }
     float m = -INFINITY, l = 0.f;
     const float* Kb = K + (int64_t)b * Lk * ldk + head * 32;
@@ -404,19 +412,23 @@ attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restri
         }
         __syncthreads();
 #pragma unroll 1
-        for (int r0 = 0; r0 < ATT_KT; r0 += 8) {
+        for (int g = 0; g < ATT_KT / 32; ++g) {          // 8 keys per lane per group
             float s[8];
             float mx = m;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float a = 0.f;
+                const int r = g * 32 + j * 4 + sub;
+                float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    float4 kk = *reinterpret_cast<const float4*>(&sK[r0 + j][i]);
-                    a = fmaf(qv[i], kk.x, a); a = fmaf(qv[i + 1], kk.y, a);
-                    a = fmaf(qv[i + 2], kk.z, a); a = fmaf(qv[i + 3], kk.w, a);
+                for (int i = 0; i < 32; i += 8) {
+                    float4 k0v = *reinterpret_cast<const float4*>(&sK[r][i]);
+                    float4 k1v = *reinterpret_cast<const float4*>(&sK[r][i + 4]);
+                    a0 = fmaf(qv[i], k0v.x, a0); a0 = fmaf(qv[i + 1], k0v.y, a0);
+                    a0 = fmaf(qv[i + 2], k0v.z, a0); a0 = fmaf(qv[i + 3], k0v.w, a0);
+                    a1 = fmaf(qv[i + 4], k1v.x, a1); a1 = fmaf(qv[i + 5], k1v.y, a1);
+                    a1 = fmaf(qv[i + 6], k1v.z, a1); a1 = fmaf(qv[i + 7], k1v.w, a1);
                 }
-                s[j] = a + sBias[r0 + j];
+                s[j] = (a0 + a1) + sBias[r];
                 mx = fmaxf(mx, s[j]);
             }
             if (mx == -INFINITY) continue;             // everything so far masked
@@ -427,33 +439,52 @@ attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restri
             for (int i = 0; i < 32; ++i) o[i] *= alpha;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
+                const int r = g * 32 + j * 4 + sub;
                 float pj = exp2f(s[j] - mx);
                 l += pj;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    float4 vv = *reinterpret_cast<const float4*>(&sV[r0 + j][i]);
+                    float4 vv = *reinterpret_cast<const float4*>(&sV[r][i]);
                     o[i] = fmaf(pj, vv.x, o[i]); o[i + 1] = fmaf(pj, vv.y, o[i + 1]);
                     o[i + 2] = fmaf(pj, vv.z, o[i + 2]); o[i + 3] = fmaf(pj, vv.w, o[i + 3]);
                 }
             }
         }
     }
+    // merge the quad's four partial states (xor 1, xor 2 stay inside the quad)
+#pragma unroll
+    for (int off = 1; off <= 2; off <<= 1) {
+        float m2 = __shfl_xor_sync(0xffffffffu, m, off);
+        float l2 = __shfl_xor_sync(0xffffffffu, l, off);
+        float mn = fmaxf(m, m2);
+        float w1 = (m == -INFINITY) ? 0.f : exp2f(m - mn);
+        float w2 = (m2 == -INFINITY) ? 0.f : exp2f(m2 - mn);
+        l = l * w1 + l2 * w2;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float o2 = __shfl_xor_sync(0xffffffffu, o[i], off);
+            o[i] = o[i] * w1 + o2 * w2;
+        }
+        m = mn;
+    }
     if (live) {
-        float inv = 1.f / l;                           // l == 0 (all keys masked) -> NaN, as torch
+        const float inv = 1.f / l;                     // l == 0 (all keys masked) -> NaN, as torch
+        // lane `sub` writes dims [8*sub, 8*sub+8)
+        float r8[8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] *= inv;
+        for (int i = 0; i < 32; ++i) if ((i >> 3) == sub) r8[i & 7] = o[i] * inv;
         if (O) {
-            float* op = O + ((int64_t)b * Lq + q) * ldo + head * 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) op[i] = o[i];
+            float* op = O + ((int64_t)b * Lq + q) * ldo + head * 32 + sub * 8;
+            *reinterpret_cast<float4*>(op) = make_float4(r8[0], r8[1], r8[2], r8[3]);
+            *reinterpret_cast<float4*>(op + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
         }
         if (O_split) {                                 // bf16 [hi | lo] rows of width 2E (bf16x3 GEMM input)
-            __nv_bfloat16* sp = O_split + ((int64_t)b * Lq + q) * (2 * E) + head * 32;
+            __nv_bfloat16* sp = O_split + ((int64_t)b * Lq + q) * (2 * E) + head * 32 + sub * 8;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                __nv_bfloat16 hi = __float2bfloat16_rn(o[i]);
+            for (int i = 0; i < 8; ++i) {
+                __nv_bfloat16 hi = __float2bfloat16_rn(r8[i]);
                 sp[i] = hi;
-                sp[E + i] = __float2bfloat16_rn(o[i] - __bfloat162float(hi));
+                sp[E + i] = __float2bfloat16_rn(r8[i] - __bfloat162float(hi));
             }
         }
     }
@@ -708,9 +739,10 @@ extern "C" int petr_attention_f32(const float* Q, int ldq, const float* K, int l
     PETR_REQUIRE(Q && K && V && (O || O_split), PETR_E_BADARG, "petr_attention_f32: null pointer");
     PETR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0, PETR_E_BADARG, "petr_attention_f32: bad dimension");
     PETR_REQUIRE(head_dim == 32, PETR_E_SHAPE, "petr_attention_f32: head_dim must be 32, got %d", head_dim);
-    PETR_REQUIRE((ldk & 3) == 0 && (ldv & 3) == 0 && aligned16(K) && aligned16(V), PETR_E_ALIGN,
-                 "petr_attention_f32: K/V rows must be 16-byte aligned");
-    dim3 grid((Lq + ATT_THREADS - 1) / ATT_THREADS, heads, B);
+    PETR_REQUIRE((ldk & 3) == 0 && (ldv & 3) == 0 && aligned16(K) && aligned16(V) && (ldq & 3) == 0 && aligned16(Q),
+                 PETR_E_ALIGN, "petr_attention_f32: Q/K/V rows must be 16-byte aligned");
+    if (O) PETR_REQUIRE((ldo & 3) == 0 && aligned16(O), PETR_E_ALIGN, "petr_attention_f32: O rows must be 16-byte aligned");
+    dim3 grid((Lq + ATT_QPB - 1) / ATT_QPB, heads, B);
     attention_f32_kernel<<<grid, ATT_THREADS, 0, (cudaStream_t)stream>>>(
         Q, ldq, K, ldk, V, ldv, key_mask, O, ldo, (__nv_bfloat16*)O_split, heads * 32, Lq, Lk,
         scale * 1.4426950408889634f);

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace petr {
 namespace {
@@ -48,6 +49,49 @@ struct AttParams {
     float* partial;            // [nsplit][rows*32 O | rows*2 (m,l)], rows = B*heads*Lq
     int B, Lq, Lk, heads, nsplit, tiles_total, write_partial;
 };
+
+// Output of one query row: un-normalised partial (O, m, l) or normalised fp32 / split-bf16 row.
+__device__ __forceinline__ void write_attention_row(const AttParams& p, float* o, float m_use, float l,
+                                                    int b, int h, int bh, int q, int split) {
+    if (p.write_partial) {
+        const int64_t prow_i = (int64_t)bh * p.Lq + q;
+        const int64_t rows = (int64_t)p.B * p.heads * p.Lq;
+        float* pbase = p.partial + (int64_t)split * rows * 34;
+        float* po = pbase + prow_i * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(po + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+        float* pm = pbase + rows * 32 + prow_i * 2;
+        pm[0] = m_use; pm[1] = l;
+        return;
+    }
+    const float inv = 1.f / l;          // l == 0 (all keys masked) -> NaN like torch
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] *= inv;
+    if (p.O) {
+        float* op = p.O + ((int64_t)b * p.Lq + q) * p.ldo + h * HD;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(op + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+    }
+    if (p.O_split) {
+        const int E = p.heads * HD;
+        __nv_bfloat16* sp = p.O_split + ((int64_t)b * p.Lq + q) * (2 * E) + h * HD;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            float h0 = __bfloat162float(__float2bfloat16_rn(o[i]));
+            float h1 = __bfloat162float(__float2bfloat16_rn(o[i + 1]));
+            hi[i >> 1] = pack_bf16x2(h0, h1);
+            lo[i >> 1] = pack_bf16x2(o[i] - h0, o[i + 1] - h1);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            *reinterpret_cast<uint4*>(sp + 2 * i) = make_uint4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]);
+            *reinterpret_cast<uint4*>(sp + E + 2 * i) = make_uint4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -305,6 +349,248 @@ cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// v2: two 128-query tiles (A, B) of one (batch, head) per CTA share every K/V tile.  Warps 2-5 are
+// the softmax group of tile A, warps 6-9 of tile B (thread r of a group owns query row r), so two
+// warps share each SM sub-partition and one group's exp2 work hides the other's TMEM / barrier
+// latency.  The softmax denominator comes from the tensor core: P is also multiplied by an
+// all-ones [keys x 16] operand, so l = sum_k bf16(p_k) is exactly consistent with the P V
+// numerator and costs no CUDA-core adds.  Row maxima use 3-input FMNMX on four independent chains.
+// ------------------------------------------------------------------------------------------
+namespace v2 {
+constexpr int NQT = 2;
+constexpr int OFF_Q = 0;                                            // 2 x 8 KB
+constexpr int OFF_KV = OFF_Q + NQT * Q_BYTES;                       // 4 x 16 KB
+constexpr int OFF_P = OFF_KV + KV_STAGES * (K_BYTES + V_BYTES);     // 2 x 32 KB
+constexpr int OFF_ONES = OFF_P + NQT * P_BYTES;                     // 4 KB of bf16 1.0
+constexpr int OFF_BIAS = OFF_ONES + 4096;                           // 2 x 128 floats
+constexpr int OFF_BAR = OFF_BIAS + NQT * KT * 4;
+constexpr int SMEM = OFF_BAR + 256 + 1024;
+constexpr int THREADS = 320;
+constexpr int TM_S = 0;          // S_x at TM_S + 128 x
+constexpr int TM_O = 256;        // O_x at TM_O + 48 x (32 cols), L_x right behind it (16 cols)
+
+__global__ void __launch_bounds__(THREADS, 1)
+cross_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, AttParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* q_full = bars;                        // 1
+    uint64_t* kv_full = bars + 1;                   // KV_STAGES
+    uint64_t* kv_empty = kv_full + KV_STAGES;       // KV_STAGES
+    uint64_t* s_full = kv_empty + KV_STAGES;        // 2 (A, B)
+    uint64_t* s_free = s_full + 2;
+    uint64_t* p_ready = s_free + 2;
+    uint64_t* pv_done = p_ready + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * (NQT * QT);
+    const int bh = blockIdx.y;
+    const int split = blockIdx.z;
+    const int b = bh / p.heads, h = bh - b * p.heads;
+    const int per = (p.tiles_total + p.nsplit - 1) / p.nsplit;
+    const int t_begin = split * per;
+    const int t_end = min(p.tiles_total, t_begin + per);
+    const int ntiles = max(0, t_end - t_begin);
+
+    // all-ones B operand for the row-sum MMA (layout irrelevant: every element is 1.0)
+    for (int i = threadIdx.x; i < 4096 / 4; i += THREADS)
+        reinterpret_cast<uint32_t*>(smem + OFF_ONES)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(q_full, 1);
+            for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128);
+                mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, TMEM_COLS);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0 && ntiles > 0) {
+            mbar_arrive_expect_tx(q_full, NQT * Q_BYTES);
+            tma_load_3d(smem + OFF_Q, &tmQ, q_full, 0, q0, bh);
+            tma_load_3d(smem + OFF_Q + Q_BYTES, &tmQ, q_full, 0, q0 + QT, bh);
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % KV_STAGES;
+                mbar_wait(&kv_empty[s], ((j / KV_STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
+                uint8_t* kd = smem + OFF_KV + s * (K_BYTES + V_BYTES);
+                const int key0 = (t_begin + j) * KT;
+                tma_load_3d(kd, &tmK, &kv_full[s], 0, key0, bh);
+                tma_load_3d(kd + K_BYTES, &tmV, &kv_full[s], 0, key0, bh);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0 && ntiles > 0) {
+            constexpr uint32_t idesc_qk = make_idesc(QT, KT, 1, 0, 0);     // S[128x128] = Q K^T
+            constexpr uint32_t idesc_pv = make_idesc(QT, HD, 1, 0, 1);     // O[128x32] += P V (V MN-major)
+            constexpr uint32_t idesc_l = make_idesc(QT, 16, 1, 0, 0);      // L[128x16] += P 1
+            const uint32_t ones_addr = smem_u32(smem + OFF_ONES);
+            auto issue_pv = [&](int t) {
+                const int s = t % KV_STAGES;
+                const uint32_t v_addr = smem_u32(smem + OFF_KV + s * (K_BYTES + V_BYTES) + K_BYTES);
+                for (int x = 0; x < NQT; ++x) {
+                    mbar_wait(&p_ready[x], t & 1);
+                    tcgen05_fence_after();
+                    const uint32_t p_addr = smem_u32(smem + OFF_P + x * P_BYTES);
+                    const uint32_t d_o = tmem_base + TM_O + x * 48, d_l = d_o + 32;
+#pragma unroll
+                    for (int kk = 0; kk < KT / 16; ++kk) {
+                        uint64_t ad = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+                        uint64_t bd = make_smem_desc(v_addr + kk * 1024, 512, 512, LAYOUT_SW64);
+                        uint64_t od = make_smem_desc(ones_addr + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+                        umma_f16_ss(d_o, ad, bd, idesc_pv, (t | kk) ? 1u : 0u);
+                        umma_f16_ss(d_l, ad, od, idesc_l, (t | kk) ? 1u : 0u);
+                    }
+                    umma_commit(&pv_done[x]);
+                }
+                umma_commit(&kv_empty[s]);
+            };
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % KV_STAGES;
+                mbar_wait(&kv_full[s], (j / KV_STAGES) & 1);
+                const uint32_t k_addr = smem_u32(smem + OFF_KV + s * (K_BYTES + V_BYTES));
+                for (int x = 0; x < NQT; ++x) {
+                    mbar_wait(&s_free[x], (j & 1) ^ 1);
+                    tcgen05_fence_after();
+                    const uint32_t q_addr = smem_u32(smem + OFF_Q + x * Q_BYTES);
+                    const uint32_t d = tmem_base + TM_S + x * 128;
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k) {
+                        uint64_t ad = make_smem_desc(q_addr + k * 32, 16, 512, LAYOUT_SW64);
+                        uint64_t bd = make_smem_desc(k_addr + k * 32, 16, 512, LAYOUT_SW64);
+                        umma_f16_ss(d, ad, bd, idesc_qk, k ? 1u : 0u);
+                    }
+                    umma_commit(&s_full[x]);
+                }
+                if (j > 0) issue_pv(j - 1);
+            }
+            issue_pv(ntiles - 1);
+        }
+    } else {
+        // ---------------- softmax / correction / epilogue ----------------
+        const int x = (warp - 2) >> 2;                       // 0: tile A (warps 2-5), 1: tile B (warps 6-9)
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t s_addr = tmem_base + lane_off + TM_S + x * 128;
+        const uint32_t o_addr = tmem_base + lane_off + TM_O + x * 48;
+        float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS) + x * KT;
+        uint8_t* pbase = smem + OFF_P + x * P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+        float m_use = -INFINITY;
+        const bool use_mask = (p.key_mask != nullptr);
+        for (int j = 0; j < ntiles; ++j) {
+            const uint32_t par = j & 1;
+            const int key0 = (t_begin + j) * KT;
+            const bool need_bias = use_mask || (key0 + KT > p.Lk);
+            if (need_bias) {
+                const int key = key0 + row;
+                bool dead = key >= p.Lk;
+                if (!dead && use_mask) dead = p.key_mask[(int64_t)b * p.Lk + key] != 0;
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");   // previous tile's readers done
+                sbias[row] = dead ? -INFINITY : 0.f;
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
+            }
+            mbar_wait(&s_full[x], par);
+            tcgen05_fence_after();
+            uint32_t sr[128];
+            tmem_ld_x32(s_addr, sr);
+            tmem_ld_x32(s_addr + 32, sr + 32);
+            tmem_ld_x32(s_addr + 64, sr + 64);
+            tmem_ld_x32(s_addr + 96, sr + 96);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(&s_free[x]);
+            float* sv = reinterpret_cast<float*>(sr);
+            if (need_bias) {
+#pragma unroll
+                for (int i = 0; i < 128; ++i) sv[i] += sbias[i];
+            }
+            float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
+#pragma unroll
+            for (int i = 4; i < 128; i += 8) {
+                mx0 = max3(mx0, sv[i], sv[i + 1]); mx1 = max3(mx1, sv[i + 2], sv[i + 3]);
+                if (i + 4 < 128) { mx2 = max3(mx2, sv[i + 4], sv[i + 5]); mx3 = max3(mx3, sv[i + 6], sv[i + 7]); }
+            }
+            const float mx = fmaxf(max3(mx0, mx1, mx2), mx3);
+            const bool grow = mx > m_use + RESCALE_TH;
+            float alpha = 1.f;
+            if (grow) { alpha = ex2(m_use - mx); m_use = mx; }
+            const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
+            uint32_t pk[64];
+#pragma unroll
+            for (int i = 0; i < 128; i += 2)
+                pk[i >> 1] = pack_bf16x2(ex2(sv[i] - m_eff), ex2(sv[i + 1] - m_eff));
+            // P_x / O_x / L_x are free once PV_x(j-1) has retired
+            mbar_wait(&pv_done[x], par ^ 1);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                uint8_t* dst = pbase + (c >> 3) * 16384 + (((c & 7) ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {        // correction: (O, L) *= alpha
+                tcgen05_fence_after();
+                uint32_t orr[48];
+                tmem_ld_x32(o_addr, orr);
+                tmem_ld_x16(o_addr + 32, orr + 32);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 48; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+                tmem_st_x32(o_addr, orr);
+                tmem_st_x16(o_addr + 32, orr + 32);
+                tmem_st_wait();
+            }
+            fence_proxy_async_smem();
+            tcgen05_fence_before();
+            mbar_arrive(&p_ready[x]);
+        }
+        // ---------------- epilogue ----------------
+        const int q = q0 + x * QT + row;
+        float o[32], l = 0.f;
+        if (ntiles > 0) {
+            mbar_wait(&pv_done[x], (ntiles - 1) & 1);
+            tcgen05_fence_after();
+            uint32_t orr[48];
+            tmem_ld_x32(o_addr, orr);
+            tmem_ld_x16(o_addr + 32, orr + 32);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(orr[i]);
+            l = __uint_as_float(orr[32]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = 0.f;
+        }
+        if (q < p.Lq) write_attention_row(p, o, m_use, l, b, h, bh, q, split);
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+}  // namespace v2
+
 // merge partial (O, m, l) over parts; thread per (row, 4 dims)
 __global__ void attention_merge_kernel(const float* __restrict__ part, int nparts, float* __restrict__ O,
                                        int ldo, __nv_bfloat16* __restrict__ O_split, int B, int Lq, int heads) {
@@ -421,8 +707,16 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
     p.partial = partial;
     p.B = B; p.Lq = Lq; p.Lk = Lk; p.heads = heads; p.nsplit = nsplit; p.tiles_total = tiles;
     p.write_partial = part ? 1 : 0;
-    dim3 grid((Lq + QT - 1) / QT, B * heads, nsplit);
-    cross_attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    static const bool use_v1 = getenv("PETR_FLASH_V1") != nullptr;     // A/B switch for profiling
+    if (use_v1) {
+        dim3 grid((Lq + QT - 1) / QT, B * heads, nsplit);
+        cross_attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    } else {
+        e = cudaFuncSetAttribute(v2::cross_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM);
+        if (e != cudaSuccess) return fail((int)e, "petr_cross_attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        dim3 grid((Lq + 2 * QT - 1) / (2 * QT), B * heads, nsplit);
+        v2::cross_attention_tc2_kernel<<<grid, v2::THREADS, v2::SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    }
     int rc = after_launch("petr_cross_attention_bf16");
     if (rc) return rc;
     if (part && !write_partial) {

@@ -39,8 +39,9 @@ def any_key_masked(img_metas, N: int, H: int, W: int) -> bool:
 
 
 def choose_nsplit(B: int, heads: int, Lq: int, Lk: int) -> int:
-    """Key splits so that the grid fills the 148 SMs in whole waves (1 CTA per SM)."""
-    base = B * heads * ((Lq + 127) // 128)
+    """Key splits so that the grid fills the 148 SMs in whole waves (1 CTA per SM; a CTA of the
+    flash kernel owns two 128-query tiles of one (batch, head))."""
+    base = B * heads * ((Lq + 255) // 256)
     tiles = (Lk + 127) // 128
     best, best_eff = 1, 0.0
     for ns in range(1, min(16, tiles) + 1):

@@ -18,24 +18,17 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID_GATE = 0, 1, 2
 A_ROWMAJOR, A_NCHW = 0, 1
 
 
-# Optional live kernel timing (bench.py roofline): name -> list of (start, end) CUDA events
-# recorded on the launching stream around the named launches.
-KERNEL_TIMERS = None
-
-
 class _Timed:
+    """Labels the C-ABI calls made inside the block for _lib.TIMERS (bench.py)."""
+
     def __init__(self, name):
         self.name = name
 
     def __enter__(self):
-        if KERNEL_TIMERS is not None:
-            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            self.ev[0].record()
+        _lib.LABEL = self.name
 
     def __exit__(self, *a):
-        if KERNEL_TIMERS is not None:
-            self.ev[1].record()
-            KERNEL_TIMERS.setdefault(self.name, []).append(self.ev)
+        _lib.LABEL = None
 
 
 def _cuda(t: torch.Tensor, name: str):

@@ -23,7 +23,17 @@ CASES = {
                        position_range=[-20.0, -20.0, -2.0, 20.0, 20.0, 2.0]),
     "tiny_v2": dict(workload="tiny-v2", batch=1, num_query=64, seed=4),
     "vov_800x320": dict(workload="vov-p4-800x320", batch=1, num_query=900, seed=0),
+    # 1500-key cases for the bf16 (tcgen05) path: bf16 rounding of V / P / position embeddings
+    # averages out as 1/sqrt(keys); at the 80 keys of the tiny cases it does not
+    "small": dict(workload="small", batch=2, num_query=64, seed=5),
+    "small_padded": dict(workload="small", batch=3, num_query=64, seed=6,
+                         img_shape=(140, 390), pad_shape=(160, 400), fully_masked=[1]),
+    "small_sharp": dict(workload="small", batch=2, num_query=64, seed=7, qk_scale=3.0),
+    "small_v2": dict(workload="small-v2", batch=1, num_query=64, seed=8),
 }
+
+TINY = [n for n in CASES if n.startswith("tiny")]
+BF16_CASES = ["small", "small_padded", "small_sharp", "small_v2", "vov_800x320"]
 
 
 def head_cfg(case: dict) -> dict:

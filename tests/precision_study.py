@@ -112,6 +112,14 @@ def forward(sd, feats, metas, cfg, fl):
             kh, kl = split2(kin); vh, vl = split2(vin); wkh, wkl = split2(w[256:512]); wvh, wvl = split2(w[512:])
             K = bf(kh @ wkh.T + kl @ wkh.T + kh @ wkl.T + b[256:512])
             V = bf(vh @ wvh.T + vl @ wvh.T + vh @ wvl.T + b[512:])
+        elif fl["kv"] == "kx3_vbf16":       # K: bf16x3 projection of fp32 kin, kept fp32; V: bf16 projection, bf16
+            K = kin @ w[256:512].T + b[256:512]; V = bf(bf(vin) @ bf(w[512:]).T + b[512:])
+        elif fl["kv"] == "kx3tf32_vbf16":
+            K = tf32(kin @ w[256:512].T + b[256:512]); V = bf(bf(vin) @ bf(w[512:]).T + b[512:])
+        elif fl["kv"] == "kx3bf16_vbf16":   # K x3 projection but rounded to bf16 at the end
+            K = bf(kin @ w[256:512].T + b[256:512]); V = bf(bf(vin) @ bf(w[512:]).T + b[512:])
+        elif fl["kv"] == "kbf16in_f32out":  # K: bf16 projection inputs, fp32 output
+            K = bf(kin) @ bf(w[256:512]).T + b[256:512]; V = bf(bf(vin) @ bf(w[512:]).T + b[512:])
         elif fl["kv"] == "tf32k_bf16v":     # bf16 projection GEMM, K kept fp32 (tf32-rounded), V bf16
             K = tf32(bf(kin) @ bf(w[256:512]).T + b[256:512]); V = bf(bf(vin) @ bf(w[512:]).T + b[512:])
         else:
