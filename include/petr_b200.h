@@ -158,7 +158,9 @@ int petr_nchw_to_tokens_bf16(const float* x, void* out, int G, int C, int hw, vo
  *   0: fp32 C[m*ldc+n];  1: bf16 C[m*ldc+n];
  *   2: bf16 head-split layout C[n / 256][b][(n % 256) / 32][key][32] with b = m / kv_Lk,
  *      key = m % kv_Lk -- the Q/K/V layout petr_cross_attention_bf16 reads;
- *   3: bf16 split C[m*2N + n] = hi, C[m*2N + N + n] = lo, plus (C2 nullable) fp32 C2[m*ldc+n].
+ *   3: bf16 split C[m*2N + n] = hi, C[m*2N + N + n] = lo, plus (C2 nullable) fp32 C2[m*ldc+n];
+ *   4: head-split [hi | lo] pair: C = hi array, C2 = lo array, both in the layout of mode 2 (the
+ *      operands of petr_attention_x3_tc).
  * residual (nullable, fp32, ldc) is added after alpha.  Used for the K/V projection of all
  * decoder layers in one launch (petr_transformer.py:341-344,:357-360), the position_encoder /
  * adapt_pos3d MLPs, input_proj and the query-side projections / FFN. */
@@ -188,6 +190,17 @@ int petr_cross_attention_bf16(const void* Qs, const void* Kh, const void* Vh,
                               const uint8_t* key_mask, float* O, int ldo, void* O_split,
                               float* partial, int B, int Lq, int Lk, int heads, int nsplit,
                               int write_partial, void* stream);
+
+/* fp32-class attention on tcgen05 (the decoder's self-attention; mmcv MultiheadAttention called by
+ * BaseTransformerLayer with q = k = query + query_pos, v = query).  Every operand is a bf16
+ * [hi | lo] pair (out_mode 4 of petr_gemm_bf16_tc), all bf16 [B, heads, L, 32]:
+ *   S = Qh Kh^T + Ql Kh^T + Qh Kl^T,  P = Ph + Pl,  O = Ph Vh + Pl Vh + Ph Vl   (~2^-16 accuracy).
+ * `scale` (head_dim^-1/2) is applied inside the softmax.  Outputs / splits / masks as
+ * petr_cross_attention_bf16. */
+int petr_attention_x3_tc(const void* Qh, const void* Ql, const void* Kh, const void* Kl,
+                         const void* Vh, const void* Vl, const uint8_t* key_mask, float* O,
+                         int ldo, void* O_split, float* partial, int B, int Lq, int Lk,
+                         int heads, float scale, int nsplit, int write_partial, void* stream);
 
 /* Merge `nparts` partial attention results (on-GPU split-KV or key-split across GPUs after an
  * all-gather):  m = max m_r;  O = sum e^{m_r-m} O_r / sum e^{m_r-m} l_r.

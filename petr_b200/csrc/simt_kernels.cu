@@ -180,9 +180,16 @@ sine3d_features_kernel(const uint8_t* __restrict__ mask, const float* __restrict
         int axis = ch / F, j = ch % F;
         float val = axis == 0 ? vn[w] : (axis == 1 ? vy[w] : vx[w]);
         float r;
-        if (j < half) r = sinf(__fdiv_rn(val, sdt[2 * j]));
-        else          r = cosf(__fdiv_rn(val, sdt[2 * (j - half) + 1]));
-        if constexpr (sizeof(OutT) == 4) orow[i] = r; else orow[i] = __float2bfloat16_rn(r);
+        if constexpr (sizeof(OutT) == 4) {
+            if (j < half) r = sinf(__fdiv_rn(val, sdt[2 * j]));
+            else          r = cosf(__fdiv_rn(val, sdt[2 * (j - half) + 1]));
+            orow[i] = r;
+        } else {
+            // bf16 output (8 mantissa bits): the fast intrinsics (abs error ~1e-6 on [0, 2*pi]) are exact enough
+            if (j < half) r = __sinf(__fdiv_rn(val, sdt[2 * j]));
+            else          r = __cosf(__fdiv_rn(val, sdt[2 * (j - half) + 1]));
+            orow[i] = __float2bfloat16_rn(r);
+        }
     }
 }
 
@@ -373,8 +380,10 @@ attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restri
                      const float* __restrict__ V, int ldv, const uint8_t* __restrict__ key_mask,
                      float* __restrict__ O, int ldo, __nv_bfloat16* __restrict__ O_split, int E,
                      int Lq, int Lk, float scale_log2) {
-    __shared__ __align__(16) float sK[ATT_KT][32];
-    __shared__ __align__(16) float sV[ATT_KT][32];
+    // rows padded to 36 floats: the four lanes of a quad read four different rows per LDS.128 and
+    // a 32-float pitch would put them on the same banks
+    __shared__ __align__(16) float sK[ATT_KT][36];
+    __shared__ __align__(16) float sV[ATT_KT][36];
     __shared__ float sBias[ATT_KT];
     const int head = blockIdx.y, b = blockIdx.z;
     const int sub = threadIdx.x & 3;

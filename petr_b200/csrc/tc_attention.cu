@@ -93,44 +93,62 @@ __device__ __forceinline__ void write_attention_row(const AttParams& p, float* o
     }
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                          const __grid_constant__ CUtensorMap tmV, AttParams p) {
+// ------------------------------------------------------------------------------------------
+// x3: fp32-class attention on the tensor cores (the decoder's self-attention, mmcv
+// MultiheadAttention via BaseTransformerLayer).  Q, K, V arrive as bf16 [hi | lo] pairs and
+//   S = Qh Kh^T + Ql Kh^T + Qh Kl^T,     O = Ph Vh + Pl Vh + Ph Vl,     P = Ph + Pl
+// so every product carries ~16 mantissa bits (error ~2^-16, like the bf16x3 GEMMs); a plain bf16
+// self-attention costs 0.04-0.06 m in cx/cy (tests/precision_study.py).  One 128-query tile per
+// CTA, S double buffered in TMEM, l accumulated in fp32 registers.
+// ------------------------------------------------------------------------------------------
+namespace x3 {
+constexpr int STAGES = 3;
+constexpr int STAGE_BYTES = 2 * K_BYTES + 2 * V_BYTES;              // Kh, Kl, Vh, Vl
+constexpr int OFF_Q = 0;                                            // Qh, Ql
+constexpr int OFF_KV = OFF_Q + 2 * Q_BYTES;
+constexpr int OFF_P = OFF_KV + STAGES * STAGE_BYTES;                // Ph, Pl
+constexpr int OFF_BIAS = OFF_P + 2 * P_BYTES;
+constexpr int OFF_BAR = OFF_BIAS + KT * 4;
+constexpr int SMEM = OFF_BAR + 256 + 1024;
+constexpr int THREADS = 192;
+
+struct Maps { CUtensorMap qh, ql, kh, kl, vh, vl; };
+
+__global__ void __launch_bounds__(THREADS, 1)
+attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale_log2) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* q_full = bars;                        // 1
-    uint64_t* kv_full = bars + 1;                   // KV_STAGES
-    uint64_t* kv_empty = kv_full + KV_STAGES;       // KV_STAGES
-    uint64_t* s_full = kv_empty + KV_STAGES;        // 2
+    uint64_t* kv_full = bars + 1;                   // STAGES
+    uint64_t* kv_empty = kv_full + STAGES;          // STAGES
+    uint64_t* s_full = kv_empty + STAGES;           // 2
     uint64_t* s_free = s_full + 2;                  // 2
-    uint64_t* p_ready = s_free + 2;                 // 2
-    uint64_t* pv_done = p_ready + 2;                // 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+    uint64_t* p_ready = s_free + 2;                 // 1
+    uint64_t* pv_done = p_ready + 1;                // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
     float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qtile = blockIdx.x;
-    const int bh = blockIdx.y;                      // b * heads + h
+    const int bh = blockIdx.y;
     const int split = blockIdx.z;
     const int b = bh / p.heads, h = bh - b * p.heads;
-    // key tiles of this split: [t_begin, t_end)
     const int per = (p.tiles_total + p.nsplit - 1) / p.nsplit;
     const int t_begin = split * per;
     const int t_end = min(p.tiles_total, t_begin + per);
     const int ntiles = max(0, t_end - t_begin);
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+        tma_prefetch_desc(&tm.qh); tma_prefetch_desc(&tm.ql); tma_prefetch_desc(&tm.kh);
+        tma_prefetch_desc(&tm.kl); tma_prefetch_desc(&tm.vh); tma_prefetch_desc(&tm.vl);
     }
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(q_full, 1);
-            for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-            for (int i = 0; i < 2; ++i) {
-                mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128);
-                mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1);
-            }
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); }
+            mbar_init(p_ready, 128); mbar_init(pv_done, 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -142,86 +160,91 @@ cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ---------------- TMA producer ----------------
-        if (lane == 0) {
-            if (ntiles > 0) {
-                mbar_arrive_expect_tx(q_full, Q_BYTES);
-                tma_load_3d(smem + OFF_Q, &tmQ, q_full, 0, qtile * QT, bh);
-            }
+        if (lane == 0 && ntiles > 0) {
+            mbar_arrive_expect_tx(q_full, 2 * Q_BYTES);
+            tma_load_3d(smem + OFF_Q, &tm.qh, q_full, 0, qtile * QT, bh);
+            tma_load_3d(smem + OFF_Q + Q_BYTES, &tm.ql, q_full, 0, qtile * QT, bh);
             for (int j = 0; j < ntiles; ++j) {
-                const int s = j % KV_STAGES;
-                const uint32_t ph = (j / KV_STAGES) & 1;
-                mbar_wait(&kv_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
-                uint8_t* kd = smem + OFF_KV + s * (K_BYTES + V_BYTES);
+                const int s = j % STAGES;
+                mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], STAGE_BYTES);
+                uint8_t* d = smem + OFF_KV + s * STAGE_BYTES;
                 const int key0 = (t_begin + j) * KT;
-                tma_load_3d(kd, &tmK, &kv_full[s], 0, key0, bh);
-                tma_load_3d(kd + K_BYTES, &tmV, &kv_full[s], 0, key0, bh);
+                tma_load_3d(d, &tm.kh, &kv_full[s], 0, key0, bh);
+                tma_load_3d(d + K_BYTES, &tm.kl, &kv_full[s], 0, key0, bh);
+                tma_load_3d(d + 2 * K_BYTES, &tm.vh, &kv_full[s], 0, key0, bh);
+                tma_load_3d(d + 2 * K_BYTES + V_BYTES, &tm.vl, &kv_full[s], 0, key0, bh);
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
         if (lane == 0 && ntiles > 0) {
-            constexpr uint32_t idesc_qk = make_idesc(QT, KT, 1, 0, 0);     // S[128x128] = Q K^T
-            constexpr uint32_t idesc_pv = make_idesc(QT, HD, 1, 0, 1);     // O[128x32] += P V (V MN-major)
+            constexpr uint32_t idesc_qk = make_idesc(QT, KT, 1, 0, 0);
+            constexpr uint32_t idesc_pv = make_idesc(QT, HD, 1, 0, 1);
             const uint32_t q_addr = smem_u32(smem + OFF_Q);
             auto issue_qk = [&](int t) {
-                const int s = t % KV_STAGES;
-                mbar_wait(&kv_full[s], (t / KV_STAGES) & 1);
+                const int s = t % STAGES;
+                mbar_wait(&kv_full[s], (t / STAGES) & 1);
                 mbar_wait(&s_free[t & 1], ((t >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
-                const uint32_t k_addr = smem_u32(smem + OFF_KV + s * (K_BYTES + V_BYTES));
+                const uint32_t k_addr = smem_u32(smem + OFF_KV + s * STAGE_BYTES);
                 const uint32_t d = tmem_base + ((t & 1) ? TM_S1 : TM_S0);
+                // (Qh,Kh), (Ql,Kh), (Qh,Kl)
+                const uint32_t qa[3] = {q_addr, q_addr + Q_BYTES, q_addr};
+                const uint32_t ka[3] = {k_addr, k_addr, k_addr + K_BYTES};
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) {
-                    uint64_t ad = make_smem_desc(q_addr + k * 32, 16, 512, LAYOUT_SW64);
-                    uint64_t bd = make_smem_desc(k_addr + k * 32, 16, 512, LAYOUT_SW64);
-                    umma_f16_ss(d, ad, bd, idesc_qk, k ? 1u : 0u);
-                }
+                for (int t3 = 0; t3 < 3; ++t3)
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k) {
+                        uint64_t ad = make_smem_desc(qa[t3] + k * 32, 16, 512, LAYOUT_SW64);
+                        uint64_t bd = make_smem_desc(ka[t3] + k * 32, 16, 512, LAYOUT_SW64);
+                        umma_f16_ss(d, ad, bd, idesc_qk, (t3 | k) ? 1u : 0u);
+                    }
                 umma_commit(&s_full[t & 1]);
             };
             mbar_wait(q_full, 0);
             issue_qk(0);
             for (int j = 0; j < ntiles; ++j) {
                 if (j + 1 < ntiles) issue_qk(j + 1);
-                const int s = j % KV_STAGES;
-                mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+                const int s = j % STAGES;
+                mbar_wait(p_ready, j & 1);
                 tcgen05_fence_after();
-                const uint32_t p_addr = smem_u32(smem + OFF_P + (j & 1) * P_BYTES);
-                const uint32_t v_addr = smem_u32(smem + OFF_KV + s * (K_BYTES + V_BYTES) + K_BYTES);
+                const uint32_t p_addr = smem_u32(smem + OFF_P);
+                const uint32_t v_addr = smem_u32(smem + OFF_KV + s * STAGE_BYTES + 2 * K_BYTES);
+                // (Ph,Vh), (Pl,Vh), (Ph,Vl)
+                const uint32_t pa[3] = {p_addr, p_addr + P_BYTES, p_addr};
+                const uint32_t va[3] = {v_addr, v_addr, v_addr + V_BYTES};
 #pragma unroll
-                for (int kk = 0; kk < KT / 16; ++kk) {
-                    // P: two 64-key K-atoms of 16 KB; 32 B per 16-key step inside an atom
-                    uint64_t ad = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
-                    // V: [key][32 dims] MN-major, 64B-swizzled; 8-key groups are 512 B apart
-                    uint64_t bd = make_smem_desc(v_addr + kk * 1024, 512, 512, LAYOUT_SW64);
-                    umma_f16_ss(tmem_base + TM_O, ad, bd, idesc_pv, (j | kk) ? 1u : 0u);
-                }
+                for (int t3 = 0; t3 < 3; ++t3)
+#pragma unroll
+                    for (int kk = 0; kk < KT / 16; ++kk) {
+                        uint64_t ad = make_smem_desc(pa[t3] + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+                        uint64_t bd = make_smem_desc(va[t3] + kk * 1024, 512, 512, LAYOUT_SW64);
+                        umma_f16_ss(tmem_base + TM_O, ad, bd, idesc_pv, (j | t3 | kk) ? 1u : 0u);
+                    }
                 umma_commit(&kv_empty[s]);
-                umma_commit(&pv_done[j & 1]);
+                umma_commit(pv_done);
             }
         }
     } else {
-        // ---------------- softmax / correction / epilogue: thread <-> query row ----------------
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        const int sm_tid = row;                              // 0..127 within the softmax group
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-        float m_use = -INFINITY, l = 0.f;
+        uint8_t* prow = smem + OFF_P + (row >> 3) * 1024 + (row & 7) * 128;
+        float m_use = -INFINITY, l = 0.f;            // m_use in the scaled (log2) domain
         const bool use_mask = (p.key_mask != nullptr);
         for (int j = 0; j < ntiles; ++j) {
             const int bsel = j & 1;
-            const uint32_t u = (j >> 1) & 1;
             const int key0 = (t_begin + j) * KT;
             const bool need_bias = use_mask || (key0 + KT > p.Lk);
             if (need_bias) {
-                const int key = key0 + sm_tid;
+                const int key = key0 + row;
                 bool dead = key >= p.Lk;
                 if (!dead && use_mask) dead = p.key_mask[(int64_t)b * p.Lk + key] != 0;
-                sbias[bsel * KT + sm_tid] = dead ? -INFINITY : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                sbias[row] = dead ? -INFINITY : 0.f;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            mbar_wait(&s_full[bsel], u);
+            mbar_wait(&s_full[bsel], (j >> 1) & 1);
             tcgen05_fence_after();
             uint32_t sr[128];
             const uint32_t s_addr = tmem_base + lane_off + (bsel ? TM_S1 : TM_S0);
@@ -233,43 +256,43 @@ cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
             tcgen05_fence_before();
             mbar_arrive(&s_free[bsel]);
             float* sv = reinterpret_cast<float*>(sr);
+#pragma unroll
+            for (int i = 0; i < 128; ++i) sv[i] *= scale_log2;
             if (need_bias) {
-                const float* bb = sbias + bsel * KT;
 #pragma unroll
-                for (int i = 0; i < 128; ++i) sv[i] += bb[i];
+                for (int i = 0; i < 128; ++i) sv[i] += sbias[i];
             }
-            float mx = sv[0];
+            float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
 #pragma unroll
-            for (int i = 1; i < 128; ++i) mx = fmaxf(mx, sv[i]);
-            // lazy rescale: only move the reference max when it grew by more than RESCALE_TH
-            bool grow = mx > m_use + RESCALE_TH;             // (-inf + 8 = -inf) -> true on first finite max
+            for (int i = 4; i < 128; i += 8) {
+                mx0 = max3(mx0, sv[i], sv[i + 1]); mx1 = max3(mx1, sv[i + 2], sv[i + 3]);
+                if (i + 4 < 128) { mx2 = max3(mx2, sv[i + 4], sv[i + 5]); mx3 = max3(mx3, sv[i + 6], sv[i + 7]); }
+            }
+            const float mx = fmaxf(max3(mx0, mx1, mx2), mx3);
+            const bool grow = mx > m_use + RESCALE_TH;
             float alpha = 1.f;
-            if (grow) {
-                alpha = ex2(m_use - mx);                     // m_use = -inf -> 0
-                m_use = mx;
-                l *= alpha;
-            }
+            if (grow) { alpha = ex2(m_use - mx); m_use = mx; l *= alpha; }
             const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
+            mbar_wait(pv_done, (j & 1) ^ 1);                   // P / O free: PV(j-1) retired
             float lsum = 0.f;
-            uint32_t pk[64];
 #pragma unroll
-            for (int i = 0; i < 128; i += 2) {
-                float p0 = ex2(sv[i] - m_eff), p1 = ex2(sv[i + 1] - m_eff);
-                lsum += p0 + p1;
-                pk[i >> 1] = pack_bf16x2(p0, p1);
+            for (int c = 0; c < 16; ++c) {                     // 16 chunks of 8 keys
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float p0 = ex2(sv[8 * c + 2 * e] - m_eff), p1 = ex2(sv[8 * c + 2 * e + 1] - m_eff);
+                    lsum += p0 + p1;
+                    const float h0 = __bfloat162float(__float2bfloat16_rn(p0));
+                    const float h1 = __bfloat162float(__float2bfloat16_rn(p1));
+                    hi[e] = pack_bf16x2(h0, h1);
+                    lo[e] = pack_bf16x2(p0 - h0, p1 - h1);
+                }
+                uint8_t* dst = prow + (c >> 3) * 16384 + (((c & 7) ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(dst + P_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
             l += lsum;
-            // P[bsel] is free once PV(j-2) has retired
-            mbar_wait(&pv_done[bsel], u ^ 1);
-            uint8_t* prow = smem + OFF_P + bsel * P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                uint8_t* dst = prow + (c >> 3) * 16384 + (((c & 7) ^ (row & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-            }
-            // correction: O *= alpha (needs PV(j-1) retired); warp-uniform decision
             if (j > 0 && __any_sync(0xffffffffu, grow)) {
-                mbar_wait(&pv_done[bsel ^ 1], ((j - 1) >> 1) & 1);
                 tcgen05_fence_after();
                 uint32_t orr[32];
                 tmem_ld_x32(tmem_base + lane_off + TM_O, orr);
@@ -281,14 +304,12 @@ cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
             }
             fence_proxy_async_smem();
             tcgen05_fence_before();
-            mbar_arrive(&p_ready[bsel]);
+            mbar_arrive(p_ready);
         }
-        // ---------------- epilogue ----------------
         const int q = qtile * QT + row;
         float o[32];
         if (ntiles > 0) {
-            const int jl = ntiles - 1;
-            mbar_wait(&pv_done[jl & 1], (jl >> 1) & 1);
+            mbar_wait(pv_done, (ntiles - 1) & 1);
             tcgen05_fence_after();
             uint32_t orr[32];
             tmem_ld_x32(tmem_base + lane_off + TM_O, orr);
@@ -299,46 +320,7 @@ cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = 0.f;
         }
-        if (q < p.Lq) {
-            if (p.write_partial) {
-                const int64_t prow_i = (int64_t)bh * p.Lq + q;
-                const int64_t rows = (int64_t)p.B * p.heads * p.Lq;
-                float* pbase = p.partial + (int64_t)split * rows * 34;
-                float* po = pbase + prow_i * 32;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(po + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-                float* pm = pbase + rows * 32 + prow_i * 2;
-                pm[0] = m_use; pm[1] = l;
-            } else {
-                const float inv = 1.f / l;          // l == 0 (all keys masked) -> NaN like torch
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] *= inv;
-                if (p.O) {
-                    float* op = p.O + ((int64_t)b * p.Lq + q) * p.ldo + h * HD;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<float4*>(op + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-                }
-                if (p.O_split) {
-                    const int E = p.heads * HD;
-                    __nv_bfloat16* sp = p.O_split + ((int64_t)b * p.Lq + q) * (2 * E) + h * HD;
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        float h0 = __bfloat162float(__float2bfloat16_rn(o[i]));
-                        float h1 = __bfloat162float(__float2bfloat16_rn(o[i + 1]));
-                        hi[i >> 1] = pack_bf16x2(h0, h1);
-                        lo[i >> 1] = pack_bf16x2(o[i] - h0, o[i + 1] - h1);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        *reinterpret_cast<uint4*>(sp + 2 * i) = make_uint4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]);
-                        *reinterpret_cast<uint4*>(sp + E + 2 * i) = make_uint4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
-                    }
-                }
-            }
-        }
+        if (q < p.Lq) write_attention_row(p, o, m_use, l, b, h, bh, q, split);
         tcgen05_fence_before();
     }
     __syncthreads();
@@ -348,6 +330,7 @@ cross_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
+}  // namespace x3
 
 // ------------------------------------------------------------------------------------------
 // v2: two 128-query tiles (A, B) of one (batch, head) per CTA share every K/V tile.  Warps 2-5 are
@@ -699,7 +682,7 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
         rc = tmap::encode(&tmV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Vh, d, s, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
     }
-    cudaError_t e = cudaFuncSetAttribute(cross_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(v2::cross_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM);
     if (e != cudaSuccess) return fail((int)e, "petr_cross_attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     AttParams p{};
     p.key_mask = key_mask; p.O = O; p.ldo = ldo; p.O_split = (__nv_bfloat16*)O_split;
@@ -707,16 +690,8 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
     p.partial = partial;
     p.B = B; p.Lq = Lq; p.Lk = Lk; p.heads = heads; p.nsplit = nsplit; p.tiles_total = tiles;
     p.write_partial = part ? 1 : 0;
-    static const bool use_v1 = getenv("PETR_FLASH_V1") != nullptr;     // A/B switch for profiling
-    if (use_v1) {
-        dim3 grid((Lq + QT - 1) / QT, B * heads, nsplit);
-        cross_attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
-    } else {
-        e = cudaFuncSetAttribute(v2::cross_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM);
-        if (e != cudaSuccess) return fail((int)e, "petr_cross_attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        dim3 grid((Lq + 2 * QT - 1) / (2 * QT), B * heads, nsplit);
-        v2::cross_attention_tc2_kernel<<<grid, v2::THREADS, v2::SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
-    }
+    dim3 grid((Lq + 2 * QT - 1) / (2 * QT), B * heads, nsplit);
+    v2::cross_attention_tc2_kernel<<<grid, v2::THREADS, v2::SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
     int rc = after_launch("petr_cross_attention_bf16");
     if (rc) return rc;
     if (part && !write_partial) {
@@ -738,4 +713,50 @@ extern "C" int petr_attention_merge(const float* partial, int nparts, float* O, 
     attention_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         partial, nparts, O, ldo, (__nv_bfloat16*)O_split, B, Lq, heads);
     return after_launch("petr_attention_merge");
+}
+
+extern "C" int petr_attention_x3_tc(const void* Qh, const void* Ql, const void* Kh, const void* Kl,
+                                    const void* Vh, const void* Vl, const uint8_t* key_mask, float* O,
+                                    int ldo, void* O_split, float* partial, int B, int Lq, int Lk,
+                                    int heads, float scale, int nsplit, int write_partial, void* stream) {
+    PETR_REQUIRE(Qh && Ql && Kh && Kl && Vh && Vl, PETR_E_BADARG, "petr_attention_x3_tc: null pointer");
+    PETR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0 && nsplit > 0, PETR_E_BADARG, "petr_attention_x3_tc: bad dimension");
+    const bool part = write_partial || nsplit > 1;
+    if (part) PETR_REQUIRE(partial, PETR_E_BADARG, "petr_attention_x3_tc: partial buffer required");
+    if (!write_partial) {
+        PETR_REQUIRE(O || O_split, PETR_E_BADARG, "petr_attention_x3_tc: O or O_split required");
+        if (O) PETR_REQUIRE(ldo >= heads * 32 && (ldo % 4) == 0 && aligned16(O), PETR_E_ALIGN, "petr_attention_x3_tc: O alignment");
+        if (O_split) PETR_REQUIRE(aligned16(O_split), PETR_E_ALIGN, "petr_attention_x3_tc: O_split alignment");
+    }
+    const void* ptrs[6] = {Qh, Ql, Kh, Kl, Vh, Vl};
+    for (int i = 0; i < 6; ++i) PETR_REQUIRE(aligned16(ptrs[i]), PETR_E_ALIGN, "petr_attention_x3_tc: operand alignment");
+    const int tiles = (Lk + KT - 1) / KT;
+    if (nsplit > tiles) nsplit = tiles;
+    x3::Maps tm;
+    CUtensorMap* maps[6] = {&tm.qh, &tm.ql, &tm.kh, &tm.kl, &tm.vh, &tm.vl};
+    for (int i = 0; i < 6; ++i) {
+        const int L = i < 2 ? Lq : Lk;
+        uint64_t d[3] = {HD, (uint64_t)L, (uint64_t)B * heads};
+        uint64_t st[2] = {HD * 2, (uint64_t)L * HD * 2};
+        uint32_t box[3] = {HD, (uint32_t)(i < 2 ? QT : KT), 1};
+        int rc = tmap::encode(maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptrs[i], d, st, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+    }
+    cudaError_t e = cudaFuncSetAttribute(x3::attention_x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, x3::SMEM);
+    if (e != cudaSuccess) return fail((int)e, "petr_attention_x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    AttParams p{};
+    p.key_mask = key_mask; p.O = O; p.ldo = ldo; p.O_split = (__nv_bfloat16*)O_split; p.partial = partial;
+    p.B = B; p.Lq = Lq; p.Lk = Lk; p.heads = heads; p.nsplit = nsplit; p.tiles_total = tiles;
+    p.write_partial = part ? 1 : 0;
+    dim3 grid((Lq + QT - 1) / QT, B * heads, nsplit);
+    x3::attention_x3_tc_kernel<<<grid, x3::THREADS, x3::SMEM, (cudaStream_t)stream>>>(tm, p, scale * 1.4426950408889634f);
+    int rc = after_launch("petr_attention_x3_tc");
+    if (rc) return rc;
+    if (part && !write_partial) {
+        const int64_t total = (int64_t)B * heads * Lq * 8;
+        attention_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            partial, nsplit, O, ldo, (__nv_bfloat16*)O_split, B, Lq, heads);
+        return after_launch("petr_attention_merge");
+    }
+    return 0;
 }

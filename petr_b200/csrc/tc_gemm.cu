@@ -163,7 +163,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(&acc_full[buf], (tcount >> 1) & 1);
             tcgen05_fence_after();
             int kv_b = 0, kv_key = 0;
-            if (p.out_mode == 2 && m < p.M) { kv_b = m / p.kv_Lk; kv_key = m - kv_b * p.kv_Lk; }
+            if ((p.out_mode == 2 || p.out_mode == 4) && m < p.M) { kv_b = m / p.kv_Lk; kv_key = m - kv_b * p.kv_Lk; }
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
@@ -232,6 +232,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) +
                         ((((int64_t)l * p.kv_B + kv_b) * (p.kv_E >> 5) + h) * p.kv_Lk + kv_key) * 32;
                     store_bf16x32(cp, v);
+                } else if (p.out_mode == 4) {
+                    // head-split [hi | lo] pair: C = hi array, C2 = lo array, both [n / E][b][head][key][32]
+                    const int l = nb / p.kv_E, h = (nb % p.kv_E) >> 5;
+                    const int64_t off = ((((int64_t)l * p.kv_B + kv_b) * (p.kv_E >> 5) + h) * p.kv_Lk + kv_key) * 32;
+                    float lo[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+                    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + off, v);
+                    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C2) + off, lo);
                 } else if (p.out_mode == 3) {
                     // bf16 split [hi | lo] for the bf16x3 GEMMs: row m, hi at [nb], lo at [N + nb]
                     float lo[32];
@@ -301,13 +310,14 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     PETR_REQUIRE(lda >= a_k_wrap && ldw >= K && (lda % 8) == 0 && (ldw % 8) == 0 && aligned16(A) && aligned16(W),
                  PETR_E_ALIGN, "petr_gemm_bf16_tc: A/W rows must be 16-byte aligned");
     PETR_REQUIRE(act == PETR_ACT_NONE || act == PETR_ACT_RELU, PETR_E_BADARG, "petr_gemm_bf16_tc: bad act");
-    PETR_REQUIRE(out_mode >= 0 && out_mode <= 3, PETR_E_BADARG, "petr_gemm_bf16_tc: bad out_mode");
+    PETR_REQUIRE(out_mode >= 0 && out_mode <= 4, PETR_E_BADARG, "petr_gemm_bf16_tc: bad out_mode");
     EpiParams p{};
     p.bias = bias; p.residual = residual; p.act = act; p.alpha = alpha;
     p.C = C; p.C2 = C2; p.ldc = ldc; p.out_mode = out_mode;
     p.M = M; p.N = N; p.K = K; p.a_k_wrap = a_k_wrap;
     if (bias) PETR_REQUIRE(aligned16(bias), PETR_E_ALIGN, "petr_gemm_bf16_tc: bias must be 16-byte aligned");
-    if (out_mode == 2) {
+    if (out_mode == 2 || out_mode == 4) {
+        if (out_mode == 4) PETR_REQUIRE(C2 && aligned16(C2), PETR_E_BADARG, "petr_gemm_bf16_tc: out_mode 4 needs C2 (lo array)");
         PETR_REQUIRE(kv_Lk > 0 && M % kv_Lk == 0 && N % 256 == 0 && !residual, PETR_E_SHAPE,
                      "petr_gemm_bf16_tc: head-split output needs M %% Lk == 0, N %% 256 == 0, no residual");
         p.kv_Lk = kv_Lk; p.kv_B = M / kv_Lk; p.kv_E = 256;

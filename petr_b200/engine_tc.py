@@ -162,7 +162,7 @@ def decoder_layer_tc(eng, P, l: int, st: dict, qpos, ks: dict, last: bool) -> di
     """One decoder layer on the tensor-core path.  `st` carries the residual stream in the forms
     the next GEMMs need: X fp32 (R,E), Xs = split(X), Xps = split(X + query_pos) (bf16 [hi|lo]).
     Every projection / FFN GEMM is a bf16x3 tcgen05 GEMM (fp32-class accuracy); the self-attention
-    core is the fp32 kernel; the cross-attention core is the bf16 flash kernel."""
+    core is the x3 (hi/lo split) tcgen05 kernel; the cross-attention core is the bf16 flash kernel."""
     s = eng.spec
     E, R, B = s.E, st["X"].shape[0], ks["B"]
     lw = P["layers"][l]
@@ -170,10 +170,13 @@ def decoder_layer_tc(eng, P, l: int, st: dict, qpos, ks: dict, last: bool) -> di
     dev = st["X"].device
     g = ops.gemm_bf16_tc
     # ---- self-attention (mmcv MultiheadAttention; q = k = X + qpos, v = X) ----
-    qk = g(st["Xps"], tw["sa_qk"], tw["sa_qk_b"], x3=True, name="gemm_q_side")
-    v = g(st["Xs"], tw["sa_v"], tw["sa_v_b"], x3=True, name="gemm_q_side")
+    qk = g(st["Xps"], tw["sa_qk"], tw["sa_qk_b"], x3=True, headsplit_Lk=s.Lq, headsplit_pair=True,
+           name="gemm_q_side")                               # (hi/lo, [Q, K], B, heads, Lq, 32)
+    v = g(st["Xs"], tw["sa_v"], tw["sa_v_b"], x3=True, headsplit_Lk=s.Lq, headsplit_pair=True,
+          name="gemm_q_side")
     o_s = torch.empty((R, 2 * E), dtype=torch.bfloat16, device=dev)
-    ops.attention_f32(qk[:, :E], qk[:, E:], v, None, B, s.Lq, s.Lq, s.heads, out_split=o_s, want_f32=False)
+    ops.attention_x3_tc(qk[:, 0], qk[:, 1], v[:, 0], None, B, s.Lq, s.Lq, s.heads, out_split=o_s,
+                        want_f32=False)
     y = g(o_s, tw["sa_out"], lw["sa_out_b"], residual=st["X"], x3=True, name="gemm_q_side")
     X1 = torch.empty_like(y)
     X1ps = torch.empty((R, 2 * E), dtype=torch.bfloat16, device=dev)

@@ -223,7 +223,8 @@ OUT_SPLIT = 3
 
 def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, act=ACT_NONE,
                  alpha: float = 1.0, out=None, out_dtype=torch.float32, headsplit_Lk: int = 0,
-                 split_out: bool = False, out_f32=None, x3: bool = False, name: str = "gemm_bf16_tc"):
+                 split_out: bool = False, out_f32=None, x3: bool = False, headsplit_pair: bool = False,
+                 name: str = "gemm_bf16_tc"):
     """C = alpha * act(A @ W.T + bias) (+ residual) on tcgen05; A (M,Ka) bf16, W (N,K) bf16.
     x3: A is a split (M, 2*K0) [hi | lo] activation and W an x3_weight (N, 3*K0).
     headsplit_Lk > 0: bf16 output in the [N/256][B][8][Lk][32] Q/K/V layout.
@@ -240,7 +241,14 @@ def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, 
     else:
         assert A.shape[1] == K
     C2 = None
-    if headsplit_Lk > 0:
+    if headsplit_Lk > 0 and headsplit_pair:
+        # (hi, lo) pair stacked on a leading axis: out[0] = hi, out[1] = lo, each [N/256][B][8][L][32]
+        B = M // headsplit_Lk
+        if out is None:
+            out = torch.empty((2, N // 256, B, 8, headsplit_Lk, 32), dtype=torch.bfloat16, device=A.device)
+        C2 = out[1]
+        mode, ldc = 4, 0
+    elif headsplit_Lk > 0:
         B = M // headsplit_Lk
         if out is None:
             out = torch.empty((N // 256, B, 8, headsplit_Lk, 32), dtype=torch.bfloat16, device=A.device)
@@ -295,6 +303,26 @@ def cross_attention_bf16(Qs, Kh, Vh, key_mask, B: int, Lq: int, Lk: int, heads: 
         call("petr_cross_attention_bf16", ptr(Qs), ptr(Kh), ptr(Vh), ptr(key_mask), ptr(out),
              out.stride(0) if out is not None else 0, ptr(out_split), ptr(partial), B, Lq, Lk, heads,
              nsplit, int(write_partial), stream_ptr(Qs.device))
+    if write_partial:
+        return partial
+    return out if out is not None else out_split
+
+
+def attention_x3_tc(Qp, Kp, Vp, key_mask, B: int, Lq: int, Lk: int, heads: int, nsplit: int = 1,
+                    out=None, out_split=None, partial=None, write_partial: bool = False,
+                    want_f32: bool = True):
+    """fp32-class attention on tcgen05.  Qp/Kp/Vp: bf16 (2, B, heads, L, 32) = (hi, lo) pairs."""
+    _cuda(Qp, "Qp")
+    nsplit = max(1, min(int(nsplit), (Lk + 127) // 128))
+    if (nsplit > 1 or write_partial) and partial is None:
+        partial = torch.empty((nsplit * attention_partial_floats(B, Lq, heads),), dtype=torch.float32,
+                              device=Qp.device)
+    if not write_partial and out is None and want_f32:
+        out = torch.empty((B * Lq, heads * 32), dtype=torch.float32, device=Qp.device)
+    with _Timed("attention_x3_tc"):
+        call("petr_attention_x3_tc", ptr(Qp[0]), ptr(Qp[1]), ptr(Kp[0]), ptr(Kp[1]), ptr(Vp[0]), ptr(Vp[1]),
+             ptr(key_mask), ptr(out), out.stride(0) if out is not None else 0, ptr(out_split), ptr(partial),
+             B, Lq, Lk, heads, 1.0 / math.sqrt(32.0), nsplit, int(write_partial), stream_ptr(Qp.device))
     if write_partial:
         return partial
     return out if out is not None else out_split

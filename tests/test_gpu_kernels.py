@@ -284,6 +284,39 @@ def test_attention_split_outputs():
         assert (sp[:, :256].float() + sp[:, 256:].float() - f32).abs().max() <= 1e-4
 
 
+@pytest.mark.parametrize("B,Lq,Lk,scale,nsplit", [(2, 900, 900, 1.0, 1), (1, 128, 128, 1.0, 1), (3, 100, 333, 6.0, 1),
+                                                  (1, 300, 1500, 3.0, 3)])
+def test_attention_x3_tc_fp32_class(B, Lq, Lk, scale, nsplit):
+    """hi/lo split attention on tcgen05 must match an fp64 evaluation to fp32-class accuracy, incl.
+    through the head-split pair epilogue of the bf16x3 GEMM that feeds it."""
+    g = torch.Generator().manual_seed(Lk + 7)
+    E = 256
+    X = (torch.randn(B * Lq, E, generator=g) * scale).to(DEV)
+    Y = (torch.randn(B * Lk, E, generator=g) * scale).to(DEV)
+    Wqk = (torch.randn(2 * E, E, generator=g) / 16).to(DEV)
+    Wv = (torch.randn(E, E, generator=g) / 16).to(DEV)
+    bqk = torch.randn(2 * E, generator=g).to(DEV)
+    if Lq == Lk:
+        Y = X
+    q = (X.double() @ Wqk[:E].double().T + bqk[:E].double()).float()
+    k = (Y.double() @ Wqk[E:].double().T + bqk[E:].double()).float()
+    v = (Y.double() @ Wv.double().T).float()
+    mask = (torch.rand(B, Lk, generator=g) < 0.2).to(DEV).to(torch.uint8) if Lk == 333 else None
+    ref = _attn_ref(q, k, v, mask, B, Lq, Lk, 8)
+    qp = ops.gemm_bf16_tc(ops.split_rows(X), ops.x3_weight(Wqk[:E].contiguous()), bqk[:E].contiguous(), x3=True,
+                          headsplit_Lk=Lq, headsplit_pair=True)
+    kp = ops.gemm_bf16_tc(ops.split_rows(Y), ops.x3_weight(Wqk[E:].contiguous()), bqk[E:].contiguous(), x3=True,
+                          headsplit_Lk=Lk, headsplit_pair=True)
+    vp = ops.gemm_bf16_tc(ops.split_rows(Y), ops.x3_weight(Wv), None, x3=True, headsplit_Lk=Lk, headsplit_pair=True)
+    qh = (qp[0, 0].float() + qp[1, 0].float()).permute(0, 2, 1, 3).reshape(B * Lq, E)
+    assert (qh - q).abs().max() <= 1e-4 * max(1.0, q.abs().max().item())
+    sp = torch.empty(B * Lq, 2 * E, dtype=torch.bfloat16, device=DEV)
+    got = ops.attention_x3_tc(qp[:, 0], kp[:, 0], vp[:, 0], mask, B, Lq, Lk, 8, nsplit, out_split=sp)
+    err = (got - ref).abs().max().item()
+    assert err <= 3e-4 * max(1.0, ref.abs().max().item()), err
+    assert (sp[:, :E].float() + sp[:, E:].float() - got).abs().max() <= 1e-4
+
+
 def test_gemm_bf16_tc_headsplit():
     B, Lk, K = 2, 200, 256
     g = torch.Generator().manual_seed(9)
