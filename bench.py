@@ -135,7 +135,7 @@ def run_reference(args, wl, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vov-p4-1600x640")
@@ -225,19 +225,40 @@ def main():
     out_host = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
                 for k in ("all_cls_scores", "all_bbox_preds")}
 
-    def e2e_step():
-        xd = x_host.to(dev, non_blocking=True)
-        o = head([xd], metas)
-        for k in out_host:
-            out_host[k].copy_(o[k], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    # Each step copies that step's features from pinned host memory, runs the public
+    # PETRHead.forward and reads the outputs back; the H2D copy of step i+1 runs on a second stream
+    # while step i computes (double-buffered device input), all inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    x_bufs = [torch.empty_like(x_dev) for _ in range(2)]
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
 
-    for _ in range(2):
-        e2e_step()
+    def e2e_run(nsteps):
+        def prefetch(i):
+            slot = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_free[slot])
+                x_bufs[slot].copy_(x_host, non_blocking=True)
+                ev_copied[slot].record(copy_stream)
+        for slot in range(2):
+            ev_free[slot].record(main_stream)
+        prefetch(0)
+        for i in range(nsteps):
+            slot = i % 2
+            if i + 1 < nsteps:
+                prefetch(i + 1)
+            main_stream.wait_event(ev_copied[slot])
+            o = head([x_bufs[slot]], metas)
+            ev_free[slot].record(main_stream)
+            for k in out_host:
+                out_host[k].copy_(o[k], non_blocking=True)
+        main_stream.synchronize()
+
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * B * args.steps / e2e_s
@@ -258,7 +279,7 @@ def main():
         s = head.engine.spec
         flops = 4.0 * s.Lq * wl.num_keys * s.E * B                  # per launch (one layer, B samples)
         achieved = flops / (avg_ms * 1e-3) / 1e12
-        roofline = dict(kernel="cross_attention_tc_kernel", bound="tensor", achieved=achieved,
+        roofline = dict(kernel="cross_attention_tc2_kernel", bound="tensor", achieved=achieved,
                         peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_sustained"],
                         traffic=None, peak_source=peaks["source"] + " bf16 sustained",
                         launches_timed=len(evs), avg_launch_ms=avg_ms,

@@ -55,7 +55,7 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;                 // 48 KB
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 
 struct EpiParams {
     const float* bias; const float* residual; int act; float alpha;
@@ -96,7 +96,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -152,8 +152,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {
-        // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+        // epilogue: 8 warps; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) and takes column
+        // half (w-2)/4 of the 256-wide tile.  TMEM loads are software-pipelined one chunk ahead.
         const int quarter = warp & 3;
+        const int chalf = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
@@ -164,11 +166,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tcgen05_fence_after();
             int kv_b = 0, kv_key = 0;
             if ((p.out_mode == 2 || p.out_mode == 4) && m < p.M) { kv_b = m / p.kv_Lk; kv_key = m - kv_b * p.kv_Lk; }
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + c * 32, r);
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + chalf * 128;
+            uint32_t rbuf[2][32];
+            tmem_ld_x32(t_addr, rbuf[0]);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = chalf * 4 + cc;
+                uint32_t* r = rbuf[cc & 1];
                 tmem_ld_wait();
+                if (cc + 1 < 4) tmem_ld_x32(t_addr + (cc + 1) * 32, rbuf[(cc + 1) & 1]);
                 const int nb = n0 + c * 32;
                 if (m >= p.M || nb >= p.N) continue;
                 const bool full = (nb + 32 <= p.N);

@@ -195,5 +195,6 @@ def test_full_size_properties(wn, B):
         assert torch.equal(o16[k], o16b[k])
     if B > 1:
         o1 = head([x[1:2]], metas[1:2])
+        # a different batch size changes the split-KV plan (summation order of bf16 partials)
         for k in ("all_cls_scores", "all_bbox_preds"):
-            assert (o1[k][:, 0] - o16[k][:, 1]).abs().max() <= 5e-3
+            assert (o1[k][:, 0] - o16[k][:, 1]).abs().max() <= 2e-2

@@ -314,7 +314,7 @@ def test_attention_x3_tc_fp32_class(B, Lq, Lk, scale, nsplit):
     got = ops.attention_x3_tc(qp[:, 0], kp[:, 0], vp[:, 0], mask, B, Lq, Lk, 8, nsplit, out_split=sp)
     err = (got - ref).abs().max().item()
     assert err <= 3e-4 * max(1.0, ref.abs().max().item()), err
-    assert (sp[:, :E].float() + sp[:, E:].float() - got).abs().max() <= 1e-4
+    assert (sp[:, :E].float() + sp[:, E:].float() - got).abs().max() <= 2e-5 * max(1.0, got.abs().max().item())
 
 
 def test_gemm_bf16_tc_headsplit():
