@@ -42,6 +42,20 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
+// exp2 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic
+// minimax for 2^f (max rel. error 7.6e-5 = 2^-13.7, 24x below bf16 half-ulp), exponent add.  Used
+// for a fixed share of the score elements so that the MUFU pipe (16 ex2/clk/SM) and the issue slots
+// are both busy.  x is clamped at -126 (masked keys arrive as -inf).
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.f);
+    const float t = x + 12582912.f;               // 1.5 * 2^23: integer part lands in the low mantissa bits
+    const float f = x - (t - 12582912.f);
+    float pz = fmaf(0.05520550534129143f, f, 0.24261397123336792f);
+    pz = fmaf(pz, f, 0.6932547688484192f);
+    pz = fmaf(pz, f, 0.9999276995658875f);
+    return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
+}
+
 struct AttParams {
     const uint8_t* key_mask;   // [B, Lk] or null
     float* O; int ldo;         // normalised output (nsplit == 1), nullable
@@ -344,15 +358,24 @@ namespace v2 {
 constexpr int NQT = 2;
 constexpr int OFF_Q = 0;                                            // 2 x 8 KB
 constexpr int OFF_KV = OFF_Q + NQT * Q_BYTES;                       // 4 x 16 KB
-constexpr int OFF_P = OFF_KV + KV_STAGES * (K_BYTES + V_BYTES);     // 2 x 32 KB
-constexpr int OFF_ONES = OFF_P + NQT * P_BYTES;                     // 4 KB of bf16 1.0
+constexpr int OFF_P = OFF_KV + KV_STAGES * (K_BYTES + V_BYTES);     // P[x][buf]: 2 x 2 x 32 KB
+constexpr int OFF_ONES = OFF_P + NQT * 2 * P_BYTES;                 // 4 KB of bf16 1.0
 constexpr int OFF_BIAS = OFF_ONES + 4096;                           // 2 x 128 floats
 constexpr int OFF_BAR = OFF_BIAS + NQT * KT * 4;
 constexpr int SMEM = OFF_BAR + 256 + 1024;
-constexpr int THREADS = 320;
+constexpr int THREADS = 352;        // TMA, MMA-A, 2x4 softmax, MMA-B
 constexpr int TM_S = 0;          // S_x at TM_S + 128 x
 constexpr int TM_O = 256;        // O_x at TM_O + 48 x (32 cols), L_x right behind it (16 cols)
 
+// kPoly of every 16 score elements take ex2_poly instead of MUFU ex2.
+template <int kPoly>
+__device__ __forceinline__ float ex2_sel(float x, int i) {
+    // spread the polynomial lanes evenly over each group of 16
+    const bool poly = ((i & 15) * kPoly) / 16 != (((i & 15) + 1) * kPoly) / 16;
+    return poly ? ex2_poly(x) : ex2(x);
+}
+
+template <int kPoly, bool kStagger>
 __global__ void __launch_bounds__(THREADS, 1)
 cross_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                            const __grid_constant__ CUtensorMap tmV, AttParams p) {
@@ -364,9 +387,10 @@ cross_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     uint64_t* kv_empty = kv_full + KV_STAGES;       // KV_STAGES
     uint64_t* s_full = kv_empty + KV_STAGES;        // 2 (A, B)
     uint64_t* s_free = s_full + 2;
-    uint64_t* p_ready = s_free + 2;
-    uint64_t* pv_done = p_ready + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+    uint64_t* p_ready = s_free + 2;                 // [x][buf], index 2x + buf
+    uint64_t* pv_done = p_ready + 4;                // [x][buf]
+    uint64_t* half_a = pv_done + 4;                 // tile A is half way through its first key tile
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(half_a + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (NQT * QT);
@@ -388,11 +412,10 @@ cross_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(q_full, 1);
-            for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-            for (int i = 0; i < 2; ++i) {
-                mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128);
-                mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1);
-            }
+            for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); }
+            for (int i = 0; i < 4; ++i) { mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1); }
+            mbar_init(half_a, 128);
             fence_barrier_init();
         }
         __syncwarp();
@@ -419,51 +442,60 @@ cross_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
                 tma_load_3d(kd + K_BYTES, &tmV, &kv_full[s], 0, key0, bh);
             }
         }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
+    } else if (warp == 1 || warp == 10) {
+        // ---------------- MMA issuers: warp 1 drives query tile A, warp 10 tile B ----------------
+        // (a single issuing thread for both tiles was the critical path: 36 tcgen05.mma + their
+        // descriptor arithmetic per key tile).  All descriptors that do not depend on the K/V stage
+        // are built once; per-stage ones are one 64-bit add.
         if (lane == 0 && ntiles > 0) {
+            const int x = (warp == 1) ? 0 : 1;
             constexpr uint32_t idesc_qk = make_idesc(QT, KT, 1, 0, 0);     // S[128x128] = Q K^T
             constexpr uint32_t idesc_pv = make_idesc(QT, HD, 1, 0, 1);     // O[128x32] += P V (V MN-major)
             constexpr uint32_t idesc_l = make_idesc(QT, 16, 1, 0, 0);      // L[128x16] += P 1
+            const uint32_t q_addr = smem_u32(smem + OFF_Q + x * Q_BYTES);
+            const uint32_t p_addr = smem_u32(smem + OFF_P + x * 2 * P_BYTES);      // buffer 0; buffer 1 is P_BYTES further
             const uint32_t ones_addr = smem_u32(smem + OFF_ONES);
+            const uint32_t kv_addr = smem_u32(smem + OFF_KV);
+            const uint64_t q_desc0 = make_smem_desc(q_addr, 16, 512, LAYOUT_SW64);
+            const uint64_t k_desc0 = make_smem_desc(kv_addr, 16, 512, LAYOUT_SW64);
+            const uint64_t v_desc0 = make_smem_desc(kv_addr + K_BYTES, 512, 512, LAYOUT_SW64);
+            uint64_t p_desc[KT / 16], o_desc[KT / 16];
+#pragma unroll
+            for (int kk = 0; kk < KT / 16; ++kk) {
+                p_desc[kk] = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+                o_desc[kk] = make_smem_desc(ones_addr + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+            }
+            const uint32_t d_s = tmem_base + TM_S + x * 128;
+            const uint32_t d_o = tmem_base + TM_O + x * 48, d_l = d_o + 32;
             auto issue_pv = [&](int t) {
                 const int s = t % KV_STAGES;
-                const uint32_t v_addr = smem_u32(smem + OFF_KV + s * (K_BYTES + V_BYTES) + K_BYTES);
-                for (int x = 0; x < NQT; ++x) {
-                    mbar_wait(&p_ready[x], t & 1);
-                    tcgen05_fence_after();
-                    const uint32_t p_addr = smem_u32(smem + OFF_P + x * P_BYTES);
-                    const uint32_t d_o = tmem_base + TM_O + x * 48, d_l = d_o + 32;
+                const uint64_t vd = v_desc0 + (uint64_t)((s * (K_BYTES + V_BYTES)) >> 4);
+                const uint64_t pb = (uint64_t)(((t & 1) * P_BYTES) >> 4);            // P buffer of tile t
+                mbar_wait(&p_ready[2 * x + (t & 1)], (t >> 1) & 1);
+                tcgen05_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < KT / 16; ++kk) {
-                        uint64_t ad = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
-                        uint64_t bd = make_smem_desc(v_addr + kk * 1024, 512, 512, LAYOUT_SW64);
-                        uint64_t od = make_smem_desc(ones_addr + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
-                        umma_f16_ss(d_o, ad, bd, idesc_pv, (t | kk) ? 1u : 0u);
-                        umma_f16_ss(d_l, ad, od, idesc_l, (t | kk) ? 1u : 0u);
-                    }
-                    umma_commit(&pv_done[x]);
+                for (int kk = 0; kk < KT / 16; ++kk) {
+                    umma_f16_ss(d_o, p_desc[kk] + pb, vd + (uint64_t)((kk * 1024) >> 4), idesc_pv, (t | kk) ? 1u : 0u);
+                    umma_f16_ss(d_l, p_desc[kk] + pb, o_desc[kk], idesc_l, (t | kk) ? 1u : 0u);
                 }
-                umma_commit(&kv_empty[s]);
+                umma_commit(&pv_done[2 * x + (t & 1)]);
+                umma_commit(&kv_empty[s]);                   // count 2: both tiles done with this stage
             };
             mbar_wait(q_full, 0);
+            // Stagger the two tiles by half a key tile: the A and B softmax warps that share an SM
+            // sub-partition then alternate between their exp2 phase (MUFU) and their TMEM-load / max /
+            // P-store phase instead of running them in lockstep.
+            if (kStagger && x == 1) mbar_wait(half_a, 0);
             for (int j = 0; j < ntiles; ++j) {
                 const int s = j % KV_STAGES;
+                const uint64_t kd = k_desc0 + (uint64_t)((s * (K_BYTES + V_BYTES)) >> 4);
                 mbar_wait(&kv_full[s], (j / KV_STAGES) & 1);
-                const uint32_t k_addr = smem_u32(smem + OFF_KV + s * (K_BYTES + V_BYTES));
-                for (int x = 0; x < NQT; ++x) {
-                    mbar_wait(&s_free[x], (j & 1) ^ 1);
-                    tcgen05_fence_after();
-                    const uint32_t q_addr = smem_u32(smem + OFF_Q + x * Q_BYTES);
-                    const uint32_t d = tmem_base + TM_S + x * 128;
+                mbar_wait(&s_free[x], (j & 1) ^ 1);
+                tcgen05_fence_after();
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k) {
-                        uint64_t ad = make_smem_desc(q_addr + k * 32, 16, 512, LAYOUT_SW64);
-                        uint64_t bd = make_smem_desc(k_addr + k * 32, 16, 512, LAYOUT_SW64);
-                        umma_f16_ss(d, ad, bd, idesc_qk, k ? 1u : 0u);
-                    }
-                    umma_commit(&s_full[x]);
-                }
+                for (int k = 0; k < HD / 16; ++k)
+                    umma_f16_ss(d_s, q_desc0 + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_qk, k ? 1u : 0u);
+                umma_commit(&s_full[x]);
                 if (j > 0) issue_pv(j - 1);
             }
             issue_pv(ntiles - 1);
@@ -477,7 +509,7 @@ cross_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         const uint32_t s_addr = tmem_base + lane_off + TM_S + x * 128;
         const uint32_t o_addr = tmem_base + lane_off + TM_O + x * 48;
         float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS) + x * KT;
-        uint8_t* pbase = smem + OFF_P + x * P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+        uint8_t* pbase = smem + OFF_P + x * 2 * P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
         float m_use = -INFINITY;
         const bool use_mask = (p.key_mask != nullptr);
         for (int j = 0; j < ntiles; ++j) {
@@ -519,17 +551,38 @@ cross_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
             if (grow) { alpha = ex2(m_use - mx); m_use = mx; }
             const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
             uint32_t pk[64];
+            if (kStagger && x == 0 && j == 0) {
+                // first half of tile 0's exponentials, then release tile B (see the MMA-B warp)
 #pragma unroll
-            for (int i = 0; i < 128; i += 2)
-                pk[i >> 1] = pack_bf16x2(ex2(sv[i] - m_eff), ex2(sv[i + 1] - m_eff));
-            // P_x / O_x / L_x are free once PV_x(j-1) has retired
-            mbar_wait(&pv_done[x], par ^ 1);
+                for (int i = 0; i < 64; i += 2)
+                    pk[i >> 1] = pack_bf16x2(ex2(sv[i] - m_eff), ex2(sv[i + 1] - m_eff));
+                mbar_arrive(half_a);
+#pragma unroll
+                for (int i = 64; i < 128; i += 2)
+                    pk[i >> 1] = pack_bf16x2(ex2(sv[i] - m_eff), ex2(sv[i + 1] - m_eff));
+            } else if (kPoly > 0 && !need_bias) {
+                // all scores finite: a share of the exponentials goes to the FMA pipe
+#pragma unroll
+                for (int i = 0; i < 128; i += 2)
+                    pk[i >> 1] = pack_bf16x2(ex2_sel<kPoly>(sv[i] - m_eff, i), ex2_sel<kPoly>(sv[i + 1] - m_eff, i + 1));
+            } else {
+                // masked / tail tiles carry -inf scores: MUFU ex2 returns the exact zeros that make
+                // fully masked rows NaN like the reference
+#pragma unroll
+                for (int i = 0; i < 128; i += 2)
+                    pk[i >> 1] = pack_bf16x2(ex2(sv[i] - m_eff), ex2(sv[i + 1] - m_eff));
+            }
+            // P is double buffered: buffer j&1 is free once PV_x(j-2) has retired, so the softmax
+            // warps never wait for their own previous P V product
+            mbar_wait(&pv_done[2 * x + par], ((j >> 1) & 1) ^ 1);
+            uint8_t* pb = pbase + par * P_BYTES;
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-                uint8_t* dst = pbase + (c >> 3) * 16384 + (((c & 7) ^ (row & 7)) << 4);
+                uint8_t* dst = pb + (c >> 3) * 16384 + (((c & 7) ^ (row & 7)) << 4);
                 *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             }
-            if (j > 0 && __any_sync(0xffffffffu, grow)) {        // correction: (O, L) *= alpha
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {        // correction: (O, L) *= alpha after PV_x(j-1)
+                mbar_wait(&pv_done[2 * x + (par ^ 1)], ((j - 1) >> 1) & 1);
                 tcgen05_fence_after();
                 uint32_t orr[48];
                 tmem_ld_x32(o_addr, orr);
@@ -543,13 +596,13 @@ cross_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
             }
             fence_proxy_async_smem();
             tcgen05_fence_before();
-            mbar_arrive(&p_ready[x]);
+            mbar_arrive(&p_ready[2 * x + par]);
         }
         // ---------------- epilogue ----------------
         const int q = q0 + x * QT + row;
         float o[32], l = 0.f;
         if (ntiles > 0) {
-            mbar_wait(&pv_done[x], (ntiles - 1) & 1);
+            mbar_wait(&pv_done[2 * x + ((ntiles - 1) & 1)], ((ntiles - 1) >> 1) & 1);
             tcgen05_fence_after();
             uint32_t orr[48];
             tmem_ld_x32(o_addr, orr);
@@ -682,7 +735,17 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
         rc = tmap::encode(&tmV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Vh, d, s, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
     }
-    cudaError_t e = cudaFuncSetAttribute(v2::cross_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM);
+    // share of exponentials evaluated on the FMA pipe (x/16).  Measured on B200 (B = 16, 24 000 keys):
+    // 0/16 -> 1.30 ms, 4/16 -> 1.42 ms, 8/16 -> 1.56 ms per launch: the softmax warps are issue-bound, not
+    // MUFU-bound, so the default is 0; PETR_FLASH_POLY overrides for experiments (masked rows then
+    // lose the exact-zero probabilities that make fully masked samples NaN).
+    static const int poly = getenv("PETR_FLASH_POLY") ? atoi(getenv("PETR_FLASH_POLY")) : 0;
+    static const bool stagger = getenv("PETR_FLASH_STAGGER") != nullptr;   // measured slower (1.23 vs 1.11 ms): off
+    auto kern = poly <= 0 ? (stagger ? v2::cross_attention_tc2_kernel<0, true> : v2::cross_attention_tc2_kernel<0, false>)
+              : poly <= 3 ? v2::cross_attention_tc2_kernel<3, true>
+              : poly == 4 ? v2::cross_attention_tc2_kernel<4, true>
+              : v2::cross_attention_tc2_kernel<6, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM);
     if (e != cudaSuccess) return fail((int)e, "petr_cross_attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     AttParams p{};
     p.key_mask = key_mask; p.O = O; p.ldo = ldo; p.O_split = (__nv_bfloat16*)O_split;
@@ -691,7 +754,7 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
     p.B = B; p.Lq = Lq; p.Lk = Lk; p.heads = heads; p.nsplit = nsplit; p.tiles_total = tiles;
     p.write_partial = part ? 1 : 0;
     dim3 grid((Lq + 2 * QT - 1) / (2 * QT), B * heads, nsplit);
-    v2::cross_attention_tc2_kernel<<<grid, v2::THREADS, v2::SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    kern<<<grid, v2::THREADS, v2::SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
     int rc = after_launch("petr_cross_attention_bf16");
     if (rc) return rc;
     if (part && !write_partial) {
