@@ -144,6 +144,9 @@ def main():
     ap.add_argument("--cpu-samples", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print per-op CUDA-event times to stderr")
+    ap.add_argument("--keysplit", action="store_true",
+                    help="BASELINE config 4: every rank works on the SAME samples, keys split over camera "
+                         "views, one NCCL all-gather of (O, m, l) partials per decoder layer (strong scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -173,9 +176,13 @@ def main():
     head.load_state_dict(synth.head_state_dict(head, 0), strict=True)
     head = head.eval().to(dev)
     head.precision = args.precision
-    # each rank gets its own shard of the global batch (different seeds per rank)
-    metas = synth.make_img_metas(wl, B, seed=rank)
-    x_host = synth.make_features(wl, B, seed=rank, pin=True)
+    if args.keysplit and world > 1:
+        head.keysplit = dict(world=world, rank=rank, group=None)
+    # data parallel: each rank gets its own shard of the global batch (different seeds per rank);
+    # key-split: every rank gets the same samples
+    data_seed = 0 if args.keysplit else rank
+    metas = synth.make_img_metas(wl, B, seed=data_seed)
+    x_host = synth.make_features(wl, B, seed=data_seed, pin=True)
     x_dev = x_host.to(dev, non_blocking=True)
     torch.cuda.synchronize()
 
@@ -219,7 +226,8 @@ def main():
     timers = _lib.TIMERS
     _lib.TIMERS = None
     ms_per_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total / 1000.0)
+    nrep = 1 if args.keysplit else world          # key-split: all ranks share the same samples
+    value = nrep * B * args.steps / (ms_total / 1000.0)
 
     # ---- end-to-end through the public API with host buffers (`e2e`) -------------------------
     out_host = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
@@ -261,7 +269,7 @@ def main():
     e2e_run(args.steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * B * args.steps / e2e_s
+    e2e_value = nrep * B * args.steps / e2e_s
     h2d = x_host.numel() * 4 + B * wl.num_cams * (64 + 8)
     d2h = sum(t.numel() * 4 for t in out_host.values())
 
@@ -295,12 +303,14 @@ def main():
                        sample=f"{len(times)} single-sample head forwards of {wl.name} "
                               f"(oracle/petr_oracle.py, torch CPU fp32, {cores} threads)")
         line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps,
-                    warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
+                    warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
+                    scaling="strong" if args.keysplit else "weak",
                     vs_baseline=None, dtype="bf16" if args.precision == "bf16" else "f32",
                     data="synthetic",
-                    config=dict(workload=wl.name, batch_per_gpu=B, global_batch=B * world,
+                    config=dict(workload=wl.name, batch_per_gpu=B, global_batch=B * nrep,
                                 num_keys=wl.num_keys, num_query=900, decoder_layers=6,
-                                parallelism=f"dp{world}", precision=args.precision,
+                                parallelism=(f"keysplit{world}" if args.keysplit else f"dp{world}"),
+                                precision=args.precision,
                                 l2="inputs larger than L2 (%.0f MB features per step)" % (x_host.numel() * 4 / 1e6)),
                     e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=int(h2d),
                              d2h_bytes_per_step=int(d2h)),

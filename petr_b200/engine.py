@@ -50,9 +50,39 @@ def mean_time_stamp(img_metas: Sequence[dict]) -> torch.Tensor:
     return (ts[:, 1, :] - ts[:, 0, :]).mean(-1)
 
 
+class _PinnedRing:
+    """Reusable pinned staging buffers for the small per-call host inputs (img2lidar, img_shape,
+    timestamps): cudaHostAlloc per call would serialise the stream.  A ring of 8 buffers per
+    (shape, dtype); a slot is reused only after the copy that last read it has completed."""
+
+    def __init__(self, depth: int = 8):
+        self.depth = depth
+        self.slots = {}
+
+    def stage(self, t: torch.Tensor, device) -> torch.Tensor:
+        key = (tuple(t.shape), t.dtype, str(device))
+        ring = self.slots.setdefault(key, dict(i=0, bufs=[], evs=[]))
+        if len(ring["bufs"]) < self.depth:
+            ring["bufs"].append(torch.empty(t.shape, dtype=t.dtype).pin_memory())
+            ring["evs"].append(None)
+        i = ring["i"] % len(ring["bufs"])
+        ring["i"] += 1
+        if ring["evs"][i] is not None:
+            ring["evs"][i].synchronize()
+        ring["bufs"][i].copy_(t)
+        out = ring["bufs"][i].to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        ring["evs"][i] = ev
+        return out
+
+
+_PINNED = _PinnedRing()
+
+
 def _h2d(arr, device) -> torch.Tensor:
     t = torch.from_numpy(np.ascontiguousarray(arr)) if isinstance(arr, np.ndarray) else arr
-    return t.pin_memory().to(device, non_blocking=True)
+    return _PINNED.stage(t, device)
 
 
 def sine_dim_t(num_feats: int, temperature: float) -> torch.Tensor:
@@ -259,12 +289,22 @@ class HeadEngine:
     # -------------------------------------------------------------------------------------
     # key side / decoder layer / whole head
     # -------------------------------------------------------------------------------------
-    def key_side(self, x: torch.Tensor, img_metas: List[dict], precision: str, taps=None) -> dict:
+    def key_side(self, x: torch.Tensor, img_metas: List[dict], precision: str, taps=None,
+                 keysplit: Optional[dict] = None) -> dict:
         """Everything that depends on the image tokens (petr_head.py:381-402 and the K/V side of
-        petr_transformer.py:341-344).  Returns the per-forward key-side state."""
+        petr_transformer.py:341-344).  Returns the per-forward key-side state.
+        keysplit: dict(world, rank, group) -> this rank's share of a key-split over camera views;
+        dict(world, emulate=True) -> all shards on this device (bf16 path only)."""
         if precision == "bf16":
-            from .engine_tc import key_side_tc
-            return key_side_tc(self, x, img_metas, taps)
+            from . import engine_tc as tc
+            if keysplit:
+                if keysplit.get("emulate"):
+                    return tc.key_side_keysplit_emulated(self, x, img_metas, keysplit["world"], taps)
+                return tc.key_side_keysplit(self, x, img_metas, keysplit["world"], keysplit["rank"],
+                                            keysplit.get("group"), taps)
+            return tc.key_side_tc(self, x, img_metas, taps)
+        if keysplit:
+            raise NotImplementedError("key-split over views is implemented on the bf16 (tcgen05) path")
         s = self.spec
         x = x.float().contiguous()
         B, N, Cin, H, W = x.shape
@@ -301,7 +341,7 @@ class HeadEngine:
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, img_metas: List[dict], precision: str = "bf16",
-                taps: Optional[dict] = None) -> dict:
+                taps: Optional[dict] = None, keysplit: Optional[dict] = None) -> dict:
         if not x.is_cuda:
             raise RuntimeError("petr_b200: features must be CUDA tensors (no CPU fallback)")
         if precision not in ("fp32", "bf16"):
@@ -311,7 +351,7 @@ class HeadEngine:
             raise NotImplementedError("petr_b200 implements with_multiview=True (all shipped configs)")
         dev = x.device
         P = self.packed(dev)
-        ks = self.key_side(x, img_metas, precision, taps)
+        ks = self.key_side(x, img_metas, precision, taps, keysplit)
         B = ks["B"]
         qpos = self.query_embeds(P)
         time_div = _h2d(mean_time_stamp(img_metas), dev) if s.with_time else None

@@ -98,23 +98,53 @@ def packed_tc(eng, device) -> dict:
     return T
 
 
-def key_side_tc(eng, x, img_metas, taps=None):
+def slice_img_metas(img_metas, views: slice):
+    """img_metas restricted to a contiguous range of camera views (key-split over views)."""
+    out = []
+    for m in img_metas:
+        d = dict(m)
+        for k in ("lidar2img", "img_shape"):
+            d[k] = list(m[k])[views]
+        out.append(d)
+    return out
+
+
+def shard_views(num_views: int, world: int, rank: int) -> slice:
+    """Contiguous, balanced split of the camera views over ranks (rank r owns views [lo, hi))."""
+    base, rem = divmod(num_views, world)
+    lo = rank * base + min(rank, rem)
+    return slice(lo, lo + base + (1 if rank < rem else 0))
+
+
+def key_side_tc(eng, x, img_metas, taps=None, views: slice = None):
     """Everything that depends on the image tokens: masks, input_proj, position embedding,
     K/V projection of all layers.  Returns the key-side state: Kh, Vh (L,B,heads,Lk,32) bf16,
-    kmask (None when no key is padded), the split-KV plan."""
+    kmask (None when no key is padded), the split-KV plan.
+
+    views: this rank's contiguous range of camera views (key-split).  The
+    sine encoding is cumulative over ALL views (positional_encoding.py:71), so masks and sine
+    features are evaluated for every view (cheap) and only the local rows are kept."""
     s = eng.spec
     if s.E != 256 or s.heads != 8:
         raise NotImplementedError("tcgen05 path is specialised for embed_dims 256, 8 heads of 32")
-    x = x.float().contiguous()
-    B, N, Cin, H, W = x.shape
+    x = x.float()
+    B, N_all, Cin, H, W = x.shape
     if Cin % 64 != 0:
         raise NotImplementedError("tcgen05 path needs in_channels % 64 == 0")
     dev = x.device
-    Lk = N * H * W
     E = s.E
     P = eng.packed(dev)
     T = packed_tc(eng, dev)
-    masks = eng.masks(img_metas, B, N, H, W, dev)
+    masks_all = eng.masks(img_metas, B, N_all, H, W, dev)
+    if views is not None:
+        x = x[:, views]
+        masks = masks_all[:, views].contiguous()
+        metas_all, img_metas = img_metas, slice_img_metas(img_metas, views)
+    else:
+        masks = masks_all
+    x = x.contiguous()
+    N = x.shape[1]
+    Lk = N * H * W
     has_mask = any_key_masked(img_metas, N, H, W)
     # input_proj (petr_head.py:390): fp32 NCHW -> bf16 tokens -> tcgen05 GEMM; mem kept in fp32 (for
     # the K input mem + pos) and as bf16 [hi | lo] whose hi half is the V-projection operand
@@ -122,7 +152,9 @@ def key_side_tc(eng, x, img_metas, taps=None):
     mem = torch.empty((B * Lk, E), dtype=torch.float32, device=dev)
     mem_split = ops.gemm_bf16_tc(xt, T["in_w"], P["in_b"], split_out=True, out_f32=mem, name="gemm_input_proj")
     vin = mem_split[:, :E]
-    sf = ops.sine3d_features(masks, P["dim_t_sine"], dtype=torch.bfloat16, **_sine_args(s))
+    sf = ops.sine3d_features(masks_all, P["dim_t_sine"], dtype=torch.bfloat16, **_sine_args(s))
+    if views is not None:
+        sf = sf.view(B, N_all, H * W, -1)[:, views].reshape(B * Lk, -1).contiguous()
     h2 = ops.gemm_bf16_tc(sf, T["ad_w1"], P["ad_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_adapt1")
     if s.with_position:
         feat, _, _ = eng.frustum(img_metas, B, N, H, W, dev, None, torch.bfloat16, want_mask=False)
@@ -183,8 +215,11 @@ def decoder_layer_tc(eng, P, l: int, st: dict, qpos, ks: dict, last: bool) -> di
     ops.layernorm_multi(y, *lw["ln"][0], qpos=qpos, Y=X1, Ypos_split=X1ps)
     # ---- cross-attention (PETRMultiheadAttention) ----
     qs = g(X1ps, tw["ca_q"], tw["ca_q_b"], x3=True, alpha=Q_SCALE, headsplit_Lk=s.Lq, name="gemm_q_side")
-    ops.cross_attention_bf16(qs[0], ks["Kh"][l], ks["Vh"][l], ks["kmask"], B, s.Lq, ks["Lk"], s.heads,
-                             ks["nsplit"], partial=ks["partial"], out_split=o_s, want_f32=False)
+    if "xattn" in ks:
+        ks["xattn"](qs[0], l, o_s)                           # key-split: partials + exchange + merge
+    else:
+        ops.cross_attention_bf16(qs[0], ks["Kh"][l], ks["Vh"][l], ks["kmask"], B, s.Lq, ks["Lk"], s.heads,
+                                 ks["nsplit"], partial=ks["partial"], out_split=o_s, want_f32=False)
     y = g(o_s, tw["ca_out"], lw["ca_out_b"], residual=X1, x3=True, name="gemm_q_side")
     X2 = torch.empty_like(y)
     X2s = torch.empty((R, 2 * E), dtype=torch.bfloat16, device=dev)
@@ -272,3 +307,54 @@ def state_from_rows(eng, X, qpos, st_like: dict) -> dict:
     """Teacher-forcing helper (tests): rebuild the split forms of an externally supplied X."""
     return dict(X=X, Xs=ops.split_rows(X), Xps=ops.split_rows(X, add=qpos), outs=st_like["outs"],
                 outs_split=st_like["outs_split"])
+
+
+# ----------------------------------------------------------------------------------------------
+# key-split over camera views (SURVEY.md section 8e): rank r owns a contiguous range of views, runs
+# the key side and the partial (un-normalised) cross-attention on its keys; per layer the packed
+# [O | m, l] partials are exchanged with ONE all-gather and merged by petr_attention_merge (the same
+# kernel and layout as on-GPU split-KV).  Queries / self-attention / FFN / branches are replicated.
+# ----------------------------------------------------------------------------------------------
+def key_side_keysplit(eng, x, img_metas, world: int, rank: int, group=None, taps=None) -> dict:
+    """Key-side state of one rank of a `world`-way key-split (torch.distributed NCCL group)."""
+    import torch.distributed as dist
+    s = eng.spec
+    N = x.shape[1]
+    ks = key_side_tc(eng, x, img_metas, taps, views=shard_views(N, world, rank))
+    B = ks["B"]
+    floats = ops.attention_partial_floats(B, s.Lq, s.heads)
+    local = torch.empty((floats,), dtype=torch.float32, device=x.device)
+    gathered = torch.empty((world * floats,), dtype=torch.float32, device=x.device)
+
+    def xattn(qs, l, o_s):
+        ops.cross_attention_bf16(qs, ks["Kh"][l], ks["Vh"][l], ks["kmask"], B, s.Lq, ks["Lk"], s.heads, 1,
+                                 partial=local, write_partial=True)
+        dist.all_gather_into_tensor(gathered, local, group=group)
+        ops.attention_merge(gathered, world, B, s.Lq, s.heads, out_split=o_s, want_f32=False)
+
+    ks["xattn"] = xattn
+    return ks
+
+
+def key_side_keysplit_emulated(eng, x, img_metas, world: int, taps=None) -> dict:
+    """Single-GPU emulation of a `world`-way key-split: every rank's shard is processed in turn on
+    this device and the partials are laid out exactly as the all-gather would (tests; also the
+    documented way to exercise the N-rank path with fewer GPUs than ranks)."""
+    s = eng.spec
+    N = x.shape[1]
+    shards = [key_side_tc(eng, x, img_metas, taps if r == 0 else None, views=shard_views(N, world, r))
+              for r in range(world)]
+    B = shards[0]["B"]
+    floats = ops.attention_partial_floats(B, s.Lq, s.heads)
+    gathered = torch.empty((world * floats,), dtype=torch.float32, device=x.device)
+
+    def xattn(qs, l, o_s):
+        for r, k in enumerate(shards):
+            ops.cross_attention_bf16(qs, k["Kh"][l], k["Vh"][l], k["kmask"], B, s.Lq, k["Lk"], s.heads, 1,
+                                     partial=gathered[r * floats:(r + 1) * floats], write_partial=True)
+        ops.attention_merge(gathered, world, B, s.Lq, s.heads, out_split=o_s, want_f32=False)
+
+    out = dict(shards[0])
+    out["xattn"] = xattn
+    out["Lk"] = sum(k["Lk"] for k in shards)
+    return out

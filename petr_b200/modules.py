@@ -517,6 +517,9 @@ class _PETRHeadBase(BaseModule):
         self.pc_range = self.bbox_coder.pc_range
         self._engine = None
         self.precision = 'bf16'
+        # None: samples are simply data-parallel.  dict(world, rank, group): this process computes its
+        # share of a key-split over camera views (every rank passes the full inputs, gets the full outputs)
+        self.keysplit = None
 
     # -- layers ---------------------------------------------------------------------------
     def _make_cls_branch(self):
@@ -601,7 +604,7 @@ class _PETRHeadBase(BaseModule):
         """petr_head.py:366-468 / petrv2_head.py:429-540."""
         _require_eval(self)
         x = mlvl_feats[self.position_level]
-        return self.engine.forward(x, img_metas, precision=self.precision)
+        return self.engine.forward(x, img_metas, precision=self.precision, keysplit=self.keysplit)
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys,
                               unexpected_keys, error_msgs):

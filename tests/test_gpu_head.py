@@ -198,3 +198,20 @@ def test_full_size_properties(wn, B):
         # a different batch size changes the split-KV plan (summation order of bf16 partials)
         for k in ("all_cls_scores", "all_bbox_preds"):
             assert (o1[k][:, 0] - o16[k][:, 1]).abs().max() <= 2e-2
+
+
+@pytest.mark.parametrize("name,world", [("small_v2", 2), ("small_v2", 4), ("small_padded", 3)])
+def test_keysplit_over_views_matches_single_gpu(name, world):
+    """Key-split over camera views, all ranks emulated on one GPU: partial attention per
+    view shard + merge == the unsplit bf16 forward (same operands, different summation order)."""
+    case, wl, feats, metas, head = _build(name)
+    x = feats.to(DEV)
+    head.precision = "bf16"
+    ref = head([x], metas)
+    head.keysplit = dict(world=world, emulate=True)
+    out = head([x], metas)
+    head.keysplit = None
+    for k in ("all_cls_scores", "all_bbox_preds"):
+        assert (out[k] - ref[k]).abs().max() <= 5e-3, (k, (out[k] - ref[k]).abs().max())
+    g = cases.load_golden(name)
+    assert np.abs(out["all_bbox_preds"].cpu().numpy() - g["all_bbox_preds"]).max() <= 2e-2
