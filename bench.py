@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--cpu-samples", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print per-op CUDA-event times to stderr")
+    ap.add_argument("--graph", action="store_true", help="replay the whole head as one CUDA graph")
     ap.add_argument("--keysplit", action="store_true",
                     help="BASELINE config 4: every rank works on the SAME samples, keys split over camera "
                          "views, one NCCL all-gather of (O, m, l) partials per decoder layer (strong scaling)")
@@ -176,6 +177,7 @@ def main():
     head.load_state_dict(synth.head_state_dict(head, 0), strict=True)
     head = head.eval().to(dev)
     head.precision = args.precision
+    head.use_cuda_graph = bool(args.graph)
     if args.keysplit and world > 1:
         head.keysplit = dict(world=world, rank=rank, group=None)
     # data parallel: each rank gets its own shard of the global batch (different seeds per rank);
@@ -219,12 +221,14 @@ def main():
     # second, separately timed pass with per-launch CUDA events (kept out of `value`: the event
     # records add host overhead per launch)
     from petr_b200 import _lib
+    head.use_cuda_graph = False                       # per-launch events need eager launches
     _lib.TIMERS = {}
     for _ in range(args.steps):
         out = head([x_dev], metas)
     torch.cuda.synchronize()
     timers = _lib.TIMERS
     _lib.TIMERS = None
+    head.use_cuda_graph = bool(args.graph)
     ms_per_step = ms_total / args.steps
     nrep = 1 if args.keysplit else world          # key-split: all ranks share the same samples
     value = nrep * B * args.steps / (ms_total / 1000.0)
@@ -310,7 +314,7 @@ def main():
                     config=dict(workload=wl.name, batch_per_gpu=B, global_batch=B * nrep,
                                 num_keys=wl.num_keys, num_query=900, decoder_layers=6,
                                 parallelism=(f"keysplit{world}" if args.keysplit else f"dp{world}"),
-                                precision=args.precision,
+                                precision=args.precision, cuda_graph=bool(args.graph),
                                 l2="inputs larger than L2 (%.0f MB features per step)" % (x_host.numel() * 4 / 1e6)),
                     e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=int(h2d),
                              d2h_bytes_per_step=int(d2h)),

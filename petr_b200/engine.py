@@ -85,6 +85,66 @@ def _h2d(arr, device) -> torch.Tensor:
     return _PINNED.stage(t, device)
 
 
+def _nearest_src(dst: int, in_size: int, out_size: int) -> int:
+    # same rule as the device kernel / torch upsample_nearest (fp32 arithmetic)
+    if out_size == in_size:
+        return dst
+    if out_size == 2 * in_size:
+        return dst >> 1
+    scale = np.float32(in_size) / np.float32(out_size)
+    return min(int(np.floor(np.float32(dst) * scale)), in_size - 1)
+
+
+def any_key_masked(img_metas, N: int, H: int, W: int) -> bool:
+    """Host-side exact test whether petr_head.py:383-394 masks any key (no device sync)."""
+    pad_h, pad_w = img_metas[0]["pad_shape"][0][:2]
+    last_r, last_c = _nearest_src(H - 1, pad_h, H), _nearest_src(W - 1, pad_w, W)
+    for m in img_metas:
+        for n in range(N):
+            ih, iw = m["img_shape"][n][:2]
+            if not (last_r < ih and last_c < iw):
+                return True
+    return False
+
+
+class MetaInputs:
+    """Device-side form of `img_metas` for one forward: everything the kernels read."""
+
+    def __init__(self, img_hw, i2l, time_div, pad_h, pad_w, has_mask):
+        self.img_hw = img_hw          # int32 (B,N,2) device
+        self.i2l = i2l                # fp32 (B,N,4,4) device: float64 inverse of lidar2img, rounded once
+        self.time_div = time_div      # fp32 (B,) device | None (PETRv2 with_time)
+        self.pad_h, self.pad_w = int(pad_h), int(pad_w)
+        self.has_mask = bool(has_mask)
+
+    def views(self, sl: slice) -> "MetaInputs":
+        return MetaInputs(self.img_hw[:, sl].contiguous(), self.i2l[:, sl].contiguous(), self.time_div,
+                          self.pad_h, self.pad_w, self.has_mask)
+
+
+def host_prep(img_metas: Sequence[dict], N: int, H: int, W: int, with_time: bool) -> dict:
+    """Vectorised host-side ingestion of the reference's list-of-dicts `img_metas` (no per-(sample,
+    camera) python launches, one batched float64 inverse; SURVEY.md hard part 7)."""
+    pad_h, pad_w = img_metas[0]["pad_shape"][0][:2]
+    return dict(img_hw=torch.from_numpy(img_hw_from_metas(img_metas, N)),
+                i2l=torch.from_numpy(img2lidar_from_metas(img_metas)),
+                time_div=mean_time_stamp(img_metas) if with_time else None,
+                pad_h=pad_h, pad_w=pad_w, has_mask=any_key_masked(img_metas, N, H, W))
+
+
+def stage_meta(host: dict, device, into: Optional[MetaInputs] = None) -> MetaInputs:
+    """H2D of the host-prepared meta tensors; `into` = static device buffers of a captured graph."""
+    if into is None:
+        td = _h2d(host["time_div"], device) if host["time_div"] is not None else None
+        return MetaInputs(_h2d(host["img_hw"], device), _h2d(host["i2l"], device), td,
+                          host["pad_h"], host["pad_w"], host["has_mask"])
+    into.img_hw.copy_(_h2d(host["img_hw"], device), non_blocking=True)
+    into.i2l.copy_(_h2d(host["i2l"], device), non_blocking=True)
+    if into.time_div is not None:
+        into.time_div.copy_(_h2d(host["time_div"], device), non_blocking=True)
+    return into
+
+
 def sine_dim_t(num_feats: int, temperature: float) -> torch.Tensor:
     """positional_encoding.py:81-83 / petr_head.py:34-35, evaluated with the same torch ops."""
     dim_t = torch.arange(num_feats, dtype=torch.float32)
@@ -127,10 +187,12 @@ class HeadEngine:
         self.spec = HeadSpec(head)
         self._head = head
         self._packed: Dict[torch.device, dict] = {}
+        self._graphs: Dict[tuple, tuple] = {}
 
     # -------------------------------------------------------------------------------------
     def invalidate(self):
         self._packed.clear()
+        self._graphs.clear()
 
     def packed(self, device) -> dict:
         device = torch.device(device)
@@ -186,23 +248,22 @@ class HeadEngine:
     # -------------------------------------------------------------------------------------
     # pieces
     # -------------------------------------------------------------------------------------
-    def masks(self, img_metas, B, N, H, W, device) -> torch.Tensor:
-        pad_h, pad_w = img_metas[0]["pad_shape"][0][:2]
-        img_hw = _h2d(img_hw_from_metas(img_metas, N), device)
-        return ops.key_padding_mask(img_hw, pad_h, pad_w, H, W)
+    def meta_inputs(self, img_metas, N, H, W, device) -> MetaInputs:
+        return stage_meta(host_prep(img_metas, N, H, W, self.spec.with_time), device)
 
-    def frustum(self, img_metas, B, N, H, W, device, masks=None, dtype=torch.float32,
+    def masks(self, mi: MetaInputs, H, W) -> torch.Tensor:
+        return ops.key_padding_mask(mi.img_hw, mi.pad_h, mi.pad_w, H, W)
+
+    def frustum(self, mi: MetaInputs, B, N, H, W, masks=None, dtype=torch.float32,
                 want_mask=True, want_coords=False):
         s = self.spec
-        pad_h, pad_w = img_metas[0]["pad_shape"][0][:2]
-        i2l = _h2d(img2lidar_from_metas(img_metas), device)
-        assert i2l.shape[:2] == (B, N), f"lidar2img has {i2l.shape[:2]}, features have {(B, N)}"
-        return ops.frustum_features(i2l, masks, H, W, s.D, pad_h, pad_w, s.lid, s.depth_start,
+        assert tuple(mi.i2l.shape[:2]) == (B, N), f"lidar2img has {tuple(mi.i2l.shape[:2])}, features have {(B, N)}"
+        return ops.frustum_features(mi.i2l, masks, H, W, s.D, mi.pad_h, mi.pad_w, s.lid, s.depth_start,
                                     s.bin_size, s.position_range, dtype, want_mask, want_coords)
 
-    def position_embedding_tokens(self, P, img_metas, B, N, H, W, device, masks):
+    def position_embedding_tokens(self, P, mi: MetaInputs, B, N, H, W, masks):
         """fp32 path of position_embeding (petr_head.py:286-334): (T,256) tokens + coords_mask."""
-        feat, cmask, _ = self.frustum(img_metas, B, N, H, W, device, masks)
+        feat, cmask, _ = self.frustum(mi, B, N, H, W, masks)
         h = ops.gemm_f32(feat, P["pe_w1"], P["pe_b1"], act=ACT_RELU)
         pos = ops.gemm_f32(h, P["pe_w2"], P["pe_b2"])
         return pos, cmask
@@ -289,7 +350,7 @@ class HeadEngine:
     # -------------------------------------------------------------------------------------
     # key side / decoder layer / whole head
     # -------------------------------------------------------------------------------------
-    def key_side(self, x: torch.Tensor, img_metas: List[dict], precision: str, taps=None,
+    def key_side(self, x: torch.Tensor, mi: MetaInputs, precision: str, taps=None,
                  keysplit: Optional[dict] = None) -> dict:
         """Everything that depends on the image tokens (petr_head.py:381-402 and the K/V side of
         petr_transformer.py:341-344).  Returns the per-forward key-side state.
@@ -299,10 +360,10 @@ class HeadEngine:
             from . import engine_tc as tc
             if keysplit:
                 if keysplit.get("emulate"):
-                    return tc.key_side_keysplit_emulated(self, x, img_metas, keysplit["world"], taps)
-                return tc.key_side_keysplit(self, x, img_metas, keysplit["world"], keysplit["rank"],
+                    return tc.key_side_keysplit_emulated(self, x, mi, keysplit["world"], taps)
+                return tc.key_side_keysplit(self, x, mi, keysplit["world"], keysplit["rank"],
                                             keysplit.get("group"), taps)
-            return tc.key_side_tc(self, x, img_metas, taps)
+            return tc.key_side_tc(self, x, mi, taps)
         if keysplit:
             raise NotImplementedError("key-split over views is implemented on the bf16 (tcgen05) path")
         s = self.spec
@@ -311,12 +372,12 @@ class HeadEngine:
         dev = x.device
         Lk = N * H * W
         P = self.packed(dev)
-        masks = self.masks(img_metas, B, N, H, W, dev)
+        masks = self.masks(mi, H, W)
         mem = ops.gemm_f32(x, P["in_w"], P["in_b"], nchw_hw=H * W)                  # (T,E)
         sf = ops.sine3d_features(masks, P["dim_t_sine"], **_sine_args(s))
         h2 = ops.gemm_f32(sf, P["ad_w1"], P["ad_b1"], act=ACT_RELU)
         if s.with_position:
-            pos, _ = self.position_embedding_tokens(P, img_metas, B, N, H, W, dev, masks)
+            pos, _ = self.position_embedding_tokens(P, mi, B, N, H, W, masks)
             if taps is not None:
                 taps["coords_position_embeding"] = pos.clone()
             if s.with_fpe:
@@ -341,7 +402,8 @@ class HeadEngine:
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, img_metas: List[dict], precision: str = "bf16",
-                taps: Optional[dict] = None, keysplit: Optional[dict] = None) -> dict:
+                taps: Optional[dict] = None, keysplit: Optional[dict] = None,
+                use_graph: bool = False) -> dict:
         if not x.is_cuda:
             raise RuntimeError("petr_b200: features must be CUDA tensors (no CPU fallback)")
         if precision not in ("fp32", "bf16"):
@@ -349,12 +411,49 @@ class HeadEngine:
         s = self.spec
         if not s.with_multiview:
             raise NotImplementedError("petr_b200 implements with_multiview=True (all shipped configs)")
+        B, N, Cin, H, W = x.shape
+        host = host_prep(img_metas, N, H, W, s.with_time)
+        if use_graph and taps is None:
+            return self._graph_forward(x, host, precision, keysplit)
+        return self._run(x, stage_meta(host, x.device), precision, taps, keysplit)
+
+    def _graph_forward(self, x, host, precision, keysplit):
+        """Whole head as one CUDA graph per (input buffer, shape, mask-ness): ~100 launches replayed
+        with one call.  The captured graph reads `x` at its current address (re-captured if the
+        caller passes a different buffer) and static meta buffers that are refreshed per call; the
+        returned tensors are the graph's static outputs, valid until the next call."""
+        dev = x.device
+        ksk = None if not keysplit else (keysplit["world"], keysplit.get("rank"), bool(keysplit.get("emulate")))
+        key = (x.data_ptr(), tuple(x.shape), x.dtype, precision, host["has_mask"], host["pad_h"], host["pad_w"], ksk)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            mi = stage_meta(host, dev)
+            mi = MetaInputs(mi.img_hw.clone(), mi.i2l.clone(),
+                            mi.time_div.clone() if mi.time_div is not None else None,
+                            mi.pad_h, mi.pad_w, mi.has_mask)
+            self._run(x, mi, precision, None, keysplit)                 # warm-up (lazy packing, attributes)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._run(x, mi, precision, None, keysplit)
+            ent = (g, mi, out)
+            self._graphs[key] = ent
+        g, mi, out = ent
+        stage_meta(host, dev, into=mi)
+        g.replay()
+        return out
+
+    def _run(self, x: torch.Tensor, mi: MetaInputs, precision: str, taps: Optional[dict],
+             keysplit: Optional[dict]) -> dict:
+        s = self.spec
         dev = x.device
         P = self.packed(dev)
-        ks = self.key_side(x, img_metas, precision, taps, keysplit)
+        ks = self.key_side(x, mi, precision, taps, keysplit)
         B = ks["B"]
         qpos = self.query_embeds(P)
-        time_div = _h2d(mean_time_stamp(img_metas), dev) if s.with_time else None
+        time_div = mi.time_div
         if taps is not None:
             taps.update(query_embeds=qpos, layers=[])
         if precision == "bf16":

@@ -16,26 +16,7 @@ from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID_GATE
 NUM_SMS = 148
 
 
-def _nearest_src(dst: int, in_size: int, out_size: int) -> int:
-    # same rule as the device kernel / torch upsample_nearest (fp32 arithmetic)
-    if out_size == in_size:
-        return dst
-    if out_size == 2 * in_size:
-        return dst >> 1
-    scale = np.float32(in_size) / np.float32(out_size)
-    return min(int(np.floor(np.float32(dst) * scale)), in_size - 1)
-
-
-def any_key_masked(img_metas, N: int, H: int, W: int) -> bool:
-    """Host-side exact test whether petr_head.py:383-394 masks any key (no device sync)."""
-    pad_h, pad_w = img_metas[0]["pad_shape"][0][:2]
-    last_r, last_c = _nearest_src(H - 1, pad_h, H), _nearest_src(W - 1, pad_w, W)
-    for m in img_metas:
-        for n in range(N):
-            ih, iw = m["img_shape"][n][:2]
-            if not (last_r < ih and last_c < iw):
-                return True
-    return False
+from .engine import MetaInputs, any_key_masked  # noqa: F401  (re-exported for tests)
 
 
 def choose_nsplit(B: int, heads: int, Lq: int, Lk: int) -> int:
@@ -116,7 +97,7 @@ def shard_views(num_views: int, world: int, rank: int) -> slice:
     return slice(lo, lo + base + (1 if rank < rem else 0))
 
 
-def key_side_tc(eng, x, img_metas, taps=None, views: slice = None):
+def key_side_tc(eng, x, mi: MetaInputs, taps=None, views: slice = None):
     """Everything that depends on the image tokens: masks, input_proj, position embedding,
     K/V projection of all layers.  Returns the key-side state: Kh, Vh (L,B,heads,Lk,32) bf16,
     kmask (None when no key is padded), the split-KV plan.
@@ -135,17 +116,17 @@ def key_side_tc(eng, x, img_metas, taps=None, views: slice = None):
     E = s.E
     P = eng.packed(dev)
     T = packed_tc(eng, dev)
-    masks_all = eng.masks(img_metas, B, N_all, H, W, dev)
+    masks_all = eng.masks(mi, H, W)
     if views is not None:
         x = x[:, views]
         masks = masks_all[:, views].contiguous()
-        metas_all, img_metas = img_metas, slice_img_metas(img_metas, views)
+        mi = mi.views(views)
     else:
         masks = masks_all
     x = x.contiguous()
     N = x.shape[1]
     Lk = N * H * W
-    has_mask = any_key_masked(img_metas, N, H, W)
+    has_mask = mi.has_mask
     # input_proj (petr_head.py:390): fp32 NCHW -> bf16 tokens -> tcgen05 GEMM; mem kept in fp32 (for
     # the K input mem + pos) and as bf16 [hi | lo] whose hi half is the V-projection operand
     xt = ops.nchw_to_tokens_bf16(x.view(B * N, Cin, H, W))
@@ -157,7 +138,7 @@ def key_side_tc(eng, x, img_metas, taps=None, views: slice = None):
         sf = sf.view(B, N_all, H * W, -1)[:, views].reshape(B * Lk, -1).contiguous()
     h2 = ops.gemm_bf16_tc(sf, T["ad_w1"], P["ad_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_adapt1")
     if s.with_position:
-        feat, _, _ = eng.frustum(img_metas, B, N, H, W, dev, None, torch.bfloat16, want_mask=False)
+        feat, _, _ = eng.frustum(mi, B, N, H, W, None, torch.bfloat16, want_mask=False)
         h1 = ops.gemm_bf16_tc(feat, T["pe_w1"], P["pe_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_pe1")
         if s.with_fpe:
             pos = ops.gemm_bf16_tc(h1, T["pe_w2"], P["pe_b2"], name="gemm_pe2")
@@ -315,12 +296,12 @@ def state_from_rows(eng, X, qpos, st_like: dict) -> dict:
 # [O | m, l] partials are exchanged with ONE all-gather and merged by petr_attention_merge (the same
 # kernel and layout as on-GPU split-KV).  Queries / self-attention / FFN / branches are replicated.
 # ----------------------------------------------------------------------------------------------
-def key_side_keysplit(eng, x, img_metas, world: int, rank: int, group=None, taps=None) -> dict:
+def key_side_keysplit(eng, x, mi: MetaInputs, world: int, rank: int, group=None, taps=None) -> dict:
     """Key-side state of one rank of a `world`-way key-split (torch.distributed NCCL group)."""
     import torch.distributed as dist
     s = eng.spec
     N = x.shape[1]
-    ks = key_side_tc(eng, x, img_metas, taps, views=shard_views(N, world, rank))
+    ks = key_side_tc(eng, x, mi, taps, views=shard_views(N, world, rank))
     B = ks["B"]
     floats = ops.attention_partial_floats(B, s.Lq, s.heads)
     local = torch.empty((floats,), dtype=torch.float32, device=x.device)
@@ -336,13 +317,13 @@ def key_side_keysplit(eng, x, img_metas, world: int, rank: int, group=None, taps
     return ks
 
 
-def key_side_keysplit_emulated(eng, x, img_metas, world: int, taps=None) -> dict:
+def key_side_keysplit_emulated(eng, x, mi: MetaInputs, world: int, taps=None) -> dict:
     """Single-GPU emulation of a `world`-way key-split: every rank's shard is processed in turn on
     this device and the partials are laid out exactly as the all-gather would (tests; also the
     documented way to exercise the N-rank path with fewer GPUs than ranks)."""
     s = eng.spec
     N = x.shape[1]
-    shards = [key_side_tc(eng, x, img_metas, taps if r == 0 else None, views=shard_views(N, world, r))
+    shards = [key_side_tc(eng, x, mi, taps if r == 0 else None, views=shard_views(N, world, r))
               for r in range(world)]
     B = shards[0]["B"]
     floats = ops.attention_partial_floats(B, s.Lq, s.heads)

@@ -520,6 +520,9 @@ class _PETRHeadBase(BaseModule):
         # None: samples are simply data-parallel.  dict(world, rank, group): this process computes its
         # share of a key-split over camera views (every rank passes the full inputs, gets the full outputs)
         self.keysplit = None
+        # True: the whole forward is captured once per (input buffer, shape) as a CUDA graph and
+        # replayed; the returned tensors are then the graph's static outputs (valid until the next call)
+        self.use_cuda_graph = False
 
     # -- layers ---------------------------------------------------------------------------
     def _make_cls_branch(self):
@@ -594,8 +597,8 @@ class _PETRHeadBase(BaseModule):
         B, N, C, H, W = feat.shape
         eng = self.engine
         m8 = masks.to(torch.uint8).contiguous() if masks is not None else None
-        pos, cmask = eng.position_embedding_tokens(eng.packed(feat.device), img_metas, B, N, H, W,
-                                                   feat.device, m8)
+        mi = eng.meta_inputs(img_metas, N, H, W, feat.device)
+        pos, cmask = eng.position_embedding_tokens(eng.packed(feat.device), mi, B, N, H, W, m8)
         pos = pos.view(B, N, H, W, self.embed_dims).permute(0, 1, 4, 2, 3)
         return pos, cmask.to(torch.bool)
 
@@ -604,7 +607,8 @@ class _PETRHeadBase(BaseModule):
         """petr_head.py:366-468 / petrv2_head.py:429-540."""
         _require_eval(self)
         x = mlvl_feats[self.position_level]
-        return self.engine.forward(x, img_metas, precision=self.precision, keysplit=self.keysplit)
+        return self.engine.forward(x, img_metas, precision=self.precision, keysplit=self.keysplit,
+                                   use_graph=self.use_cuda_graph)
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys,
                               unexpected_keys, error_msgs):

@@ -86,7 +86,8 @@ def test_decoder_layers_teacher_forced(name, precision, tol):
         ref = po.head_forward(sd, feats, metas, cases.oracle_cfg(case), taps)
     eng = head.engine
     P = eng.packed(DEV)
-    ks = eng.key_side(feats.to(DEV), metas, precision)
+    Bf, Nf, _, Hf, Wf = feats.shape
+    ks = eng.key_side(feats.to(DEV), eng.meta_inputs(metas, Nf, Hf, Wf, DEV), precision)
     qpos = eng.query_embeds(P)
     s = eng.spec
     B = feats.shape[0]
@@ -215,3 +216,30 @@ def test_keysplit_over_views_matches_single_gpu(name, world):
         assert (out[k] - ref[k]).abs().max() <= 5e-3, (k, (out[k] - ref[k]).abs().max())
     g = cases.load_golden(name)
     assert np.abs(out["all_bbox_preds"].cpu().numpy() - g["all_bbox_preds"]).max() <= 2e-2
+
+
+@pytest.mark.parametrize("name", ["small_padded", "small_v2"])
+def test_cuda_graph_forward_matches_eager(name):
+    """use_cuda_graph: the whole head captured once and replayed; meta inputs (lidar2img, img_shape,
+    timestamps) are refreshed per call through static buffers."""
+    case, wl, feats, metas, head = _build(name)
+    x = feats.to(DEV)
+    head.precision = "bf16"
+    ref = {k: v.clone() for k, v in head([x], metas).items() if v is not None}
+    head.use_cuda_graph = True
+    for _ in range(3):
+        out = head([x], metas)
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+    # new metas (other cameras) and new feature values in the same buffer: replay must follow
+    metas2 = synth.make_img_metas(wl, feats.shape[0], seed=99, img_shape=case.get("img_shape"),
+                                  pad_shape=case.get("pad_shape"))
+    for b in case.get("fully_masked", []):
+        metas2[b]["img_shape"] = [(0, 0, 3)] * wl.num_cams
+    x.mul_(0.5)
+    out2 = {k: v.clone() for k, v in head([x], metas2).items() if v is not None}
+    head.use_cuda_graph = False
+    ref2 = head([x], metas2)
+    for k in out2:
+        assert torch.equal(out2[k], ref2[k]), k
+    assert not torch.equal(out2["all_bbox_preds"], ref["all_bbox_preds"])
