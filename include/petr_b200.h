@@ -169,6 +169,20 @@ int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const void* W, int l
                       void* C, void* C2, int ldc, int out_mode, int M, int N, int K,
                       int kv_Lk, void* stream);
 
+/* ---- a1, fused (K1): the whole position embedding of petr_head.py:286-334 in one kernel per
+ * 128-token tile: frustum -> img2lidar -> normalise -> inverse_sigmoid -> bf16 A operand written
+ * straight into 128B-swizzled shared memory -> tcgen05 GEMM (192 -> hidden, TMEM) -> bias + ReLU ->
+ * bf16 shared-memory operand -> tcgen05 GEMM (hidden -> embed, TMEM) -> + bias (+ residual) -> fp32
+ * tokens out[T, embed].  The coordinate tensor, the MLP input and the hidden activation never
+ * reach HBM; W1 [hidden,192] / W2 [embed,hidden] (bf16) stream through TMA from L2.
+ * Specialised for depth_num 64, hidden 1024, embed 256 (every shipped config).  Arguments as
+ * petr_frustum_features; residual nullable fp32 [T, embed]. */
+int petr_position_mlp_fused(const float* img2lidar, int B, int N, int H, int W, int D,
+                            int pad_h, int pad_w, int lid, float depth_start, float bin_size,
+                            const float* h_range_lo, const float* h_range_span,
+                            const void* W1, const float* b1, const void* W2, const float* b2,
+                            int hidden, int embed, const float* residual, float* out, void* stream);
+
 /* fp32 Q [B*Lq, heads*32] (row stride ldq) -> bf16 [B, heads, Lq, 32] multiplied by `scale`
  * (head_dim^-1/2 * log2 e: the softmax of petr_cross_attention_bf16 runs in the exp2 domain). */
 int petr_pack_q_bf16(const float* Q, int ldq, void* out, int B, int Lq, int heads, float scale,

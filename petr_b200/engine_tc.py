@@ -14,6 +14,7 @@ from . import ops
 from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID_GATE
 
 NUM_SMS = 148
+FUSED_POSITION_MLP = True        # False: unfused frustum kernel + two GEMMs (kept for A/B tests)
 
 
 from .engine import MetaInputs, any_key_masked  # noqa: F401  (re-exported for tests)
@@ -138,14 +139,21 @@ def key_side_tc(eng, x, mi: MetaInputs, taps=None, views: slice = None):
         sf = sf.view(B, N_all, H * W, -1)[:, views].reshape(B * Lk, -1).contiguous()
     h2 = ops.gemm_bf16_tc(sf, T["ad_w1"], P["ad_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_adapt1")
     if s.with_position:
-        feat, _, _ = eng.frustum(mi, B, N, H, W, None, torch.bfloat16, want_mask=False)
-        h1 = ops.gemm_bf16_tc(feat, T["pe_w1"], P["pe_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_pe1")
+        fused = FUSED_POSITION_MLP and s.D == 64 and tuple(T["pe_w1"].shape) == (1024, 192) and \
+            tuple(T["pe_w2"].shape) == (256, 1024)
+        res = None if s.with_fpe else mem                       # mem + position MLP in the epilogue
+        if fused:
+            # K1: frustum -> inverse_sigmoid -> MLP in one tcgen05 kernel, nothing intermediate in HBM
+            pos = ops.position_mlp_fused(mi.i2l, H, W, s.D, mi.pad_h, mi.pad_w, s.lid, s.depth_start,
+                                         s.bin_size, s.position_range, T["pe_w1"], P["pe_b1"], T["pe_w2"],
+                                         P["pe_b2"], residual=res)
+        else:
+            feat, _, _ = eng.frustum(mi, B, N, H, W, None, torch.bfloat16, want_mask=False)
+            h1 = ops.gemm_bf16_tc(feat, T["pe_w1"], P["pe_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_pe1")
+            pos = ops.gemm_bf16_tc(h1, T["pe_w2"], P["pe_b2"], residual=res, name="gemm_pe2")
         if s.with_fpe:
-            pos = ops.gemm_bf16_tc(h1, T["pe_w2"], P["pe_b2"], name="gemm_pe2")
             se = ops.gemm_f32(mem, P["fpe_wr"], P["fpe_br"], act=ACT_RELU)
             pos = ops.gemm_f32(se, P["fpe_we"], P["fpe_be"], act=ACT_SIGMOID_GATE, gate=pos, residual=mem)
-        else:
-            pos = ops.gemm_bf16_tc(h1, T["pe_w2"], P["pe_b2"], residual=mem, name="gemm_pe2")   # mem + position MLP
     else:
         pos = mem
     kin = ops.gemm_bf16_tc(h2, T["ad_w2"], P["ad_b2"], residual=pos, out_dtype=torch.bfloat16, name="gemm_adapt2")

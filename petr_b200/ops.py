@@ -273,6 +273,29 @@ def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, 
     return out
 
 
+def position_mlp_fused(img2lidar, H: int, W: int, D: int, pad_h: int, pad_w: int, lid: bool,
+                       depth_start: float, bin_size: float, position_range, W1, b1, W2, b2,
+                       residual=None, out=None) -> torch.Tensor:
+    """Fused position embedding (petr_head.py:286-334) on tcgen05: img2lidar (B,N,4,4) fp32 ->
+    fp32 tokens (T, 256) = MLP(inverse_sigmoid(frustum coords)) (+ residual).  W1 (1024,192) /
+    W2 (256,1024) bf16."""
+    _cuda(img2lidar, "img2lidar")
+    B, N = img2lidar.shape[:2]
+    T = B * N * H * W
+    hidden, embed = W1.shape[0], W2.shape[0]
+    assert W1.dtype == torch.bfloat16 and W2.dtype == torch.bfloat16 and W1.is_contiguous() and W2.is_contiguous()
+    if out is None:
+        out = torch.empty((T, embed), dtype=torch.float32, device=img2lidar.device)
+    pr = [float(v) for v in position_range]
+    lo = host_floats(pr[:3])
+    span = host_floats([pr[3] - pr[0], pr[4] - pr[1], pr[5] - pr[2]])
+    with _Timed("position_mlp_fused"):
+        call("petr_position_mlp_fused", ptr(img2lidar), B, N, H, W, D, int(pad_h), int(pad_w), int(bool(lid)),
+             float(depth_start), float(bin_size), lo, span, ptr(W1), ptr(b1), ptr(W2), ptr(b2), hidden, embed,
+             ptr(residual), ptr(out), stream_ptr(img2lidar.device))
+    return out
+
+
 def pack_q_bf16(Q: torch.Tensor, B: int, Lq: int, heads: int, out=None) -> torch.Tensor:
     """fp32 (B*Lq, heads*32) -> bf16 (B, heads, Lq, 32) scaled by 32^-1/2 * log2(e)."""
     _cuda(Q, "Q")

@@ -378,3 +378,38 @@ def test_cross_attention_bf16_masks_and_merge():
     merged = ops.attention_merge(torch.cat(parts), 2, B, Lq, 8)
     assert (merged[:2 * Lq] - ref[:2 * Lq]).abs().max() <= 1e-2
     assert torch.isnan(merged[2 * Lq:]).all()
+
+
+@pytest.mark.parametrize("wn,B", [("tiny", 2), ("small", 3), ("vov-p4-800x320", 1)])
+def test_position_mlp_fused(wn, B):
+    """K1: the fused frustum -> inverse_sigmoid -> tcgen05 MLP kernel against (a) the unfused bf16
+    path (same bf16 operands; only summation order / fast-math coordinate arithmetic differ) and
+    (b) the fp32 oracle to bf16-class accuracy."""
+    wl = WORKLOADS[wn]
+    g = torch.Generator().manual_seed(17)
+    metas = synth.make_img_metas(wl, B, 5)
+    N, H, W = wl.num_cams, wl.feat_h, wl.feat_w
+    pr = (-61.2, -61.2, -10.0, 61.2, 61.2, 10.0)
+    bin_size = (pr[3] - 1.0) / (64 * 65)
+    w1 = (torch.randn(1024, 192, generator=g) * 0.05).to(DEV)
+    b1 = (torch.randn(1024, generator=g) * 0.05).to(DEV)
+    w2 = (torch.randn(256, 1024, generator=g) * 0.03).to(DEV)
+    b2 = (torch.randn(256, generator=g) * 0.05).to(DEV)
+    T = B * N * H * W
+    res = torch.randn(T, 256, generator=g).to(DEV)
+    i2l = torch.from_numpy(engine.img2lidar_from_metas(metas)).to(DEV)
+    w1b, w2b = w1.to(torch.bfloat16).contiguous(), w2.to(torch.bfloat16).contiguous()
+    got = ops.position_mlp_fused(i2l, H, W, 64, wl.img_h, wl.img_w, True, 1.0, bin_size, pr, w1b, b1, w2b, b2,
+                                 residual=res)
+    feat, _, _ = ops.frustum_features(i2l, None, H, W, 64, wl.img_h, wl.img_w, True, 1.0, bin_size, pr,
+                                      dtype=torch.bfloat16, want_mask=False)
+    h1 = ops.gemm_bf16_tc(feat, w1b, b1, act=ops.ACT_RELU, out_dtype=torch.bfloat16)
+    unf = ops.gemm_bf16_tc(h1, w2b, b2, residual=res)
+    scale = (unf - res).abs().max().item()
+    assert (got - unf).abs().max() <= 1e-2 * scale, ((got - unf).abs().max().item(), scale)
+    feat32, _, _ = po.position_features(metas, B, N, H, W, None, 64, 1.0, pr, True)
+    f = feat32.view(B * N, 192, H * W).permute(0, 2, 1).reshape(-1, 192).to(DEV)
+    ref = torch.relu(f @ w1.T + b1) @ w2.T + b2 + res
+    assert (got - ref).abs().max() <= 2e-2 * scale
+    got0 = ops.position_mlp_fused(i2l, H, W, 64, wl.img_h, wl.img_w, True, 1.0, bin_size, pr, w1b, b1, w2b, b2)
+    assert (got0 + res - got).abs().max() <= 1e-5 * max(1.0, scale)
