@@ -54,7 +54,7 @@ using namespace tc;
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = TILE_A_BYTES + TILE_B_BYTES;                 // 48 KB
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias tiles*/;
 constexpr int GEMM_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 
 struct EpiParams {
@@ -84,6 +84,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* acc_full = empty_bar + STAGES;      // 2
     uint64_t* acc_empty = acc_full + 2;           // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* sbias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);      // [2][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = p.K / BK;
@@ -162,6 +163,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
             const uint32_t buf = tcount & 1;
             const int m = m0 + row;
+            // bias of this tile's 256 columns -> shared memory once (per-chunk global loads were the
+            // top stall of the epilogue); double buffered by tile parity, one 256-thread named barrier
+            float* sb = sbias + buf * BN;
+            if (p.bias) {
+                const int et = threadIdx.x - 64;                     // 0..255 among the epilogue warps
+                sb[et] = (n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             mbar_wait(&acc_full[buf], (tcount >> 1) & 1);
             tcgen05_fence_after();
             int kv_b = 0, kv_key = 0;
@@ -182,15 +191,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 if (p.bias) {
-                    if (full) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-                            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(sb + c * 32 + j);
+                        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
                     }
                 }
                 if (p.act == PETR_ACT_RELU) {
@@ -321,7 +325,6 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     p.bias = bias; p.residual = residual; p.act = act; p.alpha = alpha;
     p.C = C; p.C2 = C2; p.ldc = ldc; p.out_mode = out_mode;
     p.M = M; p.N = N; p.K = K; p.a_k_wrap = a_k_wrap;
-    if (bias) PETR_REQUIRE(aligned16(bias), PETR_E_ALIGN, "petr_gemm_bf16_tc: bias must be 16-byte aligned");
     if (out_mode == 2 || out_mode == 4) {
         if (out_mode == 4) PETR_REQUIRE(C2 && aligned16(C2), PETR_E_BADARG, "petr_gemm_bf16_tc: out_mode 4 needs C2 (lo array)");
         PETR_REQUIRE(kv_Lk > 0 && M % kv_Lk == 0 && N % 256 == 0 && !residual, PETR_E_SHAPE,

@@ -10,12 +10,17 @@
 //   * GEMM1 runs in 8 chunks of 128 hidden units into a double-buffered TMEM accumulator; the same
 //     warps apply bias + ReLU, convert to bf16 and store the chunk to shared memory as the A operand
 //     of GEMM2, which accumulates the 128 x 256 output in TMEM across the 8 chunks;
-//   * warp 0 streams the W1 / W2 chunks with TMA (L2-resident weights), warp 1 issues tcgen05.mma.
+//   * warp 0 streams the W1 / W2 blocks with TMA through a 7-stage 16 KB ring (weights stay L2
+//     resident; 896 KB are re-streamed per tile, which is what bounds this kernel), warp 1 issues
+//     tcgen05.mma (all 128 x 128 x 16).
 // The bf16 path rounds the features to bf16 anyway, so the coordinate arithmetic uses fast fp32
 // (FMA contraction, __fdividef, __logf); the bit-exact coordinates live in petr_frustum_features.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <math.h>
+
+static long long* g_pe_dbg = nullptr;
+extern "C" void petr_debug_set_ptr(void* p) { g_pe_dbg = (long long*)p; }
 
 namespace petr {
 namespace {
@@ -28,13 +33,12 @@ constexpr int HID = 1024, EOUT = 256;
 constexpr int HC = 128;                 // hidden units per chunk
 constexpr int NCH = HID / HC;           // 8
 constexpr int A1_BYTES = TM * K1 * 2;                   // 48 KB: 3 K-atoms of 16 KB
-constexpr int W1_BYTES = HC * K1 * 2;                   // 48 KB: 3 blocks [128 x 64]
-constexpr int W2_BYTES = EOUT * HC * 2;                 // 64 KB: 2 blocks [256 x 64]
+constexpr int WST = 7;                                  // weight ring: 7 stages of [128 rows x 64 k] = 16 KB
+constexpr int WST_BYTES = 128 * 64 * 2;
 constexpr int HS_BYTES = TM * HC * 2;                   // 32 KB: 2 K-atoms of 16 KB
 constexpr int OFF_A1 = 0;
-constexpr int OFF_W1 = OFF_A1 + A1_BYTES;
-constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
-constexpr int OFF_HS = OFF_W2 + W2_BYTES;
+constexpr int OFF_WR = OFF_A1 + A1_BYTES;               // weight ring (W1 k-blocks and W2 half k-blocks, in MMA order)
+constexpr int OFF_HS = OFF_WR + WST * WST_BYTES;
 constexpr int OFF_B1 = OFF_HS + HS_BYTES;               // 1024 floats
 constexpr int OFF_B2 = OFF_B1 + HID * 4;                // 256 floats
 constexpr int OFF_BAR = OFF_B2 + EOUT * 4;
@@ -50,7 +54,10 @@ struct PeParams {
     float scale[3], shift[3];           // x_norm = X * scale + shift  (= (X - lo) / span)
     const float* b1; const float* b2; const float* residual; float* out;
     int64_t T;
+    long long* dbg;                     // optional per-CTA phase timestamps (profiling aid)
 };
+
+#define PE_STAMP(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ float inv_sigmoid_fast(float x) {
     x = fminf(fmaxf(x, 0.f), 1.f);
@@ -65,16 +72,14 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* a1_ready = bars;            // 128 producers
-    uint64_t* w1_full = bars + 1;
-    uint64_t* w1_free = bars + 2;
-    uint64_t* w2_full = bars + 3;
-    uint64_t* w2_free = bars + 4;
-    uint64_t* h_full = bars + 5;          // [2]
-    uint64_t* h_free = bars + 7;          // [2], 128
-    uint64_t* hs_ready = bars + 9;        // 128
-    uint64_t* hs_free = bars + 10;
-    uint64_t* o_full = bars + 11;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* w_full = bars + 1;          // [WST]
+    uint64_t* w_empty = w_full + WST;     // [WST]
+    uint64_t* h_full = w_empty + WST;     // [2]
+    uint64_t* h_free = h_full + 2;        // [2], 128
+    uint64_t* hs_ready = h_free + 2;      // 128
+    uint64_t* hs_free = hs_ready + 1;
+    uint64_t* o_full = hs_free + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
     float* sb1 = reinterpret_cast<float*>(smem + OFF_B1);
     float* sb2 = reinterpret_cast<float*>(smem + OFF_B2);
 
@@ -87,7 +92,7 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(a1_ready, 128);
-            mbar_init(w1_full, 1); mbar_init(w1_free, 1); mbar_init(w2_full, 1); mbar_init(w2_free, 1);
+            for (int i = 0; i < WST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_free[i], 128); }
             mbar_init(hs_ready, 128); mbar_init(hs_free, 1); mbar_init(o_full, 1);
             fence_barrier_init();
@@ -99,60 +104,79 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 64) PE_STAMP(0);
 
     if (warp == 0) {
-        // ---------------- TMA: stream the weight chunks ----------------
+        // ---------------- TMA: stream the weights through a 7-stage ring, in the MMA's order ----------------
+        // per hidden chunk c: 3 k-blocks of W1[c] (GEMM1), then the 4 half k-blocks of W2[:, c-1] (GEMM2)
         if (lane == 0) {
-            for (int c = 0; c < NCH; ++c) {
-                mbar_wait(w1_free, (c & 1) ^ 1);
-                mbar_arrive_expect_tx(w1_full, W1_BYTES);
-                for (int kb = 0; kb < K1 / 64; ++kb)
-                    tma_load_2d(smem + OFF_W1 + kb * 16384, &tmW1, w1_full, kb * 64, c * HC);
-                mbar_wait(w2_free, (c & 1) ^ 1);
-                mbar_arrive_expect_tx(w2_full, W2_BYTES);
+            uint32_t it = 0;
+            auto load = [&](const CUtensorMap* m, int c0, int c1) {
+                const int st = it % WST;
+                mbar_wait(&w_empty[st], ((it / WST) & 1) ^ 1);
+                mbar_arrive_expect_tx(&w_full[st], WST_BYTES);
+                tma_load_2d(smem + OFF_WR + st * WST_BYTES, m, &w_full[st], c0, c1);
+                ++it;
+            };
+            auto load_w2 = [&](int c) {
                 for (int kb = 0; kb < HC / 64; ++kb)
-                    tma_load_2d(smem + OFF_W2 + kb * 32768, &tmW2, w2_full, c * HC + kb * 64, 0);
+                    for (int nh = 0; nh < 2; ++nh) load(&tmW2, c * HC + kb * 64, nh * 128);
+            };
+            for (int c = 0; c < NCH; ++c) {
+                for (int kb = 0; kb < K1 / 64; ++kb) load(&tmW1, kb * 64, c * HC);
+                if (c > 0) load_w2(c - 1);
             }
+            load_w2(NCH - 1);
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
-            constexpr uint32_t idesc1 = make_idesc(TM, HC, 1, 0, 0);       // H[128x128]  = A1 W1c^T
-            constexpr uint32_t idesc2 = make_idesc(TM, EOUT, 1, 0, 0);     // O[128x256] += Hs W2c^T
+            constexpr uint32_t idesc = make_idesc(TM, 128, 1, 0, 0);       // every MMA here is 128 x 128 x 16
             const uint64_t a1d = make_smem_desc(smem_u32(smem + OFF_A1), 16, 1024, LAYOUT_SW128);
-            const uint64_t w1d = make_smem_desc(smem_u32(smem + OFF_W1), 16, 1024, LAYOUT_SW128);
-            const uint64_t w2d = make_smem_desc(smem_u32(smem + OFF_W2), 16, 1024, LAYOUT_SW128);
+            const uint64_t wrd = make_smem_desc(smem_u32(smem + OFF_WR), 16, 1024, LAYOUT_SW128);
             const uint64_t hsd = make_smem_desc(smem_u32(smem + OFF_HS), 16, 1024, LAYOUT_SW128);
-            auto gemm2 = [&](int c) {
-                mbar_wait(hs_ready, c & 1);
-                mbar_wait(w2_full, c & 1);
+            uint32_t it = 0;
+            auto next_stage = [&]() -> uint64_t {
+                const int st = it % WST;
+                mbar_wait(&w_full[st], (it / WST) & 1);
                 tcgen05_fence_after();
-#pragma unroll
+                ++it;
+                return wrd + (uint64_t)((st * WST_BYTES) >> 4);
+            };
+            auto release = [&]() { umma_commit(&w_empty[(it - 1) % WST]); };
+            auto gemm2 = [&](int c) {            // O[128 x 256] += Hs[128 x 128] W2[:, c]^T, two 128-column halves
+                mbar_wait(hs_ready, c & 1);
+                tcgen05_fence_after();
                 for (int kb = 0; kb < HC / 64; ++kb)
+                    for (int nh = 0; nh < 2; ++nh) {
+                        const uint64_t bd = next_stage();
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16_ss(tmem_base + TM_O, hsd + (uint64_t)((kb * 16384 + k * 32) >> 4),
-                                    w2d + (uint64_t)((kb * 32768 + k * 32) >> 4), idesc2, (c | kb | k) ? 1u : 0u);
-                umma_commit(w2_free);
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16_ss(tmem_base + TM_O + nh * 128, hsd + (uint64_t)((kb * 16384 + k * 32) >> 4),
+                                        bd + (uint64_t)((k * 32) >> 4), idesc, (c | kb | k) ? 1u : 0u);
+                        release();
+                    }
                 umma_commit(hs_free);
             };
             mbar_wait(a1_ready, 0);
+            PE_STAMP(16);
             for (int c = 0; c < NCH; ++c) {
-                mbar_wait(w1_full, c & 1);
                 mbar_wait(&h_free[c & 1], ((c >> 1) & 1) ^ 1);
-                tcgen05_fence_after();
-#pragma unroll
-                for (int kb = 0; kb < K1 / 64; ++kb)
+                for (int kb = 0; kb < K1 / 64; ++kb) {
+                    const uint64_t bd = next_stage();
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_f16_ss(tmem_base + TM_H + (c & 1) * HC, a1d + (uint64_t)((kb * 16384 + k * 32) >> 4),
-                                    w1d + (uint64_t)((kb * 16384 + k * 32) >> 4), idesc1, (kb | k) ? 1u : 0u);
-                umma_commit(w1_free);
+                                    bd + (uint64_t)((k * 32) >> 4), idesc, (kb | k) ? 1u : 0u);
+                    release();
+                }
                 umma_commit(&h_full[c & 1]);
+                PE_STAMP(17 + c);
                 if (c > 0) gemm2(c - 1);
             }
             gemm2(NCH - 1);
             umma_commit(o_full);
+            PE_STAMP(25);
         }
     } else {
         // ---------------- producer (features) + epilogues: thread <-> token ----------------
@@ -164,6 +188,8 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
         {
             const bool live = t < p.T;
             float M[12], u = 0.f, v = 0.f;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) M[i] = 0.f;
             if (live) {
                 const int w = (int)(t % p.W);
                 const int h = (int)((t / p.W) % p.H);
@@ -189,7 +215,9 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         const float X = M[4 * i] * p0 + M[4 * i + 1] * p1 + M[4 * i + 2] * depth + M[4 * i + 3];
-                        f[dd * 3 + i] = live ? inv_sigmoid_fast(X * p.scale[i] + p.shift[i]) : 0.f;
+                        // rows past T run on a zero matrix (finite values) and are never stored: no branch
+                        // here, so the 24 independent chains of a group interleave (MUFU latency hidden)
+                        f[dd * 3 + i] = inv_sigmoid_fast(X * p.scale[i] + p.shift[i]);
                     }
                 }
 #pragma unroll
@@ -203,6 +231,7 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
             }
             fence_proxy_async_smem();
             mbar_arrive(a1_ready);
+            if (threadIdx.x == 64) PE_STAMP(1);
         }
         // ---- per-chunk epilogue of GEMM1: bias + ReLU -> bf16 -> shared-memory A operand of GEMM2 ----
         uint8_t* hrow = smem + OFF_HS + (row >> 3) * 1024 + (row & 7) * 128;
@@ -229,30 +258,50 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
             }
             fence_proxy_async_smem();
             mbar_arrive(hs_ready);
+            if (threadIdx.x == 64) PE_STAMP(2 + c);
         }
-        // ---- final epilogue: O + b2 (+ residual) -> fp32 tokens ----
+        // ---- final epilogue: O + b2 (+ residual) -> fp32 tokens, staged through shared memory ----
+        // Every MMA has retired, so the A1 / weight-ring area (160 KB) is free: each warp parks its
+        // 32 rows x 256 fp32 there (XOR-swizzled 16-byte slots: conflict-free both ways) and then
+        // streams them out row by row, so the residual loads and the stores are fully coalesced
+        // 512-byte segments instead of 32 scattered 16-byte pieces per instruction.
         mbar_wait(o_full, 0);
+        if (threadIdx.x == 64) PE_STAMP(10);
         tcgen05_fence_after();
+        float4* stage = reinterpret_cast<float4*>(smem + OFF_A1) + (size_t)quarter * 32 * 64;     // [32 rows][64 float4]
 #pragma unroll 1
         for (int c = 0; c < EOUT / 32; ++c) {
             uint32_t r[32];
             tmem_ld_x32(tmem_base + lane_off + TM_O + c * 32, r);
             tmem_ld_wait();
-            if (t < p.T) {
-                float* op = p.out + t * EOUT + c * 32;
-                const float* rp = p.residual ? p.residual + t * EOUT + c * 32 : nullptr;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o = make_float4(__uint_as_float(r[j]) + sb2[c * 32 + j], __uint_as_float(r[j + 1]) + sb2[c * 32 + j + 1],
-                                           __uint_as_float(r[j + 2]) + sb2[c * 32 + j + 2], __uint_as_float(r[j + 3]) + sb2[c * 32 + j + 3]);
-                    if (rp) {
-                        const float4 q4 = *reinterpret_cast<const float4*>(rp + j);
-                        o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
-                    }
-                    *reinterpret_cast<float4*>(op + j) = o;
-                }
+            for (int j = 0; j < 8; ++j) {
+                const int slot = (c * 8 + j) ^ lane;
+                stage[lane * 64 + slot] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
             }
         }
+        __syncwarp();
+        if (threadIdx.x == 64) PE_STAMP(11);
+        const int64_t t0w = tile0 + quarter * 32;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+            const int64_t tt = t0w + rr;
+            if (tt >= p.T) break;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int j = lane + 32 * i;                       // float4 index along the 256 outputs
+                float4 o = stage[rr * 64 + (j ^ rr)];
+                const float4 bz = *reinterpret_cast<const float4*>(sb2 + 4 * j);
+                o.x += bz.x; o.y += bz.y; o.z += bz.z; o.w += bz.w;
+                if (p.residual) {
+                    const float4 q4 = __ldg(reinterpret_cast<const float4*>(p.residual + tt * EOUT) + j);
+                    o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
+                }
+                reinterpret_cast<float4*>(p.out + tt * EOUT)[j] = o;
+            }
+        }
+        if (threadIdx.x == 64) PE_STAMP(12);
         tcgen05_fence_before();
     }
     __syncthreads();
@@ -288,6 +337,7 @@ extern "C" int petr_position_mlp_fused(const float* img2lidar, int B, int N, int
     for (int i = 0; i < 3; ++i) { p.scale[i] = 1.f / h_range_span[i]; p.shift[i] = -h_range_lo[i] / h_range_span[i]; }
     p.b1 = b1; p.b2 = b2; p.residual = residual; p.out = out;
     p.T = (int64_t)B * N * H * W;
+    p.dbg = g_pe_dbg;
     CUtensorMap tmW1, tmW2;
     {
         uint64_t d[2] = {K1, HID}, s[1] = {K1 * 2};
@@ -297,7 +347,7 @@ extern "C" int petr_position_mlp_fused(const float* img2lidar, int B, int N, int
     }
     {
         uint64_t d[2] = {HID, EOUT}, s[1] = {HID * 2};
-        uint32_t box[2] = {64, EOUT};
+        uint32_t box[2] = {64, 128};
         int rc = tmap::encode(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W2, d, s, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
