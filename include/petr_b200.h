@@ -135,6 +135,10 @@ int petr_layernorm_multi_f32(const float* X, const float* gamma, const float* be
 int petr_split_rows_bf16(const float* X, int ldx, const float* add, int add_rows, void* out,
                          int rows, int E, int relu, void* stream);
 
+/* out[r, :] = bf16(X[r, :] + add[r % add_rows, :]); E % 4 == 0. */
+int petr_add_rows_bf16(const float* X, const float* add, int add_rows, void* out, int rows, int E,
+                       void* stream);
+
 /* ---- a12: reference-point add, sigmoid and pc_range affine.  petr_head.py:440-460
  * (+ PETRv2 with_time petrv2_head.py:499-505,:520-521).  reg: fp32 [L*B*Q, code_size] in place.
  * ref: fp32 [Q,3] (reference_points.weight).  h_pc_range: host float[6].  time_div nullable
@@ -176,12 +180,16 @@ int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const void* W, int l
  * tokens out[T, embed].  The coordinate tensor, the MLP input and the hidden activation never
  * reach HBM; W1 [hidden,192] / W2 [embed,hidden] (bf16) stream through TMA from L2.
  * Specialised for depth_num 64, hidden 1024, embed 256 (every shipped config).  Arguments as
- * petr_frustum_features; residual nullable fp32 [T, embed]. */
+ * petr_frustum_features; residual (nullable) fp32 [T, embed]; residual2 (nullable) fp32
+ * [res2_rows, embed] added with row t % res2_rows (the batch-invariant sine embedding); the result
+ * goes to out (fp32, nullable) and/or out_bf16 (nullable) -- with both residuals the bf16 output
+ * is directly the K-projection input mem + pos_embed of petr_transformer.py:343. */
 int petr_position_mlp_fused(const float* img2lidar, int B, int N, int H, int W, int D,
                             int pad_h, int pad_w, int lid, float depth_start, float bin_size,
                             const float* h_range_lo, const float* h_range_span,
                             const void* W1, const float* b1, const void* W2, const float* b2,
-                            int hidden, int embed, const float* residual, float* out, void* stream);
+                            int hidden, int embed, const float* residual, const float* residual2,
+                            int res2_rows, float* out, void* out_bf16, void* stream);
 
 /* fp32 Q [B*Lq, heads*32] (row stride ldq) -> bf16 [B, heads, Lq, 32] multiplied by `scale`
  * (head_dim^-1/2 * log2 e: the softmax of petr_cross_attention_bf16 runs in the exp2 domain). */

@@ -623,6 +623,23 @@ __global__ void split_rows_kernel(const float* __restrict__ X, int ldx, const fl
     store_split_elem(out + r * 2 * E, E, c, v);
 }
 
+// out_bf16[r, :] = bf16(X[r, :] + add[r % add_rows, :]); E % 4 == 0 (key-side K input: tokens +
+// the batch-invariant sine embedding)
+__global__ void add_rows_bf16_kernel(const float* __restrict__ X, const float* __restrict__ add, int add_rows,
+                                     __nv_bfloat16* __restrict__ out, int64_t rows, int E4) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * E4) return;
+    int64_t r = i / E4;
+    int c = (int)(i - r * E4);
+    float4 v = reinterpret_cast<const float4*>(X)[i];
+    const float4 a = __ldg(reinterpret_cast<const float4*>(add) + (r % add_rows) * E4 + c);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x + a.x, v.y + a.y), hi = __floats2bfloat162_rn(v.z + a.z, v.w + a.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(out)[i] = o;
+}
+
 // a12: reference add + sigmoid + pc_range affine (petr_head.py:440-460)
 struct DecodeParams { float pc[6]; };
 
@@ -813,4 +830,15 @@ extern "C" int petr_split_rows_bf16(const float* X, int ldx, const float* add, i
     split_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         X, ldx, add, add_rows, (__nv_bfloat16*)out, rows, E, relu);
     return after_launch("petr_split_rows_bf16");
+}
+
+extern "C" int petr_add_rows_bf16(const float* X, const float* add, int add_rows, void* out, int rows, int E,
+                                  void* stream) {
+    PETR_REQUIRE(X && add && out, PETR_E_BADARG, "petr_add_rows_bf16: null pointer");
+    PETR_REQUIRE(rows > 0 && E > 0 && add_rows > 0 && (E % 4) == 0, PETR_E_BADARG, "petr_add_rows_bf16: bad dimension");
+    PETR_REQUIRE(aligned16(X) && aligned16(add) && aligned16(out), PETR_E_ALIGN, "petr_add_rows_bf16: alignment");
+    int64_t total = (int64_t)rows * (E / 4);
+    add_rows_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        X, add, add_rows, (__nv_bfloat16*)out, rows, E / 4);
+    return after_launch("petr_add_rows_bf16");
 }

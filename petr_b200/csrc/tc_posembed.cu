@@ -53,6 +53,7 @@ struct PeParams {
     float depth_start, bin_size;
     float scale[3], shift[3];           // x_norm = X * scale + shift  (= (X - lo) / span)
     const float* b1; const float* b2; const float* residual; float* out;
+    const float* residual2; int res2_rows; __nv_bfloat16* out_bf16;   // + residual2[t % res2_rows]; optional bf16 store
     int64_t T;
     long long* dbg;                     // optional per-CTA phase timestamps (profiling aid)
 };
@@ -298,7 +299,13 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
                     const float4 q4 = __ldg(reinterpret_cast<const float4*>(p.residual + tt * EOUT) + j);
                     o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
                 }
-                reinterpret_cast<float4*>(p.out + tt * EOUT)[j] = o;
+                if (p.residual2) {
+                    const float4 q4 = __ldg(reinterpret_cast<const float4*>(p.residual2 + (tt % p.res2_rows) * EOUT) + j);
+                    o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
+                }
+                if (p.out) reinterpret_cast<float4*>(p.out + tt * EOUT)[j] = o;
+                if (p.out_bf16)
+                    reinterpret_cast<uint2*>(p.out_bf16 + tt * EOUT)[j] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
             }
         }
         if (threadIdx.x == 64) PE_STAMP(12);
@@ -321,21 +328,24 @@ extern "C" int petr_position_mlp_fused(const float* img2lidar, int B, int N, int
                                        int pad_h, int pad_w, int lid, float depth_start, float bin_size,
                                        const float* h_range_lo, const float* h_range_span,
                                        const void* W1, const float* b1, const void* W2, const float* b2,
-                                       int hidden, int embed, const float* residual, float* out,
-                                       void* stream) {
-    PETR_REQUIRE(img2lidar && W1 && b1 && W2 && b2 && out && h_range_lo && h_range_span, PETR_E_BADARG,
+                                       int hidden, int embed, const float* residual, const float* residual2,
+                                       int res2_rows, float* out, void* out_bf16, void* stream) {
+    PETR_REQUIRE(img2lidar && W1 && b1 && W2 && b2 && (out || out_bf16) && h_range_lo && h_range_span, PETR_E_BADARG,
                  "petr_position_mlp_fused: null pointer");
+    if (residual2) PETR_REQUIRE(res2_rows > 0 && aligned16(residual2), PETR_E_BADARG, "petr_position_mlp_fused: residual2");
     PETR_REQUIRE(B > 0 && N > 0 && H > 0 && W > 0, PETR_E_BADARG, "petr_position_mlp_fused: bad dimension");
     PETR_REQUIRE(D == 64 && hidden == HID && embed == EOUT, PETR_E_SHAPE,
                  "petr_position_mlp_fused: specialised for depth_num 64, hidden 1024, embed 256 (got %d, %d, %d)",
                  D, hidden, embed);
-    PETR_REQUIRE(aligned16(W1) && aligned16(W2) && aligned16(out) && aligned16(img2lidar) &&
-                 (!residual || aligned16(residual)), PETR_E_ALIGN, "petr_position_mlp_fused: 16-byte alignment");
+    PETR_REQUIRE(aligned16(W1) && aligned16(W2) && (!out || aligned16(out)) && (!out_bf16 || aligned16(out_bf16)) &&
+                 aligned16(img2lidar) && (!residual || aligned16(residual)), PETR_E_ALIGN,
+                 "petr_position_mlp_fused: 16-byte alignment");
     PeParams p{};
     p.img2lidar = img2lidar; p.B = B; p.N = N; p.H = H; p.W = W; p.pad_h = pad_h; p.pad_w = pad_w; p.lid = lid;
     p.depth_start = depth_start; p.bin_size = bin_size;
     for (int i = 0; i < 3; ++i) { p.scale[i] = 1.f / h_range_span[i]; p.shift[i] = -h_range_lo[i] / h_range_span[i]; }
     p.b1 = b1; p.b2 = b2; p.residual = residual; p.out = out;
+    p.residual2 = residual2; p.res2_rows = res2_rows; p.out_bf16 = (__nv_bfloat16*)out_bf16;
     p.T = (int64_t)B * N * H * W;
     p.dbg = g_pe_dbg;
     CUtensorMap tmW1, tmW2;

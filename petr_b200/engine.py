@@ -110,7 +110,8 @@ def any_key_masked(img_metas, N: int, H: int, W: int) -> bool:
 class MetaInputs:
     """Device-side form of `img_metas` for one forward: everything the kernels read."""
 
-    def __init__(self, img_hw, i2l, time_div, pad_h, pad_w, has_mask):
+    def __init__(self, img_hw, i2l, time_div, pad_h, pad_w, has_mask, uniform_masks=False):
+        self.uniform_masks = bool(uniform_masks)   # every sample has the same img_shape list -> same key masks
         self.img_hw = img_hw          # int32 (B,N,2) device
         self.i2l = i2l                # fp32 (B,N,4,4) device: float64 inverse of lidar2img, rounded once
         self.time_div = time_div      # fp32 (B,) device | None (PETRv2 with_time)
@@ -119,14 +120,15 @@ class MetaInputs:
 
     def views(self, sl: slice) -> "MetaInputs":
         return MetaInputs(self.img_hw[:, sl].contiguous(), self.i2l[:, sl].contiguous(), self.time_div,
-                          self.pad_h, self.pad_w, self.has_mask)
+                          self.pad_h, self.pad_w, self.has_mask, self.uniform_masks)
 
 
 def host_prep(img_metas: Sequence[dict], N: int, H: int, W: int, with_time: bool) -> dict:
     """Vectorised host-side ingestion of the reference's list-of-dicts `img_metas` (no per-(sample,
     camera) python launches, one batched float64 inverse; SURVEY.md hard part 7)."""
     pad_h, pad_w = img_metas[0]["pad_shape"][0][:2]
-    return dict(img_hw=torch.from_numpy(img_hw_from_metas(img_metas, N)),
+    hw = img_hw_from_metas(img_metas, N)
+    return dict(img_hw=torch.from_numpy(hw), uniform_masks=bool((hw == hw[:1]).all()),
                 i2l=torch.from_numpy(img2lidar_from_metas(img_metas)),
                 time_div=mean_time_stamp(img_metas) if with_time else None,
                 pad_h=pad_h, pad_w=pad_w, has_mask=any_key_masked(img_metas, N, H, W))
@@ -137,7 +139,7 @@ def stage_meta(host: dict, device, into: Optional[MetaInputs] = None) -> MetaInp
     if into is None:
         td = _h2d(host["time_div"], device) if host["time_div"] is not None else None
         return MetaInputs(_h2d(host["img_hw"], device), _h2d(host["i2l"], device), td,
-                          host["pad_h"], host["pad_w"], host["has_mask"])
+                          host["pad_h"], host["pad_w"], host["has_mask"], host["uniform_masks"])
     into.img_hw.copy_(_h2d(host["img_hw"], device), non_blocking=True)
     into.i2l.copy_(_h2d(host["i2l"], device), non_blocking=True)
     if into.time_div is not None:
@@ -424,7 +426,8 @@ class HeadEngine:
         returned tensors are the graph's static outputs, valid until the next call."""
         dev = x.device
         ksk = None if not keysplit else (keysplit["world"], keysplit.get("rank"), bool(keysplit.get("emulate")))
-        key = (x.data_ptr(), tuple(x.shape), x.dtype, precision, host["has_mask"], host["pad_h"], host["pad_w"], ksk)
+        key = (x.data_ptr(), tuple(x.shape), x.dtype, precision, host["has_mask"], host["uniform_masks"],
+               host["pad_h"], host["pad_w"], ksk)
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) >= 8:
@@ -432,7 +435,7 @@ class HeadEngine:
             mi = stage_meta(host, dev)
             mi = MetaInputs(mi.img_hw.clone(), mi.i2l.clone(),
                             mi.time_div.clone() if mi.time_div is not None else None,
-                            mi.pad_h, mi.pad_w, mi.has_mask)
+                            mi.pad_h, mi.pad_w, mi.has_mask, mi.uniform_masks)
             self._run(x, mi, precision, None, keysplit)                 # warm-up (lazy packing, attributes)
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()

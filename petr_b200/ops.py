@@ -275,7 +275,7 @@ def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, 
 
 def position_mlp_fused(img2lidar, H: int, W: int, D: int, pad_h: int, pad_w: int, lid: bool,
                        depth_start: float, bin_size: float, position_range, W1, b1, W2, b2,
-                       residual=None, out=None) -> torch.Tensor:
+                       residual=None, out=None, residual2=None, out_bf16=None, want_f32: bool = True):
     """Fused position embedding (petr_head.py:286-334) on tcgen05: img2lidar (B,N,4,4) fp32 ->
     fp32 tokens (T, 256) = MLP(inverse_sigmoid(frustum coords)) (+ residual).  W1 (1024,192) /
     W2 (256,1024) bf16."""
@@ -284,7 +284,7 @@ def position_mlp_fused(img2lidar, H: int, W: int, D: int, pad_h: int, pad_w: int
     T = B * N * H * W
     hidden, embed = W1.shape[0], W2.shape[0]
     assert W1.dtype == torch.bfloat16 and W2.dtype == torch.bfloat16 and W1.is_contiguous() and W2.is_contiguous()
-    if out is None:
+    if out is None and want_f32:
         out = torch.empty((T, embed), dtype=torch.float32, device=img2lidar.device)
     pr = [float(v) for v in position_range]
     lo = host_floats(pr[:3])
@@ -292,7 +292,19 @@ def position_mlp_fused(img2lidar, H: int, W: int, D: int, pad_h: int, pad_w: int
     with _Timed("position_mlp_fused"):
         call("petr_position_mlp_fused", ptr(img2lidar), B, N, H, W, D, int(pad_h), int(pad_w), int(bool(lid)),
              float(depth_start), float(bin_size), lo, span, ptr(W1), ptr(b1), ptr(W2), ptr(b2), hidden, embed,
-             ptr(residual), ptr(out), stream_ptr(img2lidar.device))
+             ptr(residual), ptr(residual2), residual2.shape[0] if residual2 is not None else 0, ptr(out),
+             ptr(out_bf16), stream_ptr(img2lidar.device))
+    return out if out is not None else out_bf16
+
+
+def add_rows_bf16(X, add, out=None) -> torch.Tensor:
+    """bf16(X[r] + add[r % add_rows]) for fp32 (R,E), (add_rows,E)."""
+    _cuda(X, "X")
+    assert X.is_contiguous() and add.is_contiguous()
+    R, E = X.shape
+    if out is None:
+        out = torch.empty((R, E), dtype=torch.bfloat16, device=X.device)
+    call("petr_add_rows_bf16", ptr(X), ptr(add), add.shape[0], ptr(out), R, E, stream_ptr(X.device))
     return out
 
 

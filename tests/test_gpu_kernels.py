@@ -413,3 +413,31 @@ def test_position_mlp_fused(wn, B):
     assert (got - ref).abs().max() <= 2e-2 * scale
     got0 = ops.position_mlp_fused(i2l, H, W, 64, wl.img_h, wl.img_w, True, 1.0, bin_size, pr, w1b, b1, w2b, b2)
     assert (got0 + res - got).abs().max() <= 1e-5 * max(1.0, scale)
+
+
+def test_position_mlp_fused_broadcast_residual_and_add_rows():
+    """K1 with the batch-invariant second residual + bf16 store (the direct K-projection input), and
+    the add_rows_bf16 helper of the unfused / fpe variants."""
+    wl = WORKLOADS["small"]
+    B, N, H, W = 3, wl.num_cams, wl.feat_h, wl.feat_w
+    g = torch.Generator().manual_seed(23)
+    metas = synth.make_img_metas(wl, B, 9)
+    pr = (-61.2, -61.2, -10.0, 61.2, 61.2, 10.0)
+    bin_size = (pr[3] - 1.0) / (64 * 65)
+    w1 = (torch.randn(1024, 192, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
+    b1 = (torch.randn(1024, generator=g) * 0.05).to(DEV)
+    w2 = (torch.randn(256, 1024, generator=g) * 0.03).to(DEV).to(torch.bfloat16)
+    b2 = (torch.randn(256, generator=g) * 0.05).to(DEV)
+    Lk = N * H * W
+    res = torch.randn(B * Lk, 256, generator=g).to(DEV)
+    res2 = torch.randn(Lk, 256, generator=g).to(DEV)
+    i2l = torch.from_numpy(engine.img2lidar_from_metas(metas)).to(DEV)
+    args = (i2l, H, W, 64, wl.img_h, wl.img_w, True, 1.0, bin_size, pr, w1, b1, w2, b2)
+    base = ops.position_mlp_fused(*args, residual=res)
+    f32 = torch.empty_like(base)
+    b16 = torch.empty(B * Lk, 256, dtype=torch.bfloat16, device=DEV)
+    ops.position_mlp_fused(*args, residual=res, residual2=res2, out=f32, out_bf16=b16)
+    exp = base + res2.repeat(B, 1)
+    assert (f32 - exp).abs().max() <= 1e-5 * max(1.0, exp.abs().max().item())
+    assert torch.equal(b16, f32.to(torch.bfloat16))
+    assert torch.equal(ops.add_rows_bf16(base, res2), exp.to(torch.bfloat16))
