@@ -285,8 +285,9 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
         __syncwarp();
         if (threadIdx.x == 64) PE_STAMP(11);
         const int64_t t0w = tile0 + quarter * 32;
+        int r2 = p.residual2 ? (int)(t0w % p.res2_rows) : 0;       // row of the broadcast residual (one 64-bit mod)
 #pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
+        for (int rr = 0; rr < 32; ++rr, r2 = (r2 + 1 == p.res2_rows) ? 0 : r2 + 1) {
             const int64_t tt = t0w + rr;
             if (tt >= p.T) break;
 #pragma unroll
@@ -300,7 +301,7 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
                     o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
                 }
                 if (p.residual2) {
-                    const float4 q4 = __ldg(reinterpret_cast<const float4*>(p.residual2 + (tt % p.res2_rows) * EOUT) + j);
+                    const float4 q4 = __ldg(reinterpret_cast<const float4*>(p.residual2 + (int64_t)r2 * EOUT) + j);
                     o.x += q4.x; o.y += q4.y; o.z += q4.z; o.w += q4.w;
                 }
                 if (p.out) reinterpret_cast<float4*>(p.out + tt * EOUT)[j] = o;
