@@ -267,6 +267,16 @@ def main():
                 out_host[k].copy_(o[k], non_blocking=True)
         main_stream.synchronize()
 
+    # raw H2D bandwidth of one step's features (context for the PCIe-bound e2e figure)
+    hs, he = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    hs.record()
+    for _ in range(3):
+        x_bufs[0].copy_(x_host, non_blocking=True)
+    he.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * x_host.numel() * 4 / (hs.elapsed_time(he) * 1e-3) / 1e9
+
     e2e_run(2)
     barrier()
     t0 = time.perf_counter()
@@ -317,7 +327,8 @@ def main():
                                 precision=args.precision, cuda_graph=bool(args.graph),
                                 l2="inputs larger than L2 (%.0f MB features per step)" % (x_host.numel() * 4 / 1e6)),
                     e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=int(h2d),
-                             d2h_bytes_per_step=int(d2h)),
+                             d2h_bytes_per_step=int(d2h), h2d_gbs_measured=round(h2d_gbs, 1),
+                             note="H2D of step i+1 overlaps compute of step i (two streams)"),
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline, cpu_baseline=cpu)
         if args.breakdown and breakdown:
             sys.stderr.write("per-op breakdown (ms per step, CUDA events):\n")

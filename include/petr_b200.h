@@ -135,6 +135,12 @@ int petr_layernorm_multi_f32(const float* X, const float* gamma, const float* be
 int petr_split_rows_bf16(const float* X, int ldx, const float* add, int add_rows, void* out,
                          int rows, int E, int relu, void* stream);
 
+/* Copies nbytes (multiple of 4) from PINNED host memory (UVA-mapped; the one host pointer this ABI
+ * reads from the device) to device memory with a tiny kernel instead of the copy engine, so the
+ * per-call meta data (img2lidar, img_shape, timestamps) never queues behind a concurrent bulk
+ * feature upload on another stream. */
+int petr_stage_small(const void* h_pinned, void* dst, int nbytes, void* stream);
+
 /* out[r, :] = bf16(X[r, :] + add[r % add_rows, :]); E % 4 == 0. */
 int petr_add_rows_bf16(const float* X, const float* add, int add_rows, void* out, int rows, int E,
                        void* stream);

@@ -37,6 +37,7 @@ SIGNATURES = {
     "petr_gemm_bf16_tc": (c_int, [_P, _I, _I, _P, _I, _P, _P, _I, _F, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "petr_position_mlp_fused": (c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P,
                                         _I, _I, _P, _P, _I, _P, _P, _P]),
+    "petr_stage_small": (c_int, [_P, _P, _I, _P]),
     "petr_add_rows_bf16": (c_int, [_P, _P, _I, _P, _I, _I, _P]),
     "petr_pack_q_bf16": (c_int, [_P, _I, _P, _I, _I, _I, _F, _P]),
     "petr_cross_attention_bf16": (c_int, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -640,6 +640,13 @@ __global__ void add_rows_bf16_kernel(const float* __restrict__ X, const float* _
     reinterpret_cast<uint2*>(out)[i] = o;
 }
 
+// Small host->device staging through the SMs: `src` is pinned (UVA-mapped) host memory.  The few
+// hundred bytes of per-call meta data (img2lidar, img_shape, timestamps) must not queue on the H2D
+// copy engine behind a 100s-of-MB feature upload that runs concurrently on another stream.
+__global__ void stage_small_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int nwords) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 // a12: reference add + sigmoid + pc_range affine (petr_head.py:440-460)
 struct DecodeParams { float pc[6]; };
 
@@ -841,4 +848,14 @@ extern "C" int petr_add_rows_bf16(const float* X, const float* add, int add_rows
     add_rows_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         X, add, add_rows, (__nv_bfloat16*)out, rows, E / 4);
     return after_launch("petr_add_rows_bf16");
+}
+
+extern "C" int petr_stage_small(const void* h_pinned, void* dst, int nbytes, void* stream) {
+    PETR_REQUIRE(h_pinned && dst, PETR_E_BADARG, "petr_stage_small: null pointer");
+    PETR_REQUIRE(nbytes > 0 && (nbytes % 4) == 0, PETR_E_BADARG, "petr_stage_small: nbytes must be a positive multiple of 4");
+    int nwords = nbytes / 4;
+    int blocks = (nwords + 255) / 256;
+    if (blocks > 64) blocks = 64;
+    stage_small_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)h_pinned, (uint32_t*)dst, nwords);
+    return after_launch("petr_stage_small");
 }
