@@ -179,6 +179,9 @@ def main():
     head.precision = args.precision
     head.use_cuda_graph = bool(args.graph)
     if args.keysplit and world > 1:
+        if args.graph:
+            raise SystemExit("--graph with --keysplit is not supported (NCCL collectives captured in a CUDA "
+                             "graph hung process-group teardown; see profiles/README.md)")
         head.keysplit = dict(world=world, rank=rank, group=None)
     # data parallel: each rank gets its own shard of the global batch (different seeds per rank);
     # key-split: every rank gets the same samples
@@ -208,6 +211,7 @@ def main():
     if rank == 0:
         sampler.start()
     ops.reset_launch_count()
+    head.engine.graph_replayed_launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -215,7 +219,7 @@ def main():
         out = head([x_dev], metas)
     e1.record()
     barrier()
-    launches = ops.launch_count()
+    launches = ops.launch_count() + head.engine.graph_replayed_launches
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     # second, separately timed pass with per-launch CUDA events (kept out of `value`: the event

@@ -196,6 +196,7 @@ class HeadEngine:
         self._head = head
         self._packed: Dict[torch.device, dict] = {}
         self._graphs: Dict[tuple, tuple] = {}
+        self.graph_replayed_launches = 0
 
     # -------------------------------------------------------------------------------------
     def invalidate(self):
@@ -422,6 +423,10 @@ class HeadEngine:
         B, N, Cin, H, W = x.shape
         host = host_prep(img_metas, N, H, W, s.with_time)
         if use_graph and taps is None:
+            if keysplit and not keysplit.get("emulate"):
+                # measured once (profiles/README.md): works, but tearing down a process group with live
+                # graphs that captured NCCL collectives hung the ranks at exit -- not supported
+                raise NotImplementedError("use_cuda_graph together with a multi-process key-split is not supported")
             return self._graph_forward(x, host, precision, keysplit)
         return self._run(x, stage_meta(host, x.device), precision, taps, keysplit)
 
@@ -445,13 +450,15 @@ class HeadEngine:
             self._run(x, mi, precision, None, keysplit)                 # warm-up (lazy packing, attributes)
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
             with torch.cuda.graph(g):
                 out = self._run(x, mi, precision, None, keysplit)
-            ent = (g, mi, out)
+            ent = (g, mi, out, ops.launch_count() - n0)
             self._graphs[key] = ent
-        g, mi, out = ent
+        g, mi, out, nlaunch = ent
         stage_meta(host, dev, into=mi)
         g.replay()
+        self.graph_replayed_launches += nlaunch          # kernels of this library inside the replayed graph
         return out
 
     def _run(self, x: torch.Tensor, mi: MetaInputs, precision: str, taps: Optional[dict],

@@ -443,9 +443,23 @@ class LearnedPositionalEncoding3D(BaseModule):
 # ------------------------------------------------------------------------------------------
 # bbox coder (pc_range holder; decode is the first 'next' row of SURVEY.md section 8f)
 # ------------------------------------------------------------------------------------------
+def denormalize_bbox(normalized_bboxes: torch.Tensor) -> torch.Tensor:
+    """core/bbox/util.py:63-87: (cx, cy, log w, log l, cz, log h, sin, cos[, vx, vy]) ->
+    (cx, cy, cz, w, l, h, rot[, vx, vy])."""
+    n = normalized_bboxes
+    rot = torch.atan2(n[..., 6:7], n[..., 7:8])
+    parts = [n[..., 0:1], n[..., 1:2], n[..., 4:5], n[..., 2:3].exp(), n[..., 3:4].exp(), n[..., 5:6].exp(), rot]
+    if n.size(-1) > 8:
+        parts += [n[..., 8:9], n[..., 9:10]]
+    return torch.cat(parts, dim=-1)
+
+
 @BBOX_CODERS.register_module()
 class NMSFreeCoder:
-    """nms_free_coder.py:18-119."""
+    """nms_free_coder.py:18-119.  Holds pc_range for the head and decodes the last decoder
+    layer's predictions: sigmoid -> top-`max_num` over queries x classes -> denormalise ->
+    post_center_range (and score) filter.  Post-processing downstream of the hot path (SURVEY 8f
+    row 1): plain torch tensor ops, vectorised over the batch (one top-k for all samples)."""
 
     def __init__(self, pc_range, voxel_size=None, post_center_range=None, max_num=100,
                  score_threshold=None, num_classes=10):
@@ -455,6 +469,33 @@ class NMSFreeCoder:
         self.max_num = max_num
         self.score_threshold = score_threshold
         self.num_classes = num_classes
+
+    def encode(self):
+        pass
+
+    def _decode_batch(self, cls_scores: torch.Tensor, bbox_preds: torch.Tensor):
+        """cls_scores (B, Q, C), bbox_preds (B, Q, code) -> list of dicts."""
+        if self.post_center_range is None:
+            raise NotImplementedError('Need to reorganize output as a batch, only support '
+                                      'post_center_range is not None for now!')
+        B = cls_scores.shape[0]
+        scores, indexs = cls_scores.sigmoid().reshape(B, -1).topk(self.max_num, dim=1)
+        labels = indexs % self.num_classes
+        bbox_index = indexs // self.num_classes
+        boxes = torch.gather(bbox_preds, 1, bbox_index[..., None].expand(-1, -1, bbox_preds.shape[-1]))
+        boxes = denormalize_bbox(boxes)
+        rng = torch.as_tensor(self.post_center_range, dtype=boxes.dtype, device=boxes.device)
+        mask = (boxes[..., :3] >= rng[:3]).all(-1) & (boxes[..., :3] <= rng[3:]).all(-1)
+        if self.score_threshold:
+            mask &= scores > self.score_threshold
+        return [dict(bboxes=boxes[b][mask[b]], scores=scores[b][mask[b]], labels=labels[b][mask[b]])
+                for b in range(B)]
+
+    def decode_single(self, cls_scores, bbox_preds):
+        return self._decode_batch(cls_scores[None], bbox_preds[None])[0]
+
+    def decode(self, preds_dicts):
+        return self._decode_batch(preds_dicts['all_cls_scores'][-1], preds_dicts['all_bbox_preds'][-1])
 
 
 # ------------------------------------------------------------------------------------------
@@ -624,6 +665,21 @@ class _PETRHeadBase(BaseModule):
                         break
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys,
                                       unexpected_keys, error_msgs)
+
+    def get_bboxes(self, preds_dicts, img_metas, rescale=False):
+        """petr_head.py:731-751: NMS-free decode of the last layer, gravity centre -> bottom centre,
+        wrapped in each sample's `box_type_3d` (left as a plain tensor when img_metas carries none,
+        e.g. without mmdet3d)."""
+        preds = self.bbox_coder.decode(preds_dicts)
+        ret_list = []
+        for i, pr in enumerate(preds):
+            bboxes = pr['bboxes']
+            bboxes[:, 2] = bboxes[:, 2] - bboxes[:, 5] * 0.5
+            box_type = img_metas[i].get('box_type_3d') if img_metas is not None else None
+            if box_type is not None:
+                bboxes = box_type(bboxes, bboxes.size(-1))
+            ret_list.append([bboxes, pr['scores'], pr['labels']])
+        return ret_list
 
     def loss(self, *args, **kwargs):
         raise NotImplementedError("training loss (petr_head.py:647-728) is outside the hot path; "
