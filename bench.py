@@ -28,6 +28,19 @@ sys.path.insert(0, ROOT)
 METRIC = "PETR head 6-view samples/sec at 1600x640, 1/2/4/8 B200; attn % of bf16 peak"
 
 
+def load_traffic(batch):
+    """DRAM bytes per launch of the flash cross-attention kernel from the committed `ncu --set full`
+    capture (dram__bytes_read.sum + dram__bytes_write.sum), if one exists for this batch size."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        ent = d.get(str(batch))
+        if ent:
+            return float(ent["dram_bytes_per_launch"])
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -307,7 +320,8 @@ def main():
         achieved = flops / (avg_ms * 1e-3) / 1e12
         roofline = dict(kernel="cross_attention_tc2_kernel", bound="tensor", achieved=achieved,
                         peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_sustained"],
-                        traffic=None, peak_source=peaks["source"] + " bf16 sustained",
+                        traffic=load_traffic(B) if wl.name == "vov-p4-1600x640" else None,
+                        peak_source=peaks["source"] + " bf16 sustained",
                         launches_timed=len(evs), avg_launch_ms=avg_ms,
                         share_of_step=avg_ms * s.L / ms_per_step,
                         alg_flops_per_launch=flops)

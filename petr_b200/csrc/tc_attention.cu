@@ -1,12 +1,16 @@
-// Flash cross-attention on tcgen05 (petr_transformer.py:357-362, one decoder layer):
+// Attention on tcgen05 for the PETR decoder (petr_transformer.py:341-362, one decoder layer):
 //   S = Q K^T (TMEM, fp32) -> online softmax in registers (one thread per query row, exp2 domain,
 //   lazy rescaling) -> P (bf16, shared memory, UMMA K-major 128B-swizzled) -> O += P V (TMEM).
-// No (B*heads, Lq, Lk) score tensor ever exists; K and V tiles stream through a TMA/mbarrier ring.
+// No (B*heads, Lq, Lk) score tensor ever exists; K and V tiles stream through a TMA/mbarrier ring
+// and V is consumed MN-major straight from its natural [key][32] layout.
 //
-// CTA = one (batch, head, 128-query tile, key split).  Warp 0: TMA producer.  Warp 1: TMEM
-// allocator + single-thread tcgen05.mma issuer.  Warps 2-5: softmax / correction / epilogue, thread
-// r owns query row r (TMEM lane r).  S is double buffered in TMEM and P in shared memory, so
-// QK^T of tile j+1 runs on the tensor core while the softmax warps work on tile j.
+//   v2::cross_attention_tc2_kernel  bf16 flash cross-attention (queries -> 24 000 image tokens): two
+//       128-query tiles per CTA, 11 warps (TMA, two MMA issuers, 2 x 4 softmax), P double buffered,
+//       softmax denominator from the tensor core (P x all-ones operand), split-KV + merge.
+//   x3::attention_x3_tc_kernel      fp32-class self-attention: hi/lo bf16 pairs, three products each
+//       for Q K^T and P V.
+//   attention_merge_kernel          merges (O, m, l) partials: on-GPU split-KV and the key-split
+//       over camera views across GPUs.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <math.h>

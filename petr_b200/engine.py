@@ -129,9 +129,39 @@ class MetaInputs:
                           self.pad_h, self.pad_w, self.has_mask, self.uniform_masks)
 
 
-def host_prep(img_metas: Sequence[dict], N: int, H: int, W: int, with_time: bool) -> dict:
+def stack_img_metas(img_metas: Sequence[dict]) -> dict:
+    """The reference's list-of-dicts wire format -> one dict of stacked arrays:
+    lidar2img (B,N,4,4) float64, img_shape (B,N,2) int, pad_shape (h,w), timestamp (B,N) | absent.
+    Passing this dict as `img_metas` skips the per-sample python of the list format."""
+    out = dict(lidar2img=np.asarray([np.asarray(m["lidar2img"], dtype=np.float64) for m in img_metas]),
+               img_shape=np.asarray([np.asarray(m["img_shape"])[:, :2] for m in img_metas], dtype=np.int32),
+               pad_shape=tuple(int(v) for v in img_metas[0]["pad_shape"][0][:2]))
+    if "timestamp" in img_metas[0]:
+        out["timestamp"] = np.asarray([np.asarray(m["timestamp"], dtype=np.float64) for m in img_metas])
+    return out
+
+
+def _host_prep_stacked(sm: dict, N: int, H: int, W: int, with_time: bool) -> dict:
+    pad_h, pad_w = sm["pad_shape"]
+    hw = np.ascontiguousarray(np.asarray(sm["img_shape"])[:, :N, :2].astype(np.int32))
+    l2i = np.asarray(sm["lidar2img"], dtype=np.float64)
+    last_r, last_c = _nearest_src(H - 1, pad_h, H), _nearest_src(W - 1, pad_w, W)
+    has_mask = bool(((hw[..., 0] <= last_r) | (hw[..., 1] <= last_c)).any())
+    td = None
+    if with_time:
+        ts = torch.tensor(np.asarray(sm["timestamp"]), dtype=torch.float32).view(hw.shape[0], -1, 6)
+        td = (ts[:, 1, :] - ts[:, 0, :]).mean(-1)
+    return dict(img_hw=torch.from_numpy(hw), uniform_masks=bool((hw == hw[:1]).all()),
+                i2l=torch.from_numpy(np.linalg.inv(l2i).astype(np.float32)), time_div=td,
+                pad_h=pad_h, pad_w=pad_w, has_mask=has_mask)
+
+
+def host_prep(img_metas, N: int, H: int, W: int, with_time: bool) -> dict:
     """Vectorised host-side ingestion of the reference's list-of-dicts `img_metas` (no per-(sample,
-    camera) python launches, one batched float64 inverse; SURVEY.md hard part 7)."""
+    camera) python launches, one batched float64 inverse; SURVEY.md hard part 7), or of the
+    pre-stacked dict produced by `stack_img_metas`."""
+    if isinstance(img_metas, dict):
+        return _host_prep_stacked(img_metas, N, H, W, with_time)
     pad_h, pad_w = img_metas[0]["pad_shape"][0][:2]
     hw = img_hw_from_metas(img_metas, N)
     return dict(img_hw=torch.from_numpy(hw), uniform_masks=bool((hw == hw[:1]).all()),

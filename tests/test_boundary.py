@@ -128,3 +128,23 @@ def test_nms_free_decode_properties():
         assert d["scores"][0] == flat.max() or n < 300
     res = head.get_bboxes({k: v.clone() for k, v in outs.items()}, [dict(), dict()])
     assert torch.equal(res[0][0][:, 2], dec[0]["bboxes"][:, 2] - dec[0]["bboxes"][:, 5] * 0.5)
+
+
+def test_stacked_img_metas_ingestion_equals_list_format():
+    """a pre-stacked dict of arrays is ingested identically to the list of dicts."""
+    from petr_b200 import engine, synth
+    for wn, kw in (("vov-p4-800x320", {}), ("v2-vov-p4-800x320", {}),
+                   ("tiny", dict(img_shape=(40, 130), pad_shape=(64, 160)))):
+        wl = pb.WORKLOADS[wn]
+        metas = synth.make_img_metas(wl, 3, 4, **kw)
+        if wn == "tiny":
+            metas[1]["img_shape"] = [(0, 0, 3)] * wl.num_cams
+        a = engine.host_prep(metas, wl.num_cams, wl.feat_h, wl.feat_w, wl.head == "PETRv2Head")
+        b = engine.host_prep(engine.stack_img_metas(metas), wl.num_cams, wl.feat_h, wl.feat_w, wl.head == "PETRv2Head")
+        assert a.keys() == b.keys()
+        for k in a:
+            if isinstance(a[k], torch.Tensor):
+                assert torch.equal(a[k], b[k]), k
+            else:
+                assert a[k] == b[k], k
+    assert a["has_mask"] and not a["uniform_masks"]
