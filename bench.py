@@ -157,12 +157,16 @@ def main():
     ap.add_argument("--cpu-samples", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print per-op CUDA-event times to stderr")
-    ap.add_argument("--graph", action="store_true", help="replay the whole head as one CUDA graph")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=None,
+                    help="replay the whole head as one CUDA graph per input buffer (default, except with --keysplit)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="eager launches")
     ap.add_argument("--keysplit", action="store_true",
                     help="BASELINE config 4: every rank works on the SAME samples, keys split over camera "
                          "views, one NCCL all-gather of (O, m, l) partials per decoder layer (strong scaling)")
     args = ap.parse_args()
 
+    if args.graph is None:
+        args.graph = not args.keysplit
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
