@@ -28,14 +28,19 @@ sys.path.insert(0, ROOT)
 METRIC = "PETR head 6-view samples/sec at 1600x640, 1/2/4/8 B200; attn % of bf16 peak"
 
 
+FLASH_KERNEL = ("cross_attention_tc2_kernel" if os.environ.get("PETR_FLASH_V3", "1") == "0"
+                else "cross_attention_tc3_kernel")
+
+
 def load_traffic(batch):
     """DRAM bytes per launch of the flash cross-attention kernel from the committed `ncu --set full`
-    capture (dram__bytes_read.sum + dram__bytes_write.sum), if one exists for this batch size."""
+    capture (dram__bytes_read.sum + dram__bytes_write.sum), if one exists for this kernel and
+    batch size."""
     p = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.isfile(p):
         with open(p) as f:
             d = json.load(f)
-        ent = d.get(str(batch))
+        ent = d.get(FLASH_KERNEL, {}).get(str(batch))
         if ent:
             return float(ent["dram_bytes_per_launch"])
     return None
@@ -322,7 +327,7 @@ def main():
         s = head.engine.spec
         flops = 4.0 * s.Lq * wl.num_keys * s.E * B                  # per launch (one layer, B samples)
         achieved = flops / (avg_ms * 1e-3) / 1e12
-        roofline = dict(kernel="cross_attention_tc2_kernel", bound="tensor", achieved=achieved,
+        roofline = dict(kernel=FLASH_KERNEL, bound="tensor", achieved=achieved,
                         peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_sustained"],
                         traffic=load_traffic(B) if wl.name == "vov-p4-1600x640" else None,
                         peak_source=peaks["source"] + " bf16 sustained",

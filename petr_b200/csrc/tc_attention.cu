@@ -4,9 +4,11 @@
 // No (B*heads, Lq, Lk) score tensor ever exists; K and V tiles stream through a TMA/mbarrier ring
 // and V is consumed MN-major straight from its natural [key][32] layout.
 //
-//   v2::cross_attention_tc2_kernel  bf16 flash cross-attention (queries -> 24 000 image tokens): two
-//       128-query tiles per CTA, 11 warps (TMA, two MMA issuers, 2 x 4 softmax), P double buffered,
-//       softmax denominator from the tensor core (P x all-ones operand), split-KV + merge.
+//   v3::cross_attention_tc3_kernel  bf16 flash cross-attention (queries -> 24 000 image tokens): two
+//       128-query tiles per CTA, 19 warps (TMA, two MMA issuers, 2 x 8 softmax: TWO threads per
+//       query row), P double buffered, softmax denominator from the tensor core (P x all-ones
+//       operand), split-KV + merge.  The default.
+//   v2::cross_attention_tc2_kernel  its predecessor, one thread per query row (PETR_FLASH_V3=0).
 //   x3::attention_x3_tc_kernel      fp32-class self-attention: hi/lo bf16 pairs, three products each
 //       for Q K^T and P V.
 //   attention_merge_kernel          merges (O, m, l) partials: on-GPU split-KV and the key-split
@@ -631,6 +633,262 @@ cross_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 }
 }  // namespace v2
 
+// ------------------------------------------------------------------------------------------
+// v3: same pipeline as v2, but every query row is shared by TWO softmax threads (64 keys each):
+// 16 softmax warps per CTA = 4 per SM sub-partition instead of 2, so the MUFU pipe (the measured
+// limiter of v2: XU 72 % busy) always has another warp's exponentials to issue while one waits on
+// TMEM, a barrier or its P stores.  The two halves of a row exchange their partial maxima through
+// shared memory (one named barrier per key tile, double buffered by tile parity); the lazy-rescale
+// correction is split as well (half 0 rescales O, half 1 the ones-trick row sum L).
+// Warps: 0 TMA, 1 MMA-A, 2-9 softmax A, 10-17 softmax B, 18 MMA-B.
+// ------------------------------------------------------------------------------------------
+namespace v3 {
+using v2::NQT; using v2::OFF_Q; using v2::OFF_KV; using v2::OFF_P; using v2::OFF_ONES; using v2::OFF_BIAS;
+using v2::TM_S; using v2::TM_O;
+constexpr int OFF_MAX = v2::OFF_BAR;                    // [x][parity][half][128] floats = 4 KB
+constexpr int OFF_BAR = OFF_MAX + NQT * 2 * 2 * QT * 4;
+constexpr int SMEM = OFF_BAR + 256 + 1024;
+constexpr int THREADS = 608;
+
+// (Measured and rejected: letting the warps whose 32 rows lie beyond Lq -- 900 = 7 x 128 + 4 -- skip
+// their exponentials made the launch 27 % SLOWER, 1.31 vs 1.03 ms: the idle warps then poll the
+// s_full mbarrier through the same MIO queue the MUFU instructions of their neighbours use.)
+__global__ void __launch_bounds__(THREADS, 1)
+cross_attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, AttParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* q_full = bars;                        // 1
+    uint64_t* kv_full = bars + 1;                   // KV_STAGES
+    uint64_t* kv_empty = kv_full + KV_STAGES;       // KV_STAGES
+    uint64_t* s_full = kv_empty + KV_STAGES;        // 2 (A, B)
+    uint64_t* s_free = s_full + 2;
+    uint64_t* p_ready = s_free + 2;                 // [x][buf], index 2x + buf
+    uint64_t* pv_done = p_ready + 4;                // [x][buf]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * (NQT * QT);
+    const int bh = blockIdx.y;
+    const int split = blockIdx.z;
+    const int b = bh / p.heads, h = bh - b * p.heads;
+    const int per = (p.tiles_total + p.nsplit - 1) / p.nsplit;
+    const int t_begin = split * per;
+    const int t_end = min(p.tiles_total, t_begin + per);
+    const int ntiles = max(0, t_end - t_begin);
+
+    for (int i = threadIdx.x; i < 4096 / 4; i += THREADS)
+        reinterpret_cast<uint32_t*>(smem + OFF_ONES)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(q_full, 1);
+            for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 256); }
+            for (int i = 0; i < 4; ++i) { mbar_init(&p_ready[i], 256); mbar_init(&pv_done[i], 1); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, TMEM_COLS);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0 && ntiles > 0) {
+            mbar_arrive_expect_tx(q_full, NQT * Q_BYTES);
+            tma_load_3d(smem + OFF_Q, &tmQ, q_full, 0, q0, bh);
+            tma_load_3d(smem + OFF_Q + Q_BYTES, &tmQ, q_full, 0, q0 + QT, bh);
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % KV_STAGES;
+                mbar_wait(&kv_empty[s], ((j / KV_STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
+                uint8_t* kd = smem + OFF_KV + s * (K_BYTES + V_BYTES);
+                const int key0 = (t_begin + j) * KT;
+                tma_load_3d(kd, &tmK, &kv_full[s], 0, key0, bh);
+                tma_load_3d(kd + K_BYTES, &tmV, &kv_full[s], 0, key0, bh);
+            }
+        }
+    } else if (warp == 1 || warp == 18) {
+        // ---------------- MMA issuers: warp 1 drives query tile A, warp 18 tile B ----------------
+        if (lane == 0 && ntiles > 0) {
+            const int x = (warp == 1) ? 0 : 1;
+            constexpr uint32_t idesc_qk = make_idesc(QT, KT, 1, 0, 0);     // S[128x128] = Q K^T
+            constexpr uint32_t idesc_pv = make_idesc(QT, HD, 1, 0, 1);     // O[128x32] += P V (V MN-major)
+            constexpr uint32_t idesc_l = make_idesc(QT, 16, 1, 0, 0);      // L[128x16] += P 1
+            const uint32_t q_addr = smem_u32(smem + OFF_Q + x * Q_BYTES);
+            const uint32_t p_addr = smem_u32(smem + OFF_P + x * 2 * P_BYTES);
+            const uint32_t ones_addr = smem_u32(smem + OFF_ONES);
+            const uint32_t kv_addr = smem_u32(smem + OFF_KV);
+            const uint64_t q_desc0 = make_smem_desc(q_addr, 16, 512, LAYOUT_SW64);
+            const uint64_t k_desc0 = make_smem_desc(kv_addr, 16, 512, LAYOUT_SW64);
+            const uint64_t v_desc0 = make_smem_desc(kv_addr + K_BYTES, 512, 512, LAYOUT_SW64);
+            uint64_t p_desc[KT / 16], o_desc[KT / 16];
+#pragma unroll
+            for (int kk = 0; kk < KT / 16; ++kk) {
+                p_desc[kk] = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+                o_desc[kk] = make_smem_desc(ones_addr + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+            }
+            const uint32_t d_s = tmem_base + TM_S + x * 128;
+            const uint32_t d_o = tmem_base + TM_O + x * 48, d_l = d_o + 32;
+            auto issue_pv = [&](int t) {
+                const int s = t % KV_STAGES;
+                const uint64_t vd = v_desc0 + (uint64_t)((s * (K_BYTES + V_BYTES)) >> 4);
+                const uint64_t pb = (uint64_t)(((t & 1) * P_BYTES) >> 4);
+                mbar_wait(&p_ready[2 * x + (t & 1)], (t >> 1) & 1);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < KT / 16; ++kk) {
+                    umma_f16_ss(d_o, p_desc[kk] + pb, vd + (uint64_t)((kk * 1024) >> 4), idesc_pv, (t | kk) ? 1u : 0u);
+                    umma_f16_ss(d_l, p_desc[kk] + pb, o_desc[kk], idesc_l, (t | kk) ? 1u : 0u);
+                }
+                umma_commit(&pv_done[2 * x + (t & 1)]);
+                umma_commit(&kv_empty[s]);
+            };
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % KV_STAGES;
+                const uint64_t kd = k_desc0 + (uint64_t)((s * (K_BYTES + V_BYTES)) >> 4);
+                mbar_wait(&kv_full[s], (j / KV_STAGES) & 1);
+                mbar_wait(&s_free[x], (j & 1) ^ 1);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    umma_f16_ss(d_s, q_desc0 + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_qk, k ? 1u : 0u);
+                umma_commit(&s_full[x]);
+                if (j > 0) issue_pv(j - 1);
+            }
+            issue_pv(ntiles - 1);
+        }
+    } else {
+        // ---------------- softmax / correction / epilogue ----------------
+        const int g = warp - 2;                              // 0..15
+        const int x = g >> 3;                                // 0: tile A (warps 2-9), 1: tile B (warps 10-17)
+        const int hf = (g >> 2) & 1;                         // which 64 keys of the tile this thread owns
+        const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t s_addr = tmem_base + lane_off + TM_S + x * 128 + hf * 64;
+        const uint32_t o_addr = tmem_base + lane_off + TM_O + x * 48;
+        float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS) + x * KT;
+        float* smax = reinterpret_cast<float*>(smem + OFF_MAX) + x * (4 * QT);
+        uint8_t* pbase = smem + OFF_P + x * 2 * P_BYTES + hf * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
+        float m_use = -INFINITY;
+        const bool use_mask = (p.key_mask != nullptr);
+        for (int j = 0; j < ntiles; ++j) {
+            const uint32_t par = j & 1;
+            const int key0 = (t_begin + j) * KT;
+            const bool need_bias = use_mask || (key0 + KT > p.Lk);
+            if (need_bias) {
+                asm volatile("bar.sync %0, 256;" ::"r"(1 + x) : "memory");   // previous tile's readers done
+                if (hf == 0) {
+                    const int key = key0 + row;
+                    bool dead = key >= p.Lk;
+                    if (!dead && use_mask) dead = p.key_mask[(int64_t)b * p.Lk + key] != 0;
+                    sbias[row] = dead ? -INFINITY : 0.f;
+                }
+                asm volatile("bar.sync %0, 256;" ::"r"(1 + x) : "memory");
+            }
+            mbar_wait(&s_full[x], par);
+            tcgen05_fence_after();
+            uint32_t sr[64];
+            tmem_ld_x32(s_addr, sr);
+            tmem_ld_x32(s_addr + 32, sr + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(&s_free[x]);
+            float* sv = reinterpret_cast<float*>(sr);
+            if (need_bias) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) sv[i] += sbias[hf * 64 + i];
+            }
+            float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
+#pragma unroll
+            for (int i = 4; i < 64; i += 8) {
+                mx0 = max3(mx0, sv[i], sv[i + 1]); mx1 = max3(mx1, sv[i + 2], sv[i + 3]);
+                if (i + 4 < 64) { mx2 = max3(mx2, sv[i + 4], sv[i + 5]); mx3 = max3(mx3, sv[i + 6], sv[i + 7]); }
+            }
+            float mx = fmaxf(max3(mx0, mx1, mx2), mx3);
+            smax[(par * 2 + hf) * QT + row] = mx;
+            asm volatile("bar.sync %0, 256;" ::"r"(3 + x) : "memory");
+            mx = fmaxf(mx, smax[(par * 2 + (hf ^ 1)) * QT + row]);
+            const bool grow = mx > m_use + RESCALE_TH;
+            float alpha = 1.f;
+            if (grow) { alpha = ex2(m_use - mx); m_use = mx; }
+            const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 64; i += 2)
+                pk[i >> 1] = pack_bf16x2(ex2(sv[i] - m_eff), ex2(sv[i + 1] - m_eff));
+            mbar_wait(&pv_done[2 * x + par], ((j >> 1) & 1) ^ 1);          // P buffer j&1 free (PV(j-2) retired)
+            uint8_t* pb = pbase + par * P_BYTES;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint8_t* dst = pb + ((c ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {        // correction after PV_x(j-1): half 0 -> O, half 1 -> L
+                mbar_wait(&pv_done[2 * x + (par ^ 1)], ((j - 1) >> 1) & 1);
+                tcgen05_fence_after();
+                if (hf == 0) {
+                    uint32_t orr[32];
+                    tmem_ld_x32(o_addr, orr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+                    tmem_st_x32(o_addr, orr);
+                } else {
+                    uint32_t orr[16];
+                    tmem_ld_x16(o_addr + 32, orr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+                    tmem_st_x16(o_addr + 32, orr);
+                }
+                tmem_st_wait();
+            }
+            fence_proxy_async_smem();
+            tcgen05_fence_before();
+            mbar_arrive(&p_ready[2 * x + par]);
+        }
+        // ---------------- epilogue (half 0 threads own the output rows) ----------------
+        if (hf == 0) {
+            const int q = q0 + x * QT + row;
+            float o[32], l = 0.f;
+            if (ntiles > 0) {
+                mbar_wait(&pv_done[2 * x + ((ntiles - 1) & 1)], ((ntiles - 1) >> 1) & 1);
+                tcgen05_fence_after();
+                uint32_t orr[48];
+                tmem_ld_x32(o_addr, orr);
+                tmem_ld_x16(o_addr + 32, orr + 32);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(orr[i]);
+                l = __uint_as_float(orr[32]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = 0.f;
+            }
+            if (q < p.Lq) write_attention_row(p, o, m_use, l, b, h, bh, q, split);
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+}  // namespace v3
+
 // merge partial (O, m, l) over parts; thread per (row, 4 dims)
 __global__ void attention_merge_kernel(const float* __restrict__ part, int nparts, float* __restrict__ O,
                                        int ldo, __nv_bfloat16* __restrict__ O_split, int B, int Lq, int heads) {
@@ -749,7 +1007,12 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
               : poly <= 3 ? v2::cross_attention_tc2_kernel<3, true>
               : poly == 4 ? v2::cross_attention_tc2_kernel<4, true>
               : v2::cross_attention_tc2_kernel<6, true>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM);
+    // PETR_FLASH_V3=0 selects the older v2 kernel (one thread per row) for A/B measurements
+    static const bool use_v3 = getenv("PETR_FLASH_V3") ? atoi(getenv("PETR_FLASH_V3")) != 0 : true;
+    typedef void (*flash_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, AttParams);
+    flash_fn fn = kern; int fn_threads = v2::THREADS, smem_bytes = v2::SMEM;
+    if (use_v3) { fn = v3::cross_attention_tc3_kernel; fn_threads = v3::THREADS; smem_bytes = v3::SMEM; }
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return fail((int)e, "petr_cross_attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     AttParams p{};
     p.key_mask = key_mask; p.O = O; p.ldo = ldo; p.O_split = (__nv_bfloat16*)O_split;
@@ -758,7 +1021,7 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
     p.B = B; p.Lq = Lq; p.Lk = Lk; p.heads = heads; p.nsplit = nsplit; p.tiles_total = tiles;
     p.write_partial = part ? 1 : 0;
     dim3 grid((Lq + 2 * QT - 1) / (2 * QT), B * heads, nsplit);
-    kern<<<grid, v2::THREADS, v2::SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    fn<<<grid, fn_threads, smem_bytes, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
     int rc = after_launch("petr_cross_attention_bf16");
     if (rc) return rc;
     if (part && !write_partial) {
