@@ -125,7 +125,8 @@ int petr_layernorm_f32(const float* X, const float* gamma, const float* beta, fl
  * split(Y) and split(Y + qpos[row % qpos_rows]) as bf16 [hi | lo] rows (bf16x3 GEMM inputs:
  * query+query_pos of petr_transformer.py:341); Z = LN2(Y) with nan_to_num (the decoder's
  * post_norm on a copy, petr_transformer.py:444 + petr_head.py:435) as fp32 and/or split bf16.
- * relu != 0 applies ReLU to Y (cls_branches, petr_head.py:226-231). */
+ * relu != 0 applies ReLU to Y (cls_branches, petr_head.py:226-231).  Every pointer must be 16-byte
+ * aligned (one warp per row, 16-byte loads and stores). */
 int petr_layernorm_multi_f32(const float* X, const float* gamma, const float* beta, float eps,
                              const float* qpos, int qpos_rows, float* Y, void* Y_split,
                              void* Ypos_split, const float* gamma2, const float* beta2,

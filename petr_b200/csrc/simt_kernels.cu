@@ -556,16 +556,43 @@ __device__ __forceinline__ void store_split_elem(__nv_bfloat16* base, int E, int
     base[E + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// 8 consecutive fp32 values -> bf16 hi / residual rows (one 16-byte store each).  Paired converts
+// (F2FP, ALU pipe) instead of scalar ones (F2F, quarter-rate XU pipe).
+__device__ __forceinline__ void store_split8(__nv_bfloat16* hp, __nv_bfloat16* lp, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 hv = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        h[i] = *reinterpret_cast<uint32_t*>(&hv);
+        __nv_bfloat162 lv = __floats2bfloat162_rn(v[2 * i] - __uint_as_float(h[i] << 16),
+                                                  v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u));
+        l[i] = *reinterpret_cast<uint32_t*>(&lv);
+    }
+    *reinterpret_cast<uint4*>(hp) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lp) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void load8(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// one warp per row of E = 256; lane owns columns [8 lane, 8 lane + 8): 16-byte loads and stores
 __global__ void __launch_bounds__(256)
 layernorm_multi_kernel(LnMultiParams p) {
     constexpr int PER = 8, E = 256;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= p.rows) return;
-    const float* x = p.X + (int64_t)row * E;
-    float v[PER], y[PER];
+    const int c0 = lane * PER;
+    float v[PER], y[PER], g[PER], bt[PER];
+    load8(p.X + (int64_t)row * E + c0, v);
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { v[i] = x[lane + 32 * i]; s += v[i]; }
+    for (int i = 0; i < PER; ++i) s += v[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     float mean = s / (float)E, q = 0.f;
@@ -574,16 +601,25 @@ layernorm_multi_kernel(LnMultiParams p) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     float rstd = rsqrtf(q / (float)E + p.eps);
+    load8(p.gamma + c0, g);
+    load8(p.beta + c0, bt);
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-        int c = lane + 32 * i;
-        y[i] = (v[i] - mean) * rstd * p.gamma[c] + p.beta[c];
+        y[i] = (v[i] - mean) * rstd * g[i] + bt[i];
         if (p.relu) y[i] = fmaxf(y[i], 0.f);
-        if (p.Y) p.Y[(int64_t)row * E + c] = y[i];
-        if (p.Y_split) store_split_elem(p.Y_split + (int64_t)row * 2 * E, E, c, y[i]);
-        if (p.Ypos_split)
-            store_split_elem(p.Ypos_split + (int64_t)row * 2 * E, E, c,
-                             y[i] + p.qpos[(int64_t)(row % p.qpos_rows) * E + c]);
+    }
+    if (p.Y) store8(p.Y + (int64_t)row * E + c0, y);
+    if (p.Y_split) {
+        __nv_bfloat16* sp = p.Y_split + (int64_t)row * 2 * E + c0;
+        store_split8(sp, sp + E, y);
+    }
+    if (p.Ypos_split) {
+        float qp[PER];
+        load8(p.qpos + (int64_t)(row % p.qpos_rows) * E + c0, qp);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) qp[i] += y[i];
+        __nv_bfloat16* sp = p.Ypos_split + (int64_t)row * 2 * E + c0;
+        store_split8(sp, sp + E, qp);
     }
     if (p.gamma2) {
         s = 0.f;
@@ -597,14 +633,19 @@ layernorm_multi_kernel(LnMultiParams p) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
         rstd = rsqrtf(q / (float)E + p.eps);
+        load8(p.gamma2 + c0, g);
+        load8(p.beta2 + c0, bt);
+        float r[PER];
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
-            int c = lane + 32 * i;
-            float r = (y[i] - mean) * rstd * p.gamma2[c] + p.beta2[c];
-            if (isnan(r)) r = 0.f;
-            else if (isinf(r)) r = r > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
-            if (p.Z) p.Z[(int64_t)row * E + c] = r;
-            if (p.Z_split) store_split_elem(p.Z_split + (int64_t)row * 2 * E, E, c, r);
+            r[i] = (y[i] - mean) * rstd * g[i] + bt[i];
+            if (isnan(r[i])) r[i] = 0.f;
+            else if (isinf(r[i])) r[i] = r[i] > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+        }
+        if (p.Z) store8(p.Z + (int64_t)row * E + c0, r);
+        if (p.Z_split) {
+            __nv_bfloat16* sp = p.Z_split + (int64_t)row * 2 * E + c0;
+            store_split8(sp, sp + E, r);
         }
     }
 }
@@ -821,6 +862,10 @@ extern "C" int petr_layernorm_multi_f32(const float* X, const float* gamma, cons
     PETR_REQUIRE(E == 256, PETR_E_SHAPE, "petr_layernorm_multi_f32: E must be 256, got %d", E);
     if (Ypos_split) PETR_REQUIRE(qpos && qpos_rows > 0, PETR_E_BADARG, "petr_layernorm_multi_f32: qpos required");
     if (Z || Z_split) PETR_REQUIRE(gamma2 && beta2, PETR_E_BADARG, "petr_layernorm_multi_f32: gamma2/beta2 required");
+    PETR_REQUIRE(aligned16(X) && aligned16(gamma) && aligned16(beta) && aligned16(qpos) && aligned16(Y) &&
+                 aligned16(Y_split) && aligned16(Ypos_split) && aligned16(gamma2) && aligned16(beta2) &&
+                 aligned16(Z) && aligned16(Z_split), PETR_E_ALIGN,
+                 "petr_layernorm_multi_f32: every pointer must be 16-byte aligned");
     LnMultiParams p{X, gamma, beta, eps, qpos, qpos_rows, Y, (__nv_bfloat16*)Y_split,
                     (__nv_bfloat16*)Ypos_split, (Z || Z_split) ? gamma2 : nullptr, beta2, Z,
                     (__nv_bfloat16*)Z_split, rows, relu};

@@ -99,12 +99,7 @@ __device__ __forceinline__ void write_attention_row(const AttParams& p, float* o
         __nv_bfloat16* sp = p.O_split + ((int64_t)b * p.Lq + q) * (2 * E) + h * HD;
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-            float h0 = __bfloat162float(__float2bfloat16_rn(o[i]));
-            float h1 = __bfloat162float(__float2bfloat16_rn(o[i + 1]));
-            hi[i >> 1] = pack_bf16x2(h0, h1);
-            lo[i >> 1] = pack_bf16x2(o[i] - h0, o[i + 1] - h1);
-        }
+        for (int i = 0; i < 32; i += 2) split_bf16x2(o[i], o[i + 1], hi[i >> 1], lo[i >> 1]);
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
             *reinterpret_cast<uint4*>(sp + 2 * i) = make_uint4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]);
@@ -119,18 +114,22 @@ __device__ __forceinline__ void write_attention_row(const AttParams& p, float* o
 //   S = Qh Kh^T + Ql Kh^T + Qh Kl^T,     O = Ph Vh + Pl Vh + Ph Vl,     P = Ph + Pl
 // so every product carries ~16 mantissa bits (error ~2^-16, like the bf16x3 GEMMs); a plain bf16
 // self-attention costs 0.04-0.06 m in cx/cy (tests/precision_study.py).  One 128-query tile per
-// CTA, S double buffered in TMEM, l accumulated in fp32 registers.
+// CTA, S double buffered in TMEM, P (hi and lo) double buffered in shared memory, two softmax
+// threads per query row (the exp + hi/lo split is ~10 instructions per score: one warp per SM
+// sub-partition was latency-bound), l accumulated in fp32 registers.
 // ------------------------------------------------------------------------------------------
 namespace x3 {
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;
 constexpr int STAGE_BYTES = 2 * K_BYTES + 2 * V_BYTES;              // Kh, Kl, Vh, Vl
 constexpr int OFF_Q = 0;                                            // Qh, Ql
 constexpr int OFF_KV = OFF_Q + 2 * Q_BYTES;
-constexpr int OFF_P = OFF_KV + STAGES * STAGE_BYTES;                // Ph, Pl
-constexpr int OFF_BIAS = OFF_P + 2 * P_BYTES;
-constexpr int OFF_BAR = OFF_BIAS + KT * 4;
+constexpr int OFF_P = OFF_KV + STAGES * STAGE_BYTES;                // 2 buffers x (Ph, Pl)
+constexpr int OFF_BIAS = OFF_P + 4 * P_BYTES;
+constexpr int OFF_MAX = OFF_BIAS + KT * 4;                          // [parity][half][128] row maxima
+constexpr int OFF_LX = OFF_MAX + 2 * 2 * QT * 4;                    // [128] half-row sums (epilogue)
+constexpr int OFF_BAR = OFF_LX + QT * 4;
 constexpr int SMEM = OFF_BAR + 256 + 1024;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;        // TMA, MMA, 2 x 4 softmax (two threads per query row)
 
 struct Maps { CUtensorMap qh, ql, kh, kl, vh, vl; };
 
@@ -140,13 +139,15 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* q_full = bars;                        // 1
-    uint64_t* kv_full = bars + 1;                   // STAGES
-    uint64_t* kv_empty = kv_full + STAGES;          // STAGES
-    uint64_t* s_full = kv_empty + STAGES;           // 2
+    uint64_t* k_full = bars + 1;                    // STAGES: (Kh, Kl) of a stage landed
+    uint64_t* k_empty = k_full + STAGES;            // STAGES: Q K^T of that stage retired
+    uint64_t* v_full = k_empty + STAGES;            // STAGES: (Vh, Vl) landed
+    uint64_t* v_empty = v_full + STAGES;            // STAGES: P V of that stage retired
+    uint64_t* s_full = v_empty + STAGES;            // 2
     uint64_t* s_free = s_full + 2;                  // 2
-    uint64_t* p_ready = s_free + 2;                 // 1
-    uint64_t* pv_done = p_ready + 1;                // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+    uint64_t* p_ready = s_free + 2;                 // 2 (P buffer)
+    uint64_t* pv_done = p_ready + 2;                // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
     float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -166,9 +167,12 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(q_full, 1);
-            for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); }
-            mbar_init(p_ready, 128); mbar_init(pv_done, 1);
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+                mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+            }
+            for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 256); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], 256); mbar_init(&pv_done[i], 1); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -184,163 +188,205 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
             mbar_arrive_expect_tx(q_full, 2 * Q_BYTES);
             tma_load_3d(smem + OFF_Q, &tm.qh, q_full, 0, qtile * QT, bh);
             tma_load_3d(smem + OFF_Q + Q_BYTES, &tm.ql, q_full, 0, qtile * QT, bh);
-            for (int j = 0; j < ntiles; ++j) {
+            // K and V of a stage are released separately (K right after Q K^T, V after P V) and the K
+            // loads run one tile ahead of the V loads: with one shared barrier the K tile of j + 1 was
+            // requested only after P V of j - 1, and its TMA latency stalled the softmax warps on S
+            auto load_k = [&](int j) {
                 const int s = j % STAGES;
-                mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(&kv_full[s], STAGE_BYTES);
+                mbar_wait(&k_empty[s], ((j / STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&k_full[s], 2 * K_BYTES);
                 uint8_t* d = smem + OFF_KV + s * STAGE_BYTES;
                 const int key0 = (t_begin + j) * KT;
-                tma_load_3d(d, &tm.kh, &kv_full[s], 0, key0, bh);
-                tma_load_3d(d + K_BYTES, &tm.kl, &kv_full[s], 0, key0, bh);
-                tma_load_3d(d + 2 * K_BYTES, &tm.vh, &kv_full[s], 0, key0, bh);
-                tma_load_3d(d + 2 * K_BYTES + V_BYTES, &tm.vl, &kv_full[s], 0, key0, bh);
+                tma_load_3d(d, &tm.kh, &k_full[s], 0, key0, bh);
+                tma_load_3d(d + K_BYTES, &tm.kl, &k_full[s], 0, key0, bh);
+            };
+            auto load_v = [&](int j) {
+                const int s = j % STAGES;
+                mbar_wait(&v_empty[s], ((j / STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&v_full[s], 2 * V_BYTES);
+                uint8_t* d = smem + OFF_KV + s * STAGE_BYTES + 2 * K_BYTES;
+                const int key0 = (t_begin + j) * KT;
+                tma_load_3d(d, &tm.vh, &v_full[s], 0, key0, bh);
+                tma_load_3d(d + V_BYTES, &tm.vl, &v_full[s], 0, key0, bh);
+            };
+            load_k(0);
+            for (int j = 0; j < ntiles; ++j) {
+                if (j + 1 < ntiles) load_k(j + 1);
+                load_v(j);
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && ntiles > 0) {
             constexpr uint32_t idesc_qk = make_idesc(QT, KT, 1, 0, 0);
             constexpr uint32_t idesc_pv = make_idesc(QT, HD, 1, 0, 1);
+            // every descriptor that does not depend on the K/V stage is built once; per-stage ones
+            // are one 64-bit add (the single issuing thread is on the critical path of each tile)
             const uint32_t q_addr = smem_u32(smem + OFF_Q);
+            const uint32_t p_addr = smem_u32(smem + OFF_P);
+            const uint32_t kv_addr = smem_u32(smem + OFF_KV);
+            const uint64_t qh_desc = make_smem_desc(q_addr, 16, 512, LAYOUT_SW64);
+            const uint64_t ql_desc = make_smem_desc(q_addr + Q_BYTES, 16, 512, LAYOUT_SW64);
+            const uint64_t kh_desc0 = make_smem_desc(kv_addr, 16, 512, LAYOUT_SW64);
+            const uint64_t vh_desc0 = make_smem_desc(kv_addr + 2 * K_BYTES, 512, 512, LAYOUT_SW64);
+            uint64_t ph_desc[KT / 16];
+#pragma unroll
+            for (int kk = 0; kk < KT / 16; ++kk)
+                ph_desc[kk] = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
             auto issue_qk = [&](int t) {
                 const int s = t % STAGES;
-                mbar_wait(&kv_full[s], (t / STAGES) & 1);
+                mbar_wait(&k_full[s], (t / STAGES) & 1);
                 mbar_wait(&s_free[t & 1], ((t >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
-                const uint32_t k_addr = smem_u32(smem + OFF_KV + s * STAGE_BYTES);
+                const uint64_t kh = kh_desc0 + (uint64_t)((s * STAGE_BYTES) >> 4);
+                const uint64_t kl = kh + (uint64_t)(K_BYTES >> 4);
                 const uint32_t d = tmem_base + ((t & 1) ? TM_S1 : TM_S0);
                 // (Qh,Kh), (Ql,Kh), (Qh,Kl)
-                const uint32_t qa[3] = {q_addr, q_addr + Q_BYTES, q_addr};
-                const uint32_t ka[3] = {k_addr, k_addr, k_addr + K_BYTES};
 #pragma unroll
-                for (int t3 = 0; t3 < 3; ++t3)
+                for (int k = 0; k < HD / 16; ++k) umma_f16_ss(d, qh_desc + (uint64_t)(k * 2), kh + (uint64_t)(k * 2), idesc_qk, k ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k) {
-                        uint64_t ad = make_smem_desc(qa[t3] + k * 32, 16, 512, LAYOUT_SW64);
-                        uint64_t bd = make_smem_desc(ka[t3] + k * 32, 16, 512, LAYOUT_SW64);
-                        umma_f16_ss(d, ad, bd, idesc_qk, (t3 | k) ? 1u : 0u);
-                    }
+                for (int k = 0; k < HD / 16; ++k) umma_f16_ss(d, ql_desc + (uint64_t)(k * 2), kh + (uint64_t)(k * 2), idesc_qk, 1u);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) umma_f16_ss(d, qh_desc + (uint64_t)(k * 2), kl + (uint64_t)(k * 2), idesc_qk, 1u);
                 umma_commit(&s_full[t & 1]);
+                umma_commit(&k_empty[s]);
             };
             mbar_wait(q_full, 0);
             issue_qk(0);
             for (int j = 0; j < ntiles; ++j) {
                 if (j + 1 < ntiles) issue_qk(j + 1);
                 const int s = j % STAGES;
-                mbar_wait(p_ready, j & 1);
+                mbar_wait(&v_full[s], (j / STAGES) & 1);
+                mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
                 tcgen05_fence_after();
-                const uint32_t p_addr = smem_u32(smem + OFF_P);
-                const uint32_t v_addr = smem_u32(smem + OFF_KV + s * STAGE_BYTES + 2 * K_BYTES);
+                const uint64_t pb = (uint64_t)(((j & 1) * 2 * P_BYTES) >> 4);          // P buffer of tile j
+                const uint64_t vh = vh_desc0 + (uint64_t)((s * STAGE_BYTES) >> 4);
+                const uint64_t vl = vh + (uint64_t)(V_BYTES >> 4);
+                const uint64_t pl_off = (uint64_t)(P_BYTES >> 4);
                 // (Ph,Vh), (Pl,Vh), (Ph,Vl)
-                const uint32_t pa[3] = {p_addr, p_addr + P_BYTES, p_addr};
-                const uint32_t va[3] = {v_addr, v_addr, v_addr + V_BYTES};
 #pragma unroll
-                for (int t3 = 0; t3 < 3; ++t3)
+                for (int kk = 0; kk < KT / 16; ++kk)
+                    umma_f16_ss(tmem_base + TM_O, ph_desc[kk] + pb, vh + (uint64_t)((kk * 1024) >> 4), idesc_pv, (j | kk) ? 1u : 0u);
 #pragma unroll
-                    for (int kk = 0; kk < KT / 16; ++kk) {
-                        uint64_t ad = make_smem_desc(pa[t3] + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
-                        uint64_t bd = make_smem_desc(va[t3] + kk * 1024, 512, 512, LAYOUT_SW64);
-                        umma_f16_ss(tmem_base + TM_O, ad, bd, idesc_pv, (j | t3 | kk) ? 1u : 0u);
-                    }
-                umma_commit(&kv_empty[s]);
-                umma_commit(pv_done);
+                for (int kk = 0; kk < KT / 16; ++kk)
+                    umma_f16_ss(tmem_base + TM_O, ph_desc[kk] + pb + pl_off, vh + (uint64_t)((kk * 1024) >> 4), idesc_pv, 1u);
+#pragma unroll
+                for (int kk = 0; kk < KT / 16; ++kk)
+                    umma_f16_ss(tmem_base + TM_O, ph_desc[kk] + pb, vl + (uint64_t)((kk * 1024) >> 4), idesc_pv, 1u);
+                umma_commit(&v_empty[s]);
+                umma_commit(&pv_done[j & 1]);
             }
         }
     } else {
-        const int quarter = warp & 3;
+        // ---------------- softmax: two threads per query row, 64 keys each ----------------
+        const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
+        const int hf = (warp - 2) >> 2;                      // which 64 keys of the tile
         const int row = quarter * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-        uint8_t* prow = smem + OFF_P + (row >> 3) * 1024 + (row & 7) * 128;
-        float m_use = -INFINITY, l = 0.f;            // m_use in the scaled (log2) domain
+        const uint32_t o_addr = tmem_base + lane_off + TM_O + hf * 16;     // this half rescales 16 O columns
+        uint8_t* prow = smem + OFF_P + hf * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
+        float* smax = reinterpret_cast<float*>(smem + OFF_MAX);            // [parity][half][128]
+        float m_use = -INFINITY, l = 0.f;            // m_use in the scaled (log2) domain; l: this half's share
         const bool use_mask = (p.key_mask != nullptr);
         for (int j = 0; j < ntiles; ++j) {
             const int bsel = j & 1;
             const int key0 = (t_begin + j) * KT;
             const bool need_bias = use_mask || (key0 + KT > p.Lk);
             if (need_bias) {
-                const int key = key0 + row;
-                bool dead = key >= p.Lk;
-                if (!dead && use_mask) dead = p.key_mask[(int64_t)b * p.Lk + key] != 0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                sbias[row] = dead ? -INFINITY : 0.f;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // previous tile's readers done
+                if (hf == 0) {
+                    const int key = key0 + row;
+                    bool dead = key >= p.Lk;
+                    if (!dead && use_mask) dead = p.key_mask[(int64_t)b * p.Lk + key] != 0;
+                    sbias[row] = dead ? -INFINITY : 0.f;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             mbar_wait(&s_full[bsel], (j >> 1) & 1);
             tcgen05_fence_after();
-            uint32_t sr[128];
-            const uint32_t s_addr = tmem_base + lane_off + (bsel ? TM_S1 : TM_S0);
+            uint32_t sr[64];
+            const uint32_t s_addr = tmem_base + lane_off + (bsel ? TM_S1 : TM_S0) + hf * 64;
             tmem_ld_x32(s_addr, sr);
             tmem_ld_x32(s_addr + 32, sr + 32);
-            tmem_ld_x32(s_addr + 64, sr + 64);
-            tmem_ld_x32(s_addr + 96, sr + 96);
             tmem_ld_wait();
             tcgen05_fence_before();
             mbar_arrive(&s_free[bsel]);
             float* sv = reinterpret_cast<float*>(sr);
 #pragma unroll
-            for (int i = 0; i < 128; ++i) sv[i] *= scale_log2;
+            for (int i = 0; i < 64; ++i) sv[i] *= scale_log2;
             if (need_bias) {
 #pragma unroll
-                for (int i = 0; i < 128; ++i) sv[i] += sbias[i];
+                for (int i = 0; i < 64; ++i) sv[i] += sbias[hf * 64 + i];
             }
             float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
 #pragma unroll
-            for (int i = 4; i < 128; i += 8) {
+            for (int i = 4; i < 64; i += 8) {
                 mx0 = max3(mx0, sv[i], sv[i + 1]); mx1 = max3(mx1, sv[i + 2], sv[i + 3]);
-                if (i + 4 < 128) { mx2 = max3(mx2, sv[i + 4], sv[i + 5]); mx3 = max3(mx3, sv[i + 6], sv[i + 7]); }
+                if (i + 4 < 64) { mx2 = max3(mx2, sv[i + 4], sv[i + 5]); mx3 = max3(mx3, sv[i + 6], sv[i + 7]); }
             }
-            const float mx = fmaxf(max3(mx0, mx1, mx2), mx3);
+            float mx = fmaxf(max3(mx0, mx1, mx2), mx3);
+            smax[(bsel * 2 + hf) * QT + row] = mx;           // the two halves of a row agree on one maximum
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            mx = fmaxf(mx, smax[(bsel * 2 + (hf ^ 1)) * QT + row]);
             const bool grow = mx > m_use + RESCALE_TH;
             float alpha = 1.f;
             if (grow) { alpha = ex2(m_use - mx); m_use = mx; l *= alpha; }
             const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
-            mbar_wait(pv_done, (j & 1) ^ 1);                   // P / O free: PV(j-1) retired
-            float lsum = 0.f;
+            // P (hi and lo) is double buffered: buffer j&1 is free once PV(j-2) has retired, so neither
+            // the exponentials nor the stores wait for P V of the previous tile
+            float lsum0 = 0.f, lsum1 = 0.f;
+            uint32_t hi[32], lo[32];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {                     // 16 chunks of 8 keys
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float p0 = ex2(sv[8 * c + 2 * e] - m_eff), p1 = ex2(sv[8 * c + 2 * e + 1] - m_eff);
-                    lsum += p0 + p1;
-                    const float h0 = __bfloat162float(__float2bfloat16_rn(p0));
-                    const float h1 = __bfloat162float(__float2bfloat16_rn(p1));
-                    hi[e] = pack_bf16x2(h0, h1);
-                    lo[e] = pack_bf16x2(p0 - h0, p1 - h1);
-                }
-                uint8_t* dst = prow + (c >> 3) * 16384 + (((c & 7) ^ (row & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(dst + P_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            for (int i = 0; i < 32; ++i) {
+                const float p0 = ex2(sv[2 * i] - m_eff), p1 = ex2(sv[2 * i + 1] - m_eff);
+                lsum0 += p0; lsum1 += p1;
+                split_bf16x2(p0, p1, hi[i], lo[i]);
             }
-            l += lsum;
-            if (j > 0 && __any_sync(0xffffffffu, grow)) {
+            l += lsum0 + lsum1;
+            mbar_wait(&pv_done[j & 1], ((j >> 1) & 1) ^ 1);
+            uint8_t* pbuf = prow + (j & 1) * 2 * P_BYTES;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {                      // 8 chunks of 8 keys
+                uint8_t* dst = pbuf + ((c ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                *reinterpret_cast<uint4*>(dst + P_BYTES) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+            }
+            if (j > 0 && __any_sync(0xffffffffu, grow)) {        // correction: O *= alpha after PV(j-1)
+                mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                tcgen05_fence_after();
+                uint32_t orr[16];
+                tmem_ld_x16(o_addr, orr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+                tmem_st_x16(o_addr, orr);
+                tmem_st_wait();
+            }
+            fence_proxy_async_smem();
+            tcgen05_fence_before();
+            mbar_arrive(&p_ready[j & 1]);
+        }
+        // ---------------- epilogue: half 1 hands its share of l over, half 0 writes the row ----------------
+        float* lx = reinterpret_cast<float*>(smem + OFF_LX);
+        if (hf == 1) lx[row] = l;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (hf == 0) {
+            l += lx[row];
+            const int q = qtile * QT + row;
+            float o[32];
+            if (ntiles > 0) {
+                mbar_wait(&pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
                 tcgen05_fence_after();
                 uint32_t orr[32];
                 tmem_ld_x32(tmem_base + lane_off + TM_O, orr);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
-                tmem_st_x32(tmem_base + lane_off + TM_O, orr);
-                tmem_st_wait();
+                for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(orr[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = 0.f;
             }
-            fence_proxy_async_smem();
-            tcgen05_fence_before();
-            mbar_arrive(p_ready);
+            if (q < p.Lq) write_attention_row(p, o, m_use, l, b, h, bh, q, split);
         }
-        const int q = qtile * QT + row;
-        float o[32];
-        if (ntiles > 0) {
-            mbar_wait(pv_done, (ntiles - 1) & 1);
-            tcgen05_fence_after();
-            uint32_t orr[32];
-            tmem_ld_x32(tmem_base + lane_off + TM_O, orr);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(orr[i]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = 0.f;
-        }
-        if (q < p.Lq) write_attention_row(p, o, m_use, l, b, h, bh, q, split);
         tcgen05_fence_before();
     }
     __syncthreads();
@@ -650,9 +696,13 @@ constexpr int OFF_BAR = OFF_MAX + NQT * 2 * 2 * QT * 4;
 constexpr int SMEM = OFF_BAR + 256 + 1024;
 constexpr int THREADS = 608;
 
-// (Measured and rejected: letting the warps whose 32 rows lie beyond Lq -- 900 = 7 x 128 + 4 -- skip
-// their exponentials made the launch 27 % SLOWER, 1.31 vs 1.03 ms: the idle warps then poll the
-// s_full mbarrier through the same MIO queue the MUFU instructions of their neighbours use.)
+// Measured on B200 at B = 16 (24 000 keys, 1.03 ms per launch) and rejected:
+//   * warps whose 32 rows lie beyond Lq (900 = 7 x 128 + 4) skipping their exponentials: 1.31-1.36 ms,
+//     with a spinning or a nanosleep-backed wait and with zero-filled P rows alike (cause not found);
+//   * 2/16 or 4/16 of the exponentials on the FMA pipe (cubic): 1.25 / 1.28 ms (issue-bound);
+//   * independent half-row streams merged in the epilogue (no per-tile max exchange): 1.06 ms;
+//   * half-tile software pipelining of v2 (TMEM load of the next 64 scores under the current 64
+//     exponentials, one thread per row): 1.48 ms.
 __global__ void __launch_bounds__(THREADS, 1)
 cross_attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                            const __grid_constant__ CUtensorMap tmV, AttParams p) {
@@ -919,10 +969,11 @@ __global__ void attention_merge_kernel(const float* __restrict__ part, int npart
     if (O_split) {
         const int E = heads * 32;
         __nv_bfloat16* sp = O_split + ((int64_t)b * Lq + q) * (2 * E) + h * 32 + d4;
-        float h0 = __bfloat162float(__float2bfloat16_rn(acc.x)), h1 = __bfloat162float(__float2bfloat16_rn(acc.y));
-        float h2 = __bfloat162float(__float2bfloat16_rn(acc.z)), h3 = __bfloat162float(__float2bfloat16_rn(acc.w));
-        *reinterpret_cast<uint2*>(sp) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-        *reinterpret_cast<uint2*>(sp + E) = make_uint2(pack_bf16x2(acc.x - h0, acc.y - h1), pack_bf16x2(acc.z - h2, acc.w - h3));
+        uint32_t hi0, lo0, hi1, lo1;
+        split_bf16x2(acc.x, acc.y, hi0, lo0);
+        split_bf16x2(acc.z, acc.w, hi1, lo1);
+        *reinterpret_cast<uint2*>(sp) = make_uint2(hi0, hi1);
+        *reinterpret_cast<uint2*>(sp + E) = make_uint2(lo0, lo1);
     }
 }
 

@@ -207,6 +207,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// (a, b) -> packed bf16 pair hi = rn(a, b) and packed residual lo = rn(a - hi.a, b - hi.b) for the
+// bf16x3 operands.  The paired convert is one F2FP on the ALU pipe; a scalar __float2bfloat16_rn is
+// an F2F on the quarter-rate XU pipe that the exponentials need (x3 attention: XU 44 % busy, half of
+// it conversions).
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(a, b);
+    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+
 }  // namespace tc
 
 // ---- host: tensor maps (driver entry point resolved at run time; no link-time libcuda) --------

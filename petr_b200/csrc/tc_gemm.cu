@@ -74,6 +74,18 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* cp, const float* v)
     }
 }
 
+// 32 fp32 values -> bf16 hi row and bf16 residual row (bf16x3 operand pair), 4 x 16-byte stores each
+__device__ __forceinline__ void store_split_bf16x32(__nv_bfloat16* hp, __nv_bfloat16* lp, const float* v) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        uint4 h, l;
+        split_bf16x2(v[j], v[j + 1], h.x, l.x); split_bf16x2(v[j + 2], v[j + 3], h.y, l.y);
+        split_bf16x2(v[j + 4], v[j + 5], h.z, l.z); split_bf16x2(v[j + 6], v[j + 7], h.w, l.w);
+        *reinterpret_cast<uint4*>(hp + j) = h;
+        *reinterpret_cast<uint4*>(lp + j) = l;
+    }
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     EpiParams p) {
@@ -246,22 +258,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     // head-split [hi | lo] pair: C = hi array, C2 = lo array, both [n / E][b][head][key][32]
                     const int l = nb / p.kv_E, h = (nb % p.kv_E) >> 5;
                     const int64_t off = ((((int64_t)l * p.kv_B + kv_b) * (p.kv_E >> 5) + h) * p.kv_Lk + kv_key) * 32;
-                    float lo[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
-                    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + off, v);
-                    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C2) + off, lo);
+                    store_split_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + off,
+                                        reinterpret_cast<__nv_bfloat16*>(p.C2) + off, v);
                 } else if (p.out_mode == 3) {
                     // bf16 split [hi | lo] for the bf16x3 GEMMs: row m, hi at [nb], lo at [N + nb]
-                    float lo[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float hi = __bfloat162float(__float2bfloat16_rn(v[j]));
-                        lo[j] = v[j] - hi;
-                    }
                     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m * (2 * p.N) + nb;
-                    store_bf16x32(cp, v);
-                    store_bf16x32(cp + p.N, lo);
+                    store_split_bf16x32(cp, cp + p.N, v);
                 }
             }
             tcgen05_fence_before();
