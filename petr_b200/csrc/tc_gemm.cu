@@ -171,17 +171,29 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int chalf = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         uint32_t tcount = 0;
+        // bias of a tile's 256 columns lives in shared memory (per-chunk global loads were the top
+        // stall of the epilogue), double buffered by tile parity.  The values of tile i + 1 are
+        // fetched into a register while tile i is processed and stored at its end, so the global
+        // load latency is off the per-tile critical path; one 256-thread named barrier per tile.
+        const int et = threadIdx.x - 64;                             // 0..255 among the epilogue warps
+        const uint32_t sbias_u32 = smem_u32(sbias);
+        if (p.bias && (int)blockIdx.x < num_tiles) {
+            const int n0 = ((int)blockIdx.x % p.tiles_n) * BN;
+            sbias[et] = (n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
+        }
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
             const uint32_t buf = tcount & 1;
             const int m = m0 + row;
-            // bias of this tile's 256 columns -> shared memory once (per-chunk global loads were the
-            // top stall of the epilogue); double buffered by tile parity, one 256-thread named barrier
-            float* sb = sbias + buf * BN;
+            const uint32_t sb = sbias_u32 + buf * BN * 4;
+            float next_bias = 0.f;
             if (p.bias) {
-                const int et = threadIdx.x - 64;                     // 0..255 among the epilogue warps
-                sb[et] = (n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // this tile's bias visible; previous tile's readers done
+                const int nt = tile + gridDim.x;
+                if (nt < num_tiles) {
+                    const int nn = (nt % p.tiles_n) * BN + et;
+                    if (nn < p.N) next_bias = __ldg(p.bias + nn);
+                }
             }
             mbar_wait(&acc_full[buf], (tcount >> 1) & 1);
             tcgen05_fence_after();
@@ -205,7 +217,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (p.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 t = *reinterpret_cast<const float4*>(sb + c * 32 + j);
+                        float4 t;                                    // explicit ld.shared (the generic form was an LD.E)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(sb + (c * 32 + j) * 4));
                         v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
                     }
                 }
@@ -268,6 +282,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             tcgen05_fence_before();
             mbar_arrive(&acc_empty[buf]);
+            if (p.bias) sbias[(buf ^ 1) * BN + et] = next_bias;     // read after the next tile's barrier
         }
     }
     __syncthreads();

@@ -330,6 +330,31 @@ def test_gemm_bf16_tc_headsplit():
     assert (got.float() - ref).abs().max() <= 0.05
 
 
+@pytest.mark.parametrize("M,N", [(148 * 128, 256), (19000, 256), (40 * 128 + 5, 1536), (2 * 24000, 1536)])
+def test_gemm_bf16_tc_large_m(M, N):
+    """K = 256 with more output tiles than SMs (the key-side GEMMs over B * Lk tokens): several
+    tiles per persistent CTA, bias tiles prefetched one tile ahead, all output forms, ragged last
+    m-tile, n-tile changing from one tile of a CTA to the next."""
+    K = 256
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) / 16).to(DEV).to(torch.bfloat16)
+    b = torch.randn(N, generator=g).to(DEV)
+    ref = A.float() @ W.float().T + b                                      # fp32 on bf16-exact inputs
+    got = ops.gemm_bf16_tc(A, W, b)
+    assert (got - ref).abs().max() <= 3e-4
+    f32 = torch.empty(M, N, device=DEV)
+    sp = ops.gemm_bf16_tc(A, W, b, split_out=True, out_f32=f32)
+    assert (f32 - ref).abs().max() <= 3e-4
+    assert (sp[:, :N].float() + sp[:, N:].float() - ref).abs().max() <= 6e-5 * ref.abs().max()
+    if M % 24000 == 0:
+        Lk = 24000
+        hs = ops.gemm_bf16_tc(A, W, b, headsplit_Lk=Lk)
+        want = ref.view(M // Lk, Lk, N // 256, 8, 32).permute(2, 0, 3, 1, 4)
+        assert hs.shape == want.shape
+        assert (hs.float() - want).abs().max() <= 0.05
+
+
 def _flash_inputs(B, Lq, Lk, qscale, seed):
     g = torch.Generator().manual_seed(seed)
     q = (torch.randn(B * Lq, 256, generator=g) * qscale).to(DEV)
