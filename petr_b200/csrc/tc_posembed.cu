@@ -19,8 +19,6 @@
 #include "tc_common.cuh"
 #include <math.h>
 
-static long long* g_pe_dbg = nullptr;
-extern "C" void petr_debug_set_ptr(void* p) { g_pe_dbg = (long long*)p; }
 
 namespace petr {
 namespace {
@@ -55,10 +53,8 @@ struct PeParams {
     const float* b1; const float* b2; const float* residual; float* out;
     const float* residual2; int res2_rows; __nv_bfloat16* out_bf16;   // + residual2[t % res2_rows]; optional bf16 store
     int64_t T;
-    long long* dbg;                     // optional per-CTA phase timestamps (profiling aid)
 };
 
-#define PE_STAMP(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ float inv_sigmoid_fast(float x) {
     x = fminf(fmaxf(x, 0.f), 1.f);
@@ -105,7 +101,6 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (threadIdx.x == 64) PE_STAMP(0);
 
     if (warp == 0) {
         // ---------------- TMA: stream the weights through a 7-stage ring, in the MMA's order ----------------
@@ -160,7 +155,6 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
                 umma_commit(hs_free);
             };
             mbar_wait(a1_ready, 0);
-            PE_STAMP(16);
             for (int c = 0; c < NCH; ++c) {
                 mbar_wait(&h_free[c & 1], ((c >> 1) & 1) ^ 1);
                 for (int kb = 0; kb < K1 / 64; ++kb) {
@@ -172,12 +166,10 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
                     release();
                 }
                 umma_commit(&h_full[c & 1]);
-                PE_STAMP(17 + c);
                 if (c > 0) gemm2(c - 1);
             }
             gemm2(NCH - 1);
             umma_commit(o_full);
-            PE_STAMP(25);
         }
     } else {
         // ---------------- producer (features) + epilogues: thread <-> token ----------------
@@ -232,7 +224,6 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
             }
             fence_proxy_async_smem();
             mbar_arrive(a1_ready);
-            if (threadIdx.x == 64) PE_STAMP(1);
         }
         // ---- per-chunk epilogue of GEMM1: bias + ReLU -> bf16 -> shared-memory A operand of GEMM2 ----
         uint8_t* hrow = smem + OFF_HS + (row >> 3) * 1024 + (row & 7) * 128;
@@ -259,7 +250,6 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
             }
             fence_proxy_async_smem();
             mbar_arrive(hs_ready);
-            if (threadIdx.x == 64) PE_STAMP(2 + c);
         }
         // ---- final epilogue: O + b2 (+ residual) -> fp32 tokens, staged through shared memory ----
         // Every MMA has retired, so the A1 / weight-ring area (160 KB) is free: each warp parks its
@@ -267,7 +257,6 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
         // streams them out row by row, so the residual loads and the stores are fully coalesced
         // 512-byte segments instead of 32 scattered 16-byte pieces per instruction.
         mbar_wait(o_full, 0);
-        if (threadIdx.x == 64) PE_STAMP(10);
         tcgen05_fence_after();
         float4* stage = reinterpret_cast<float4*>(smem + OFF_A1) + (size_t)quarter * 32 * 64;     // [32 rows][64 float4]
 #pragma unroll 1
@@ -283,7 +272,6 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
             }
         }
         __syncwarp();
-        if (threadIdx.x == 64) PE_STAMP(11);
         const int64_t t0w = tile0 + quarter * 32;
         int r2 = p.residual2 ? (int)(t0w % p.res2_rows) : 0;       // row of the broadcast residual (one 64-bit mod)
 #pragma unroll 4
@@ -309,7 +297,6 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
                     reinterpret_cast<uint2*>(p.out_bf16 + tt * EOUT)[j] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
             }
         }
-        if (threadIdx.x == 64) PE_STAMP(12);
         tcgen05_fence_before();
     }
     __syncthreads();
@@ -348,7 +335,6 @@ extern "C" int petr_position_mlp_fused(const float* img2lidar, int B, int N, int
     p.b1 = b1; p.b2 = b2; p.residual = residual; p.out = out;
     p.residual2 = residual2; p.res2_rows = res2_rows; p.out_bf16 = (__nv_bfloat16*)out_bf16;
     p.T = (int64_t)B * N * H * W;
-    p.dbg = g_pe_dbg;
     CUtensorMap tmW1, tmW2;
     {
         uint64_t d[2] = {K1, HID}, s[1] = {K1 * 2};
