@@ -698,7 +698,12 @@ constexpr int THREADS = 608;
 
 // Measured on B200 at B = 16 (24 000 keys, 1.03 ms per launch) and rejected:
 //   * warps whose 32 rows lie beyond Lq (900 = 7 x 128 + 4) skipping their exponentials: 1.31-1.36 ms,
-//     with a spinning or a nanosleep-backed wait and with zero-filled P rows alike (cause not found);
+//     with a spinning or a nanosleep-backed wait and with zero-filled P rows alike.  Cause, found in
+//     the SASS afterwards: with an `if (live)` around the exponentials ptxas stops interleaving --
+//     64 FADDs, then a dense MUFU/F2FP block, then the stores -- so the warps of a tile go through
+//     MUFU-free phases together.  The same holds for the two-branch polynomial variants below.  A
+//     form that duplicates the whole tile loop outside the branch keeps the schedule (draft on
+//     branch next/flash-skip-dead, not yet timed);
 //   * 2/16 or 4/16 of the exponentials on the FMA pipe (cubic): 1.25 / 1.28 ms (issue-bound);
 //   * independent half-row streams merged in the epilogue (no per-tile max exchange): 1.06 ms;
 //   * half-tile software pipelining of v2 (TMEM load of the next 64 scores under the current 64
