@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PETR_B200_ABI_VERSION 1
+#define PETR_B200_ABI_VERSION 2
 
 #define PETR_E_BADARG   (-1)   /* null pointer / non-positive dimension */
 #define PETR_E_SHAPE    (-2)   /* unsupported shape (see each function) */
@@ -56,6 +56,13 @@ const char* petr_last_error_string(void);
 /* number of kernels this library has launched on the calling thread since the last reset */
 int64_t petr_launch_count(void);
 void petr_launch_count_reset(void);
+/* Explicit, process-wide tuning switches (A/B measurements and tests; the library reads no
+ * environment variables).  Keys: "flash_exact_only" (0/1: skip the max-free fast pass of
+ * petr_cross_attention_bf16), "flash_poly" (0..3: exponentials per 8 evaluated on the FMA pipes in
+ * the fast pass).  Returns 0, or PETR_E_BADARG for an unknown key / out-of-range value;
+ * petr_get_tuning returns the current value or -1. */
+int petr_set_tuning(const char* key, int value);
+int petr_get_tuning(const char* key);
 
 /* ---- a4: key-padding masks.  petr_head.py:383-394 (ones(pad) / zero img_shape /
  * F.interpolate nearest / .to(bool)).  img_hw: int32 [B*N*2] = (img_h, img_w) per view.
@@ -203,8 +210,8 @@ int petr_position_mlp_fused(const float* img2lidar, int B, int N, int H, int W, 
 int petr_pack_q_bf16(const float* Q, int ldq, void* out, int B, int Lq, int heads, float scale,
                      void* stream);
 
-/* Flash cross-attention on tcgen05 (QK^T -> TMEM, online softmax in registers, P -> bf16,
- * PV -> TMEM), petr_transformer.py:357-362 for one decoder layer.
+/* Flash cross-attention on tcgen05 (QK^T -> TMEM, softmax in registers, P -> bf16, PV -> TMEM),
+ * petr_transformer.py:357-362 for one decoder layer.
  *   Qs : bf16 [B, heads, Lq, 32]  (petr_pack_q_bf16)
  *   Kh : bf16 [B, heads, Lk, 32]  (out_mode 2 of petr_gemm_bf16_tc)
  *   Vh : bf16 [B, heads, Lk, 32]
@@ -214,11 +221,17 @@ int petr_pack_q_bf16(const float* Q, int ldq, void* out, int B, int Lq, int head
  * 2*heads*32, nullable) receive the normalised result (partials of nsplit > 1 are
  * merged internally; `partial` is then the scratch, petr_attention_partial_floats * nsplit).
  * write_partial == 1: only the un-normalised partials (O, m, l) are written to `partial`
- * (layout below) for a later petr_attention_merge -- the key-split-across-GPUs path. */
+ * (layout below) for a later petr_attention_merge -- the key-split-across-GPUs path.
+ * workspace (nullable): petr_cross_attention_workspace_bytes(...) bytes of device scratch.  With
+ * it the call runs a fast "max-free" softmax pass (p = 2^s, no running maximum; valid while every
+ * row sum stays inside [2^-80, 2^100], which the pass verifies per row) followed by the exact
+ * online-softmax pass restricted to the CTAs whose check failed (fully masked rows, extreme
+ * logits); without it only the exact pass runs.  Results are within bf16 rounding either way. */
 int petr_cross_attention_bf16(const void* Qs, const void* Kh, const void* Vh,
                               const uint8_t* key_mask, float* O, int ldo, void* O_split,
-                              float* partial, int B, int Lq, int Lk, int heads, int nsplit,
-                              int write_partial, void* stream);
+                              float* partial, void* workspace, int B, int Lq, int Lk, int heads,
+                              int nsplit, int write_partial, void* stream);
+int64_t petr_cross_attention_workspace_bytes(int B, int Lq, int Lk, int heads, int nsplit);
 
 /* fp32-class attention on tcgen05 (the decoder's self-attention; mmcv MultiheadAttention called by
  * BaseTransformerLayer with q = k = query + query_pos, v = query).  Every operand is a bf16

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpetr_b200.so")
 
 _P, _I, _F = c_void_p, c_int, c_float
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/petr_b200.h one to one
 SIGNATURES = {
@@ -22,6 +23,8 @@ SIGNATURES = {
     "petr_last_error_string": (c_char_p, []),
     "petr_launch_count": (c_int64, []),
     "petr_launch_count_reset": (None, []),
+    "petr_set_tuning": (c_int, [c_char_p, _I]),
+    "petr_get_tuning": (c_int, [c_char_p]),
     "petr_key_padding_mask": (c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "petr_frustum_features": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P,
                                       _P, _I, _P, _P, _P]),
@@ -40,7 +43,8 @@ SIGNATURES = {
     "petr_stage_small": (c_int, [_P, _P, _I, _P]),
     "petr_add_rows_bf16": (c_int, [_P, _P, _I, _P, _I, _I, _P]),
     "petr_pack_q_bf16": (c_int, [_P, _I, _P, _I, _I, _I, _F, _P]),
-    "petr_cross_attention_bf16": (c_int, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "petr_cross_attention_bf16": (c_int, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "petr_cross_attention_workspace_bytes": (c_int64, [_I, _I, _I, _I, _I]),
     "petr_attention_x3_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P]),
     "petr_attention_merge": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
     "petr_attention_partial_floats": (c_int64, [_I, _I, _I]),
@@ -61,7 +65,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.petr_abi_version() != 1:
+        if L.petr_abi_version() != ABI_VERSION:
             raise RuntimeError("libpetr_b200.so ABI version mismatch")
         _lib = L
     return _lib
@@ -104,6 +108,14 @@ def call(name: str, *args):
     check(getattr(lib(), name)(*args), name)
     e1.record()
     TIMERS.setdefault(LABEL or name, []).append((e0, e1))
+
+
+def set_tuning(key: str, value: int):
+    check(lib().petr_set_tuning(key.encode(), int(value)), "petr_set_tuning")
+
+
+def get_tuning(key: str) -> int:
+    return int(lib().petr_get_tuning(key.encode()))
 
 
 def launch_count() -> int:

@@ -1,5 +1,7 @@
 // ABI bookkeeping: version, thread-local error string, launch accounting.
 #include "common.cuh"
+#include <atomic>
+#include <string.h>
 
 namespace petr {
 char* last_error_buf() {
@@ -10,7 +12,39 @@ int64_t& launch_counter() {
     static thread_local int64_t n = 0;
     return n;
 }
+namespace tuning {
+static std::atomic<int> g_flash_exact_only{0};
+static std::atomic<int> g_flash_poly{0};
+static std::atomic<int> g_gemm_staged{1};
+bool flash_exact_only() { return g_flash_exact_only.load(std::memory_order_relaxed) != 0; }
+int flash_poly() { return g_flash_poly.load(std::memory_order_relaxed); }
+bool gemm_staged() { return g_gemm_staged.load(std::memory_order_relaxed) != 0; }
+struct Entry { const char* key; std::atomic<int>* v; int lo, hi; };
+static const Entry kEntries[] = {
+    {"flash_exact_only", &g_flash_exact_only, 0, 1},
+    {"flash_poly", &g_flash_poly, 0, 3},
+    {"gemm_staged", &g_gemm_staged, 0, 1},
+};
+}  // namespace tuning
 }  // namespace petr
+
+extern "C" int petr_set_tuning(const char* key, int value) {
+    if (key)
+        for (const auto& e : petr::tuning::kEntries)
+            if (!strcmp(key, e.key)) {
+                if (value < e.lo || value > e.hi)
+                    return petr::fail(PETR_E_BADARG, "petr_set_tuning: %s must be in [%d, %d]", key, e.lo, e.hi);
+                e.v->store(value);
+                return 0;
+            }
+    return petr::fail(PETR_E_BADARG, "petr_set_tuning: unknown key %s", key ? key : "(null)");
+}
+extern "C" int petr_get_tuning(const char* key) {
+    if (key)
+        for (const auto& e : petr::tuning::kEntries)
+            if (!strcmp(key, e.key)) return e.v->load();
+    return -1;
+}
 
 extern "C" int petr_abi_version(void) { return PETR_B200_ABI_VERSION; }
 extern "C" const char* petr_last_error_string(void) { return petr::last_error_buf(); }

@@ -29,6 +29,13 @@ inline int after_launch(const char* what) {
     return 0;
 }
 
+// process-wide tuning switches behind petr_set_tuning (capi.cu)
+namespace tuning {
+bool flash_exact_only();
+int flash_poly();
+bool gemm_staged();
+}  // namespace tuning
+
 #define PETR_REQUIRE(cond, code, ...) \
     do { if (!(cond)) return ::petr::fail((code), __VA_ARGS__); } while (0)
 

@@ -16,7 +16,6 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <math.h>
-#include <stdlib.h>
 
 namespace petr {
 namespace {
@@ -67,6 +66,7 @@ struct AttParams {
     float* O; int ldo;         // normalised output (nsplit == 1), nullable
     __nv_bfloat16* O_split;    // bf16 [hi | lo] rows of width 2*heads*32, nullable
     float* partial;            // [nsplit][rows*32 O | rows*2 (m,l)], rows = B*heads*Lq
+    int* flags;                // [grid CTAs] fast pass -> exact pass (cross-attention), nullable
     int B, Lq, Lk, heads, nsplit, tiles_total, write_partial;
 };
 
@@ -399,318 +399,61 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
 }  // namespace x3
 
 // ------------------------------------------------------------------------------------------
-// v2: two 128-query tiles (A, B) of one (batch, head) per CTA share every K/V tile.  Warps 2-5 are
-// the softmax group of tile A, warps 6-9 of tile B (thread r of a group owns query row r), so two
-// warps share each SM sub-partition and one group's exp2 work hides the other's TMEM / barrier
-// latency.  The softmax denominator comes from the tensor core: P is also multiplied by an
-// all-ones [keys x 16] operand, so l = sum_k bf16(p_k) is exactly consistent with the P V
-// numerator and costs no CUDA-core adds.  Row maxima use 3-input FMNMX on four independent chains.
+// bf16 flash cross-attention (queries -> N*H*W image tokens), PETRMultiheadAttention's core
+// (petr_transformer.py:341-362).  Two 128-query tiles (A, B) of one (batch, head) per CTA, 19 warps:
+//   warp 0 TMA (K/V through a 4-stage mbarrier ring), warp 1 / 18 single-thread tcgen05.mma issuers of
+//   tile A / B, warps 2-9 / 10-17 softmax of tile A / B: TWO threads per query row (64 keys each), so
+//   each SM sub-partition always has four warps' exponentials to feed the MUFU pipe (16 ex2/clk/SM is
+//   the binding unit at head_dim 32, not the tensor pipe).
+// P (bf16, UMMA K-major 128B-swizzled) is double buffered in shared memory; the softmax denominator
+// comes from the tensor core as well (P x all-ones operand), split-KV partials + merge for small B.
+//
+// Two instantiations share the body:
+//   FAST  -- "max-free" softmax: p = 2^s with NO running row maximum.  Scores live in the exp2
+//            domain (Q pre-scaled by head_dim^-1/2 * log2 e) and every accumulator is fp32, whose
+//            exponent range makes a shift by the row maximum unnecessary as long as the row sum l stays
+//            inside [2^-80, 2^100] -- true for any sane attention logits (|q.k|/sqrt(d) < ~55).  It
+//            saves the per-element subtraction, the 3-input max tree, the half-row max exchange
+//            (a 256-thread named barrier per key tile) and all O/L rescaling: ~1.7 instead of ~3.5
+//            issued instructions per score element.  The epilogue VERIFIES the assumption per row; a
+//            CTA with a row outside the range (or a fully masked row, l = 0) raises flags[cta].
+//   !FAST -- the exact online softmax (running maximum, lazy rescale threshold 2^8, O rescaled in
+//            TMEM).  Launched right behind the FAST kernel on the same grid; CTAs whose flag is clear
+//            exit at once, flagged ones recompute and overwrite their rows.  No host round trip.
+// Softmax warps whose 32 query rows all lie beyond Lq (900 = 7 x 128 + 4: six of the eight tile-B
+// warps of every fourth CTA) exit before the key loop; the mbarrier / named-barrier arrival counts
+// are derived from the live warp count, so live warps never wait for them (12 % of all exponentials).
+// POLY of every 8 exponentials are evaluated on the FMA/ALU pipes (cubic minimax) instead of MUFU.
 // ------------------------------------------------------------------------------------------
-namespace v2 {
+namespace v4 {
 constexpr int NQT = 2;
 constexpr int OFF_Q = 0;                                            // 2 x 8 KB
 constexpr int OFF_KV = OFF_Q + NQT * Q_BYTES;                       // 4 x 16 KB
 constexpr int OFF_P = OFF_KV + KV_STAGES * (K_BYTES + V_BYTES);     // P[x][buf]: 2 x 2 x 32 KB
 constexpr int OFF_ONES = OFF_P + NQT * 2 * P_BYTES;                 // 4 KB of bf16 1.0
 constexpr int OFF_BIAS = OFF_ONES + 4096;                           // 2 x 128 floats
-constexpr int OFF_BAR = OFF_BIAS + NQT * KT * 4;
-constexpr int SMEM = OFF_BAR + 256 + 1024;
-constexpr int THREADS = 352;        // TMA, MMA-A, 2x4 softmax, MMA-B
-constexpr int TM_S = 0;          // S_x at TM_S + 128 x
-constexpr int TM_O = 256;        // O_x at TM_O + 48 x (32 cols), L_x right behind it (16 cols)
-
-// kPoly of every 16 score elements take ex2_poly instead of MUFU ex2.
-template <int kPoly>
-__device__ __forceinline__ float ex2_sel(float x, int i) {
-    // spread the polynomial lanes evenly over each group of 16
-    const bool poly = ((i & 15) * kPoly) / 16 != (((i & 15) + 1) * kPoly) / 16;
-    return poly ? ex2_poly(x) : ex2(x);
-}
-
-template <int kPoly, bool kStagger>
-__global__ void __launch_bounds__(THREADS, 1)
-cross_attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                           const __grid_constant__ CUtensorMap tmV, AttParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* q_full = bars;                        // 1
-    uint64_t* kv_full = bars + 1;                   // KV_STAGES
-    uint64_t* kv_empty = kv_full + KV_STAGES;       // KV_STAGES
-    uint64_t* s_full = kv_empty + KV_STAGES;        // 2 (A, B)
-    uint64_t* s_free = s_full + 2;
-    uint64_t* p_ready = s_free + 2;                 // [x][buf], index 2x + buf
-    uint64_t* pv_done = p_ready + 4;                // [x][buf]
-    uint64_t* half_a = pv_done + 4;                 // tile A is half way through its first key tile
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(half_a + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * (NQT * QT);
-    const int bh = blockIdx.y;
-    const int split = blockIdx.z;
-    const int b = bh / p.heads, h = bh - b * p.heads;
-    const int per = (p.tiles_total + p.nsplit - 1) / p.nsplit;
-    const int t_begin = split * per;
-    const int t_end = min(p.tiles_total, t_begin + per);
-    const int ntiles = max(0, t_end - t_begin);
-
-    // all-ones B operand for the row-sum MMA (layout irrelevant: every element is 1.0)
-    for (int i = threadIdx.x; i < 4096 / 4; i += THREADS)
-        reinterpret_cast<uint32_t*>(smem + OFF_ONES)[i] = 0x3F803F80u;
-    fence_proxy_async_smem();
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    }
-    if (warp == 1) {
-        if (lane == 0) {
-            mbar_init(q_full, 1);
-            for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 128); }
-            for (int i = 0; i < 4; ++i) { mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1); }
-            mbar_init(half_a, 128);
-            fence_barrier_init();
-        }
-        __syncwarp();
-        tmem_alloc(tmem_slot, TMEM_COLS);
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ---------------- TMA producer ----------------
-        if (lane == 0 && ntiles > 0) {
-            mbar_arrive_expect_tx(q_full, NQT * Q_BYTES);
-            tma_load_3d(smem + OFF_Q, &tmQ, q_full, 0, q0, bh);
-            tma_load_3d(smem + OFF_Q + Q_BYTES, &tmQ, q_full, 0, q0 + QT, bh);
-            for (int j = 0; j < ntiles; ++j) {
-                const int s = j % KV_STAGES;
-                mbar_wait(&kv_empty[s], ((j / KV_STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
-                uint8_t* kd = smem + OFF_KV + s * (K_BYTES + V_BYTES);
-                const int key0 = (t_begin + j) * KT;
-                tma_load_3d(kd, &tmK, &kv_full[s], 0, key0, bh);
-                tma_load_3d(kd + K_BYTES, &tmV, &kv_full[s], 0, key0, bh);
-            }
-        }
-    } else if (warp == 1 || warp == 10) {
-        // ---------------- MMA issuers: warp 1 drives query tile A, warp 10 tile B ----------------
-        // (a single issuing thread for both tiles was the critical path: 36 tcgen05.mma + their
-        // descriptor arithmetic per key tile).  All descriptors that do not depend on the K/V stage
-        // are built once; per-stage ones are one 64-bit add.
-        if (lane == 0 && ntiles > 0) {
-            const int x = (warp == 1) ? 0 : 1;
-            constexpr uint32_t idesc_qk = make_idesc(QT, KT, 1, 0, 0);     // S[128x128] = Q K^T
-            constexpr uint32_t idesc_pv = make_idesc(QT, HD, 1, 0, 1);     // O[128x32] += P V (V MN-major)
-            constexpr uint32_t idesc_l = make_idesc(QT, 16, 1, 0, 0);      // L[128x16] += P 1
-            const uint32_t q_addr = smem_u32(smem + OFF_Q + x * Q_BYTES);
-            const uint32_t p_addr = smem_u32(smem + OFF_P + x * 2 * P_BYTES);      // buffer 0; buffer 1 is P_BYTES further
-            const uint32_t ones_addr = smem_u32(smem + OFF_ONES);
-            const uint32_t kv_addr = smem_u32(smem + OFF_KV);
-            const uint64_t q_desc0 = make_smem_desc(q_addr, 16, 512, LAYOUT_SW64);
-            const uint64_t k_desc0 = make_smem_desc(kv_addr, 16, 512, LAYOUT_SW64);
-            const uint64_t v_desc0 = make_smem_desc(kv_addr + K_BYTES, 512, 512, LAYOUT_SW64);
-            uint64_t p_desc[KT / 16], o_desc[KT / 16];
-#pragma unroll
-            for (int kk = 0; kk < KT / 16; ++kk) {
-                p_desc[kk] = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
-                o_desc[kk] = make_smem_desc(ones_addr + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
-            }
-            const uint32_t d_s = tmem_base + TM_S + x * 128;
-            const uint32_t d_o = tmem_base + TM_O + x * 48, d_l = d_o + 32;
-            auto issue_pv = [&](int t) {
-                const int s = t % KV_STAGES;
-                const uint64_t vd = v_desc0 + (uint64_t)((s * (K_BYTES + V_BYTES)) >> 4);
-                const uint64_t pb = (uint64_t)(((t & 1) * P_BYTES) >> 4);            // P buffer of tile t
-                mbar_wait(&p_ready[2 * x + (t & 1)], (t >> 1) & 1);
-                tcgen05_fence_after();
-#pragma unroll
-                for (int kk = 0; kk < KT / 16; ++kk) {
-                    umma_f16_ss(d_o, p_desc[kk] + pb, vd + (uint64_t)((kk * 1024) >> 4), idesc_pv, (t | kk) ? 1u : 0u);
-                    umma_f16_ss(d_l, p_desc[kk] + pb, o_desc[kk], idesc_l, (t | kk) ? 1u : 0u);
-                }
-                umma_commit(&pv_done[2 * x + (t & 1)]);
-                umma_commit(&kv_empty[s]);                   // count 2: both tiles done with this stage
-            };
-            mbar_wait(q_full, 0);
-            // Stagger the two tiles by half a key tile: the A and B softmax warps that share an SM
-            // sub-partition then alternate between their exp2 phase (MUFU) and their TMEM-load / max /
-            // P-store phase instead of running them in lockstep.
-            if (kStagger && x == 1) mbar_wait(half_a, 0);
-            for (int j = 0; j < ntiles; ++j) {
-                const int s = j % KV_STAGES;
-                const uint64_t kd = k_desc0 + (uint64_t)((s * (K_BYTES + V_BYTES)) >> 4);
-                mbar_wait(&kv_full[s], (j / KV_STAGES) & 1);
-                mbar_wait(&s_free[x], (j & 1) ^ 1);
-                tcgen05_fence_after();
-#pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    umma_f16_ss(d_s, q_desc0 + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_qk, k ? 1u : 0u);
-                umma_commit(&s_full[x]);
-                if (j > 0) issue_pv(j - 1);
-            }
-            issue_pv(ntiles - 1);
-        }
-    } else {
-        // ---------------- softmax / correction / epilogue ----------------
-        const int x = (warp - 2) >> 2;                       // 0: tile A (warps 2-5), 1: tile B (warps 6-9)
-        const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;
-        const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-        const uint32_t s_addr = tmem_base + lane_off + TM_S + x * 128;
-        const uint32_t o_addr = tmem_base + lane_off + TM_O + x * 48;
-        float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS) + x * KT;
-        uint8_t* pbase = smem + OFF_P + x * 2 * P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
-        float m_use = -INFINITY;
-        const bool use_mask = (p.key_mask != nullptr);
-        for (int j = 0; j < ntiles; ++j) {
-            const uint32_t par = j & 1;
-            const int key0 = (t_begin + j) * KT;
-            const bool need_bias = use_mask || (key0 + KT > p.Lk);
-            if (need_bias) {
-                const int key = key0 + row;
-                bool dead = key >= p.Lk;
-                if (!dead && use_mask) dead = p.key_mask[(int64_t)b * p.Lk + key] != 0;
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");   // previous tile's readers done
-                sbias[row] = dead ? -INFINITY : 0.f;
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
-            }
-            mbar_wait(&s_full[x], par);
-            tcgen05_fence_after();
-            uint32_t sr[128];
-            tmem_ld_x32(s_addr, sr);
-            tmem_ld_x32(s_addr + 32, sr + 32);
-            tmem_ld_x32(s_addr + 64, sr + 64);
-            tmem_ld_x32(s_addr + 96, sr + 96);
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            mbar_arrive(&s_free[x]);
-            float* sv = reinterpret_cast<float*>(sr);
-            if (need_bias) {
-#pragma unroll
-                for (int i = 0; i < 128; ++i) sv[i] += sbias[i];
-            }
-            float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
-#pragma unroll
-            for (int i = 4; i < 128; i += 8) {
-                mx0 = max3(mx0, sv[i], sv[i + 1]); mx1 = max3(mx1, sv[i + 2], sv[i + 3]);
-                if (i + 4 < 128) { mx2 = max3(mx2, sv[i + 4], sv[i + 5]); mx3 = max3(mx3, sv[i + 6], sv[i + 7]); }
-            }
-            const float mx = fmaxf(max3(mx0, mx1, mx2), mx3);
-            const bool grow = mx > m_use + RESCALE_TH;
-            float alpha = 1.f;
-            if (grow) { alpha = ex2(m_use - mx); m_use = mx; }
-            const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
-            uint32_t pk[64];
-            if (kStagger && x == 0 && j == 0) {
-                // first half of tile 0's exponentials, then release tile B (see the MMA-B warp)
-#pragma unroll
-                for (int i = 0; i < 64; i += 2)
-                    pk[i >> 1] = pack_bf16x2(ex2(sv[i] - m_eff), ex2(sv[i + 1] - m_eff));
-                mbar_arrive(half_a);
-#pragma unroll
-                for (int i = 64; i < 128; i += 2)
-                    pk[i >> 1] = pack_bf16x2(ex2(sv[i] - m_eff), ex2(sv[i + 1] - m_eff));
-            } else if (kPoly > 0 && !need_bias) {
-                // all scores finite: a share of the exponentials goes to the FMA pipe
-#pragma unroll
-                for (int i = 0; i < 128; i += 2)
-                    pk[i >> 1] = pack_bf16x2(ex2_sel<kPoly>(sv[i] - m_eff, i), ex2_sel<kPoly>(sv[i + 1] - m_eff, i + 1));
-            } else {
-                // masked / tail tiles carry -inf scores: MUFU ex2 returns the exact zeros that make
-                // fully masked rows NaN like the reference
-#pragma unroll
-                for (int i = 0; i < 128; i += 2)
-                    pk[i >> 1] = pack_bf16x2(ex2(sv[i] - m_eff), ex2(sv[i + 1] - m_eff));
-            }
-            // P is double buffered: buffer j&1 is free once PV_x(j-2) has retired, so the softmax
-            // warps never wait for their own previous P V product
-            mbar_wait(&pv_done[2 * x + par], ((j >> 1) & 1) ^ 1);
-            uint8_t* pb = pbase + par * P_BYTES;
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                uint8_t* dst = pb + (c >> 3) * 16384 + (((c & 7) ^ (row & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-            }
-            if (j > 0 && __any_sync(0xffffffffu, grow)) {        // correction: (O, L) *= alpha after PV_x(j-1)
-                mbar_wait(&pv_done[2 * x + (par ^ 1)], ((j - 1) >> 1) & 1);
-                tcgen05_fence_after();
-                uint32_t orr[48];
-                tmem_ld_x32(o_addr, orr);
-                tmem_ld_x16(o_addr + 32, orr + 32);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 48; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
-                tmem_st_x32(o_addr, orr);
-                tmem_st_x16(o_addr + 32, orr + 32);
-                tmem_st_wait();
-            }
-            fence_proxy_async_smem();
-            tcgen05_fence_before();
-            mbar_arrive(&p_ready[2 * x + par]);
-        }
-        // ---------------- epilogue ----------------
-        const int q = q0 + x * QT + row;
-        float o[32], l = 0.f;
-        if (ntiles > 0) {
-            mbar_wait(&pv_done[2 * x + ((ntiles - 1) & 1)], ((ntiles - 1) >> 1) & 1);
-            tcgen05_fence_after();
-            uint32_t orr[48];
-            tmem_ld_x32(o_addr, orr);
-            tmem_ld_x16(o_addr + 32, orr + 32);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(orr[i]);
-            l = __uint_as_float(orr[32]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = 0.f;
-        }
-        if (q < p.Lq) write_attention_row(p, o, m_use, l, b, h, bh, q, split);
-        tcgen05_fence_before();
-    }
-    __syncthreads();
-    if (warp == 1) {
-        __syncwarp();
-        tcgen05_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-}
-}  // namespace v2
-
-// ------------------------------------------------------------------------------------------
-// v3: same pipeline as v2, but every query row is shared by TWO softmax threads (64 keys each):
-// 16 softmax warps per CTA = 4 per SM sub-partition instead of 2, so the MUFU pipe (the measured
-// limiter of v2: XU 72 % busy) always has another warp's exponentials to issue while one waits on
-// TMEM, a barrier or its P stores.  The two halves of a row exchange their partial maxima through
-// shared memory (one named barrier per key tile, double buffered by tile parity); the lazy-rescale
-// correction is split as well (half 0 rescales O, half 1 the ones-trick row sum L).
-// Warps: 0 TMA, 1 MMA-A, 2-9 softmax A, 10-17 softmax B, 18 MMA-B.
-// ------------------------------------------------------------------------------------------
-namespace v3 {
-using v2::NQT; using v2::OFF_Q; using v2::OFF_KV; using v2::OFF_P; using v2::OFF_ONES; using v2::OFF_BIAS;
-using v2::TM_S; using v2::TM_O;
-constexpr int OFF_MAX = v2::OFF_BAR;                    // [x][parity][half][128] floats = 4 KB
+constexpr int OFF_MAX = OFF_BIAS + NQT * KT * 4;                    // [x][parity][half][128] floats = 4 KB
 constexpr int OFF_BAR = OFF_MAX + NQT * 2 * 2 * QT * 4;
 constexpr int SMEM = OFF_BAR + 256 + 1024;
 constexpr int THREADS = 608;
+constexpr int TM_S = 0;          // S_x at TM_S + 128 x
+constexpr int TM_O = 256;        // O_x at TM_O + 48 x (32 cols), L_x right behind it (16 cols)
+constexpr float L_MIN = 8.3e-25f;   // 2^-80
+constexpr float L_MAX = 1.2e30f;    // ~2^100
 
-// Measured on B200 at B = 16 (24 000 keys, 1.03 ms per launch) and rejected:
-//   * warps whose 32 rows lie beyond Lq (900 = 7 x 128 + 4) skipping their exponentials: 1.31-1.36 ms,
-//     with a spinning or a nanosleep-backed wait and with zero-filled P rows alike.  Cause, found in
-//     the SASS afterwards: with an `if (live)` around the exponentials ptxas stops interleaving --
-//     64 FADDs, then a dense MUFU/F2FP block, then the stores -- so the warps of a tile go through
-//     MUFU-free phases together.  The same holds for the two-branch polynomial variants below.  A
-//     form that duplicates the whole tile loop outside the branch keeps the schedule (draft on
-//     branch next/flash-skip-dead, not yet timed);
-//   * 2/16 or 4/16 of the exponentials on the FMA pipe (cubic): 1.25 / 1.28 ms (issue-bound);
-//   * independent half-row streams merged in the epilogue (no per-tile max exchange): 1.06 ms;
-//   * half-tile software pipelining of v2 (TMEM load of the next 64 scores under the current 64
-//     exponentials, one thread per row): 1.48 ms.
+// POLY of every 8 score elements take ex2_poly (FMA/ALU pipes) instead of MUFU ex2, spread evenly.
+template <int POLY>
+__device__ __forceinline__ float ex2_sel(float x, int i) {
+    const bool poly = ((i & 7) * POLY) / 8 != (((i & 7) + 1) * POLY) / 8;
+    return poly ? ex2_poly(x) : ex2(x);
+}
+
+template <bool FAST, int POLY>
 __global__ void __launch_bounds__(THREADS, 1)
-cross_attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                            const __grid_constant__ CUtensorMap tmV, AttParams p) {
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (!FAST && p.flags && p.flags[cta] == 0) return;      // exact pass: only CTAs the fast pass flagged
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -732,19 +475,24 @@ cross_attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const int t_begin = split * per;
     const int t_end = min(p.tiles_total, t_begin + per);
     const int ntiles = max(0, t_end - t_begin);
+    // live 32-row quarters of tile A / B (a prefix 0..k-1 of the four quarters)
+    const int lq0 = min(4, max(0, (p.Lq - q0 + 31) >> 5));
+    const int lq1 = min(4, max(0, (p.Lq - q0 - QT + 31) >> 5));
+    const int live_tiles = (lq0 > 0) + (lq1 > 0);
 
     for (int i = threadIdx.x; i < 4096 / 4; i += THREADS)
         reinterpret_cast<uint32_t*>(smem + OFF_ONES)[i] = 0x3F803F80u;
     fence_proxy_async_smem();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+        if (FAST && p.flags) p.flags[cta] = 0;
     }
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(q_full, 1);
-            for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 256); }
-            for (int i = 0; i < 4; ++i) { mbar_init(&p_ready[i], 256); mbar_init(&pv_done[i], 1); }
+            for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], live_tiles); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 64 * (i ? lq1 : lq0)); }
+            for (int i = 0; i < 4; ++i) { mbar_init(&p_ready[i], 64 * ((i >> 1) ? lq1 : lq0)); mbar_init(&pv_done[i], 1); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -773,8 +521,8 @@ cross_attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         }
     } else if (warp == 1 || warp == 18) {
         // ---------------- MMA issuers: warp 1 drives query tile A, warp 18 tile B ----------------
-        if (lane == 0 && ntiles > 0) {
-            const int x = (warp == 1) ? 0 : 1;
+        const int x = (warp == 1) ? 0 : 1;
+        if (lane == 0 && ntiles > 0 && (x ? lq1 : lq0) > 0) {
             constexpr uint32_t idesc_qk = make_idesc(QT, KT, 1, 0, 0);     // S[128x128] = Q K^T
             constexpr uint32_t idesc_pv = make_idesc(QT, HD, 1, 0, 1);     // O[128x32] += P V (V MN-major)
             constexpr uint32_t idesc_l = make_idesc(QT, 16, 1, 0, 0);      // L[128x16] += P 1
@@ -828,28 +576,32 @@ cross_attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         const int x = g >> 3;                                // 0: tile A (warps 2-9), 1: tile B (warps 10-17)
         const int hf = (g >> 2) & 1;                         // which 64 keys of the tile this thread owns
         const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
+        const int lq = x ? lq1 : lq0;
+        if (quarter < lq) {                                  // else: all 32 rows beyond Lq -- nothing to do
+        const int nlive = 64 * lq;                           // live softmax threads of this tile
         const int row = quarter * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
         const uint32_t s_addr = tmem_base + lane_off + TM_S + x * 128 + hf * 64;
         const uint32_t o_addr = tmem_base + lane_off + TM_O + x * 48;
         float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS) + x * KT;
         float* smax = reinterpret_cast<float*>(smem + OFF_MAX) + x * (4 * QT);
-        uint8_t* pbase = smem + OFF_P + x * 2 * P_BYTES + hf * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
-        float m_use = -INFINITY;
+        const uint32_t pbase = smem_u32(smem + OFF_P + x * 2 * P_BYTES + hf * 16384 + (row >> 3) * 1024 + (row & 7) * 128);
+        const uint32_t sbias_u32 = smem_u32(sbias + hf * 64);
+        float m_use = FAST ? 0.f : -INFINITY;
         const bool use_mask = (p.key_mask != nullptr);
         for (int j = 0; j < ntiles; ++j) {
             const uint32_t par = j & 1;
             const int key0 = (t_begin + j) * KT;
             const bool need_bias = use_mask || (key0 + KT > p.Lk);
             if (need_bias) {
-                asm volatile("bar.sync %0, 256;" ::"r"(1 + x) : "memory");   // previous tile's readers done
-                if (hf == 0) {
-                    const int key = key0 + row;
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + x), "r"(nlive) : "memory");   // previous tile's readers done
+                for (int i = (hf * lq + quarter) * 32 + lane; i < KT; i += nlive) {
+                    const int key = key0 + i;
                     bool dead = key >= p.Lk;
                     if (!dead && use_mask) dead = p.key_mask[(int64_t)b * p.Lk + key] != 0;
-                    sbias[row] = dead ? -INFINITY : 0.f;
+                    sbias[i] = dead ? -INFINITY : 0.f;
                 }
-                asm volatile("bar.sync %0, 256;" ::"r"(1 + x) : "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + x), "r"(nlive) : "memory");
             }
             mbar_wait(&s_full[x], par);
             tcgen05_fence_after();
@@ -862,34 +614,42 @@ cross_attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
             float* sv = reinterpret_cast<float*>(sr);
             if (need_bias) {
 #pragma unroll
-                for (int i = 0; i < 64; ++i) sv[i] += sbias[hf * 64 + i];
+                for (int i = 0; i < 64; i += 4) {
+                    const float4 t = ld_shared_f32x4(sbias_u32 + i * 4);
+                    sv[i] += t.x; sv[i + 1] += t.y; sv[i + 2] += t.z; sv[i + 3] += t.w;
+                }
             }
-            float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
-#pragma unroll
-            for (int i = 4; i < 64; i += 8) {
-                mx0 = max3(mx0, sv[i], sv[i + 1]); mx1 = max3(mx1, sv[i + 2], sv[i + 3]);
-                if (i + 4 < 64) { mx2 = max3(mx2, sv[i + 4], sv[i + 5]); mx3 = max3(mx3, sv[i + 6], sv[i + 7]); }
-            }
-            float mx = fmaxf(max3(mx0, mx1, mx2), mx3);
-            smax[(par * 2 + hf) * QT + row] = mx;
-            asm volatile("bar.sync %0, 256;" ::"r"(3 + x) : "memory");
-            mx = fmaxf(mx, smax[(par * 2 + (hf ^ 1)) * QT + row]);
-            const bool grow = mx > m_use + RESCALE_TH;
-            float alpha = 1.f;
-            if (grow) { alpha = ex2(m_use - mx); m_use = mx; }
-            const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
             uint32_t pk[32];
+            float alpha = 1.f;
+            bool grow = false;
+            if (FAST) {
 #pragma unroll
-            for (int i = 0; i < 64; i += 2)
-                pk[i >> 1] = pack_bf16x2(ex2(sv[i] - m_eff), ex2(sv[i + 1] - m_eff));
-            mbar_wait(&pv_done[2 * x + par], ((j >> 1) & 1) ^ 1);          // P buffer j&1 free (PV(j-2) retired)
-            uint8_t* pb = pbase + par * P_BYTES;
+                for (int i = 0; i < 64; i += 2)
+                    pk[i >> 1] = pack_bf16x2(ex2_sel<POLY>(sv[i], i), ex2_sel<POLY>(sv[i + 1], i + 1));
+            } else {
+                float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint8_t* dst = pb + ((c ^ (row & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                for (int i = 4; i < 64; i += 8) {
+                    mx0 = max3(mx0, sv[i], sv[i + 1]); mx1 = max3(mx1, sv[i + 2], sv[i + 3]);
+                    if (i + 4 < 64) { mx2 = max3(mx2, sv[i + 4], sv[i + 5]); mx3 = max3(mx3, sv[i + 6], sv[i + 7]); }
+                }
+                float mx = fmaxf(max3(mx0, mx1, mx2), mx3);
+                smax[(par * 2 + hf) * QT + row] = mx;
+                asm volatile("bar.sync %0, %1;" ::"r"(3 + x), "r"(nlive) : "memory");
+                mx = fmaxf(mx, smax[(par * 2 + (hf ^ 1)) * QT + row]);
+                grow = mx > m_use + RESCALE_TH;
+                if (grow) { alpha = ex2(m_use - mx); m_use = mx; }
+                const float m_eff = (m_use == -INFINITY) ? 0.f : m_use;
+#pragma unroll
+                for (int i = 0; i < 64; i += 2)
+                    pk[i >> 1] = pack_bf16x2(ex2(sv[i] - m_eff), ex2(sv[i + 1] - m_eff));
             }
-            if (j > 0 && __any_sync(0xffffffffu, grow)) {        // correction after PV_x(j-1): half 0 -> O, half 1 -> L
+            mbar_wait(&pv_done[2 * x + par], ((j >> 1) & 1) ^ 1);          // P buffer j&1 free (PV(j-2) retired)
+            const uint32_t pb = pbase + par * P_BYTES;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                st_shared_v4(pb + ((c ^ (row & 7)) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            if (!FAST && j > 0 && __any_sync(0xffffffffu, grow)) {   // correction after PV_x(j-1): half 0 -> O, half 1 -> L
                 mbar_wait(&pv_done[2 * x + (par ^ 1)], ((j - 1) >> 1) & 1);
                 tcgen05_fence_after();
                 if (hf == 0) {
@@ -930,10 +690,17 @@ cross_attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) o[i] = 0.f;
+                if (FAST) m_use = -INFINITY;                  // empty split: neutral element of the merge
+            }
+            if (FAST && p.flags) {
+                // the max-free assumption, verified: l inside the fp32-safe window (NaN fails both tests)
+                const bool bad = q < p.Lq && ntiles > 0 && !(l > L_MIN && l < L_MAX);
+                if (__any_sync(0xffffffffu, bad) && lane == 0) p.flags[cta] = 1;
             }
             if (q < p.Lq) write_attention_row(p, o, m_use, l, b, h, bh, q, split);
         }
         tcgen05_fence_before();
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -942,7 +709,9 @@ cross_attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
-}  // namespace v3
+}  // namespace v4
+
+
 
 // merge partial (O, m, l) over parts; thread per (row, 4 dims)
 __global__ void attention_merge_kernel(const float* __restrict__ part, int nparts, float* __restrict__ O,
@@ -1007,6 +776,14 @@ extern "C" int64_t petr_attention_partial_floats(int B, int Lq, int heads) {
     return (int64_t)B * heads * Lq * 34;
 }
 
+// one int32 flag per CTA of the cross-attention grid (fast pass -> exact pass hand-over)
+extern "C" int64_t petr_cross_attention_workspace_bytes(int B, int Lq, int Lk, int heads, int nsplit) {
+    if (B <= 0 || Lq <= 0 || Lk <= 0 || heads <= 0 || nsplit <= 0) return 0;
+    const int tiles = (Lk + KT - 1) / KT;
+    if (nsplit > tiles) nsplit = tiles;
+    return (int64_t)((Lq + 2 * QT - 1) / (2 * QT)) * B * heads * nsplit * (int64_t)sizeof(int);
+}
+
 extern "C" int petr_pack_q_bf16(const float* Q, int ldq, void* out, int B, int Lq, int heads,
                                 float scale, void* stream) {
     PETR_REQUIRE(Q && out, PETR_E_BADARG, "petr_pack_q_bf16: null pointer");
@@ -1019,8 +796,8 @@ extern "C" int petr_pack_q_bf16(const float* Q, int ldq, void* out, int B, int L
 
 extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const void* Vh,
                                          const uint8_t* key_mask, float* O, int ldo, void* O_split,
-                                         float* partial, int B, int Lq, int Lk, int heads, int nsplit,
-                                         int write_partial, void* stream) {
+                                         float* partial, void* workspace, int B, int Lq, int Lk, int heads,
+                                         int nsplit, int write_partial, void* stream) {
     PETR_REQUIRE(Qs && Kh && Vh, PETR_E_BADARG, "petr_cross_attention_bf16: null pointer");
     PETR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0 && nsplit > 0, PETR_E_BADARG,
                  "petr_cross_attention_bf16: bad dimension");
@@ -1053,22 +830,20 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
         rc = tmap::encode(&tmV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Vh, d, s, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
     }
-    // share of exponentials evaluated on the FMA pipe (x/16).  Measured on B200 (B = 16, 24 000 keys):
-    // 0/16 -> 1.30 ms, 4/16 -> 1.42 ms, 8/16 -> 1.56 ms per launch: the softmax warps are issue-bound, not
-    // MUFU-bound, so the default is 0; PETR_FLASH_POLY overrides for experiments (masked rows then
-    // lose the exact-zero probabilities that make fully masked samples NaN).
-    static const int poly = getenv("PETR_FLASH_POLY") ? atoi(getenv("PETR_FLASH_POLY")) : 0;
-    static const bool stagger = getenv("PETR_FLASH_STAGGER") != nullptr;   // measured slower (1.23 vs 1.11 ms): off
-    auto kern = poly <= 0 ? (stagger ? v2::cross_attention_tc2_kernel<0, true> : v2::cross_attention_tc2_kernel<0, false>)
-              : poly <= 3 ? v2::cross_attention_tc2_kernel<3, true>
-              : poly == 4 ? v2::cross_attention_tc2_kernel<4, true>
-              : v2::cross_attention_tc2_kernel<6, true>;
-    // PETR_FLASH_V3=0 selects the older v2 kernel (one thread per row) for A/B measurements
-    static const bool use_v3 = getenv("PETR_FLASH_V3") ? atoi(getenv("PETR_FLASH_V3")) != 0 : true;
+    // fast (max-free) pass + exact pass over the CTAs it flagged; without a workspace, or with
+    // petr_set_tuning("flash_exact_only", 1), the exact online-softmax kernel alone
+    const bool fast = workspace != nullptr && !tuning::flash_exact_only();
     typedef void (*flash_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, AttParams);
-    flash_fn fn = kern; int fn_threads = v2::THREADS, smem_bytes = v2::SMEM;
-    if (use_v3) { fn = v3::cross_attention_tc3_kernel; fn_threads = v3::THREADS; smem_bytes = v3::SMEM; }
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    const flash_fn exact_fn = v4::cross_attention_tc4_kernel<false, 0>;
+    flash_fn fast_fn;
+    switch (tuning::flash_poly()) {
+        case 1: fast_fn = v4::cross_attention_tc4_kernel<true, 1>; break;
+        case 2: fast_fn = v4::cross_attention_tc4_kernel<true, 2>; break;
+        case 3: fast_fn = v4::cross_attention_tc4_kernel<true, 3>; break;
+        default: fast_fn = v4::cross_attention_tc4_kernel<true, 0>; break;
+    }
+    cudaError_t e = cudaFuncSetAttribute(exact_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v4::SMEM);
+    if (e == cudaSuccess && fast) e = cudaFuncSetAttribute(fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v4::SMEM);
     if (e != cudaSuccess) return fail((int)e, "petr_cross_attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     AttParams p{};
     p.key_mask = key_mask; p.O = O; p.ldo = ldo; p.O_split = (__nv_bfloat16*)O_split;
@@ -1076,9 +851,16 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
     p.partial = partial;
     p.B = B; p.Lq = Lq; p.Lk = Lk; p.heads = heads; p.nsplit = nsplit; p.tiles_total = tiles;
     p.write_partial = part ? 1 : 0;
+    p.flags = fast ? (int*)workspace : nullptr;
     dim3 grid((Lq + 2 * QT - 1) / (2 * QT), B * heads, nsplit);
-    fn<<<grid, fn_threads, smem_bytes, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
-    int rc = after_launch("petr_cross_attention_bf16");
+    int rc = 0;
+    if (fast) {
+        fast_fn<<<grid, v4::THREADS, v4::SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+        rc = after_launch("petr_cross_attention_bf16 (fast pass)");
+        if (rc) return rc;
+    }
+    exact_fn<<<grid, v4::THREADS, v4::SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    rc = after_launch("petr_cross_attention_bf16");
     if (rc) return rc;
     if (part && !write_partial) {
         // on-GPU split-KV: merge right away

@@ -188,7 +188,9 @@ def key_side_tc(eng, x, mi: MetaInputs, taps=None, views: slice = None):
     if nsplit > 1:
         partial = torch.empty((nsplit * ops.attention_partial_floats(B, s.Lq, s.heads),),
                               dtype=torch.float32, device=dev)
-    return dict(precision="bf16", B=B, Lk=Lk, Kh=Kh, Vh=Vh, kmask=kmask, nsplit=nsplit, partial=partial)
+    att_ws = ops.cross_attention_workspace(B, s.Lq, Lk, s.heads, nsplit, dev)
+    return dict(precision="bf16", B=B, Lk=Lk, Kh=Kh, Vh=Vh, kmask=kmask, nsplit=nsplit, partial=partial,
+                att_ws=att_ws)
 
 
 def _sine_args(s):
@@ -229,7 +231,8 @@ def decoder_layer_tc(eng, P, l: int, st: dict, qpos, ks: dict, last: bool) -> di
         ks["xattn"](qs[0], l, o_s)                           # key-split: partials + exchange + merge
     else:
         ops.cross_attention_bf16(qs[0], ks["Kh"][l], ks["Vh"][l], ks["kmask"], B, s.Lq, ks["Lk"], s.heads,
-                                 ks["nsplit"], partial=ks["partial"], out_split=o_s, want_f32=False)
+                                 ks["nsplit"], partial=ks["partial"], out_split=o_s, want_f32=False,
+                                 workspace=ks["att_ws"])
     y = g(o_s, tw["ca_out"], lw["ca_out_b"], residual=X1, x3=True, name="gemm_q_side")
     X2 = torch.empty_like(y)
     X2s = torch.empty((R, 2 * E), dtype=torch.bfloat16, device=dev)
@@ -338,7 +341,7 @@ def key_side_keysplit(eng, x, mi: MetaInputs, world: int, rank: int, group=None,
 
     def xattn(qs, l, o_s):
         ops.cross_attention_bf16(qs, ks["Kh"][l], ks["Vh"][l], ks["kmask"], B, s.Lq, ks["Lk"], s.heads, 1,
-                                 partial=local, write_partial=True)
+                                 partial=local, write_partial=True, workspace=ks["att_ws"])
         dist.all_gather_into_tensor(gathered, local, group=group)
         ops.attention_merge(gathered, world, B, s.Lq, s.heads, out_split=o_s, want_f32=False)
 
@@ -361,7 +364,8 @@ def key_side_keysplit_emulated(eng, x, mi: MetaInputs, world: int, taps=None) ->
     def xattn(qs, l, o_s):
         for r, k in enumerate(shards):
             ops.cross_attention_bf16(qs, k["Kh"][l], k["Vh"][l], k["kmask"], B, s.Lq, k["Lk"], s.heads, 1,
-                                     partial=gathered[r * floats:(r + 1) * floats], write_partial=True)
+                                     partial=gathered[r * floats:(r + 1) * floats], write_partial=True,
+                                     workspace=k["att_ws"])
         ops.attention_merge(gathered, world, B, s.Lq, s.heads, out_split=o_s, want_f32=False)
 
     out = dict(shards[0])

@@ -609,13 +609,32 @@ class _PETRHeadBase(BaseModule):
     # -- engine cache ---------------------------------------------------------------------
     @property
     def engine(self) -> HeadEngine:
+        """The engine keeps derived copies of the parameters (bf16 / [hi|hi|lo] packs, concatenated
+        K/V weights) and captured CUDA graphs.  They are dropped whenever the parameters may have
+        changed: load_state_dict / _load_from_state_dict (also reached by a detector-level or mmcv
+        `load_checkpoint` recursion), _apply (.to/.cuda/.half), init_weights, and -- checked on every
+        access -- any in-place edit, through the tensors' version counters."""
         if self._engine is None:
             self._engine = HeadEngine(self)
+            self._engine_sig = self._param_signature()
+        else:
+            sig = self._param_signature()
+            if sig != self._engine_sig:
+                self._engine.invalidate()
+                self._engine_sig = sig
         return self._engine
+
+    def _param_signature(self):
+        v = n = 0
+        for p in self.parameters():
+            v += p._version
+            n += 1
+        return (v, n)
 
     def _invalidate_engine(self):
         if self._engine is not None:
             self._engine.invalidate()
+            self._engine_sig = self._param_signature()
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
@@ -665,6 +684,7 @@ class _PETRHeadBase(BaseModule):
                         break
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys,
                                       unexpected_keys, error_msgs)
+        self._invalidate_engine()
 
     def get_bboxes(self, preds_dicts, img_metas, rescale=False):
         """petr_head.py:731-751: NMS-free decode of the last layer, gravity centre -> bottom centre,

@@ -322,13 +322,24 @@ def attention_partial_floats(B: int, Lq: int, heads: int) -> int:
     return int(_lib.lib().petr_attention_partial_floats(B, Lq, heads))
 
 
+def cross_attention_workspace(B: int, Lq: int, Lk: int, heads: int, nsplit: int, device) -> torch.Tensor:
+    """Scratch of petr_cross_attention_bf16's fast pass (one flag per CTA)."""
+    n = int(_lib.lib().petr_cross_attention_workspace_bytes(B, Lq, Lk, heads, nsplit))
+    return torch.empty((max(n, 4),), dtype=torch.uint8, device=device)
+
+
 def cross_attention_bf16(Qs, Kh, Vh, key_mask, B: int, Lq: int, Lk: int, heads: int, nsplit: int = 1,
                          out=None, partial=None, write_partial: bool = False, out_split=None,
-                         want_f32: bool = True):
+                         want_f32: bool = True, workspace=None, exact_only: bool = False):
     """Flash cross-attention on tcgen05.  Returns O fp32 (B*Lq, heads*32), or the partial
-    buffer when write_partial."""
+    buffer when write_partial.  workspace: cross_attention_workspace(...) (allocated here when
+    None); exact_only skips the max-free fast pass."""
     _cuda(Qs, "Qs")
     nsplit = max(1, min(int(nsplit), (Lk + 127) // 128))
+    if workspace is None and not exact_only:
+        workspace = cross_attention_workspace(B, Lq, Lk, heads, nsplit, Qs.device)
+    if exact_only:
+        workspace = None
     if (nsplit > 1 or write_partial) and partial is None:
         partial = torch.empty((nsplit * attention_partial_floats(B, Lq, heads),), dtype=torch.float32,
                               device=Qs.device)
@@ -336,8 +347,8 @@ def cross_attention_bf16(Qs, Kh, Vh, key_mask, B: int, Lq: int, Lk: int, heads: 
         out = torch.empty((B * Lq, heads * 32), dtype=torch.float32, device=Qs.device)
     with _Timed("cross_attention_bf16"):
         call("petr_cross_attention_bf16", ptr(Qs), ptr(Kh), ptr(Vh), ptr(key_mask), ptr(out),
-             out.stride(0) if out is not None else 0, ptr(out_split), ptr(partial), B, Lq, Lk, heads,
-             nsplit, int(write_partial), stream_ptr(Qs.device))
+             out.stride(0) if out is not None else 0, ptr(out_split), ptr(partial), ptr(workspace),
+             B, Lq, Lk, heads, nsplit, int(write_partial), stream_ptr(Qs.device))
     if write_partial:
         return partial
     return out if out is not None else out_split

@@ -97,7 +97,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     for name in declared:
         assert hasattr(L, name), f"{name} declared in petr_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.lib().petr_abi_version() == 1
+    assert _lib.lib().petr_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_argument_errors_are_reported_not_thrown(lib_built):
@@ -148,3 +148,28 @@ def test_stacked_img_metas_ingestion_equals_list_format():
             else:
                 assert a[k] == b[k], k
     assert a["has_mask"] and not a["uniform_masks"]
+
+
+def test_engine_cache_follows_parameter_updates():
+    """The packed-weight / CUDA-graph cache must not survive a checkpoint load that goes through a
+    parent module's recursion (detector.load_state_dict, mmcv load_checkpoint: the head's own
+    load_state_dict is never called) nor an in-place parameter update."""
+    head = pb.build_head(pb.petr_head_cfg(256))
+    eng = head.engine
+    dev = torch.device("cpu")
+
+    class Detector(torch.nn.Module):
+        def __init__(self, h):
+            super().__init__()
+            self.pts_bbox_head = h
+
+    det = Detector(head)
+    eng._packed[dev] = {"stale": True}
+    det.load_state_dict({k: v.clone() + 0.5 for k, v in det.state_dict().items()}, strict=True)
+    assert head.engine is eng and dev not in eng._packed
+    eng._packed[dev] = {"stale": True}
+    with torch.no_grad():
+        head.reference_points.weight.mul_(0.5)
+    assert dev not in head.engine._packed
+    eng._packed[dev] = {"fresh": True}
+    assert dev in head.engine._packed              # nothing changed: the cache is kept

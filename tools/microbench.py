@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Kernel-level A/B timings on one B200 (CUDA events, inputs larger than L2 at the default sizes).
+
+  python tools/microbench.py flash [--batch 16] [--keys 24000]
+  python tools/microbench.py kproj [--batch 16]
+  python tools/microbench.py k1    [--batch 16]
+
+Prints one JSON line per variant.  Variants are selected through petr_set_tuning (explicit ABI)."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from petr_b200 import _lib, ops  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2], ts[0]
+
+
+def flash(args):
+    B, Lq, Lk, H = args.batch, 900, args.keys, 8
+    g = torch.Generator(device=DEV).manual_seed(0)
+    q = torch.randn(B * Lq, 256, generator=g, device=DEV)
+    Kh = torch.randn(B, H, Lk, 32, generator=g, device=DEV).to(torch.bfloat16)
+    Vh = torch.randn(B, H, Lk, 32, generator=g, device=DEV).to(torch.bfloat16)
+    qs = ops.pack_q_bf16(q, B, Lq, H)
+    from petr_b200.engine_tc import choose_nsplit
+    ns = args.nsplit or choose_nsplit(B, H, Lq, Lk)
+    o_s = torch.empty((B * Lq, 512), dtype=torch.bfloat16, device=DEV)
+    part = torch.empty((ns * ops.attention_partial_floats(B, Lq, H),), dtype=torch.float32, device=DEV) if ns > 1 else None
+    ws = ops.cross_attention_workspace(B, Lq, Lk, H, ns, DEV)
+    flops = 4.0 * Lq * Lk * 256 * B
+    ref = None
+    for mode in ["exact", "poly0", "poly1", "poly2", "poly3"]:
+        if mode != "exact":
+            _lib.set_tuning("flash_poly", int(mode[4:]))
+        fn = lambda: ops.cross_attention_bf16(qs, Kh, Vh, None, B, Lq, Lk, H, ns, partial=part, out_split=o_s,
+                                              want_f32=False, workspace=ws, exact_only=(mode == "exact"))
+        med, best = timeit(fn)
+        out = o_s[:, :256].float() + o_s[:, 256:].float()
+        if ref is None:
+            ref = out.clone()
+        print(json.dumps(dict(kernel="flash", mode=mode, B=B, Lk=Lk, nsplit=ns, ms_median=med, ms_best=best,
+                              tflops=flops / med / 1e9, flagged=int(ws.view(torch.int32).sum()) if mode != "exact" else None,
+                              max_diff_vs_exact=float((out - ref).abs().max()))), flush=True)
+    _lib.set_tuning("flash_poly", 0)
+
+
+def kproj(args):
+    B, Lk = args.batch, args.keys
+    M, N, K = B * Lk, 1536, 256
+    A = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=DEV) / 16).to(torch.bfloat16)
+    b = torch.randn(N, device=DEV)
+    ref = None
+    for staged in (0, 1):
+        _lib.set_tuning("gemm_staged", staged)
+        out = [None]
+
+        def fn():
+            out[0] = ops.gemm_bf16_tc(A, W, b, headsplit_Lk=Lk, name="gemm_kproj")
+        med, best = timeit(fn)
+        if ref is None:
+            ref = out[0].clone()
+        print(json.dumps(dict(kernel="kproj", staged=staged, M=M, ms_median=med, ms_best=best,
+                              tflops=2.0 * M * N * K / med / 1e9, write_gbs=M * N * 2 / med / 1e6,
+                              equal=bool(torch.equal(ref, out[0])))), flush=True)
+    _lib.set_tuning("gemm_staged", 1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["flash", "kproj", "all"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--keys", type=int, default=24000)
+    ap.add_argument("--nsplit", type=int, default=0)
+    args = ap.parse_args()
+    if args.what in ("flash", "all"):
+        flash(args)
+    if args.what in ("kproj", "all"):
+        kproj(args)
+
+
+if __name__ == "__main__":
+    main()
