@@ -58,7 +58,7 @@ int64_t petr_launch_count(void);
 void petr_launch_count_reset(void);
 /* Explicit, process-wide tuning switches (A/B measurements and tests; the library reads no
  * environment variables).  Keys: "flash_exact_only" (0/1: skip the max-free fast pass of
- * petr_cross_attention_bf16), "flash_poly" (0..3: exponentials per 8 evaluated on the FMA pipes in
+ * petr_cross_attention_bf16), "flash_poly" (0..4: exponential pairs per 4 evaluated on the FMA pipe in
  * the fast pass).  Returns 0, or PETR_E_BADARG for an unknown key / out-of-range value;
  * petr_get_tuning returns the current value or -1. */
 int petr_set_tuning(const char* key, int value);
@@ -232,6 +232,12 @@ int petr_cross_attention_bf16(const void* Qs, const void* Kh, const void* Vh,
                               float* partial, void* workspace, int B, int Lq, int Lk, int heads,
                               int nsplit, int write_partial, void* stream);
 int64_t petr_cross_attention_workspace_bytes(int B, int Lq, int Lk, int heads, int nsplit);
+/* Diagnostic (not a product path): the fast pass of petr_cross_attention_bf16 with clock64() stamps of
+ * CTA 0's pipeline events written to trace[7 roles][64 key tiles][8 events] (int64); the partials go
+ * to `partial` (nsplit * petr_attention_partial_floats).  See tools/flash_trace.py. */
+int petr_cross_attention_trace(const void* Qs, const void* Kh, const void* Vh, float* partial,
+                               void* workspace, long long* trace, int B, int Lq, int Lk, int heads,
+                               int nsplit, void* stream);
 
 /* fp32-class attention on tcgen05 (the decoder's self-attention; mmcv MultiheadAttention called by
  * BaseTransformerLayer with q = k = query + query_pos, v = query).  Every operand is a bf16

@@ -14,7 +14,7 @@ int64_t& launch_counter() {
 }
 namespace tuning {
 static std::atomic<int> g_flash_exact_only{0};
-static std::atomic<int> g_flash_poly{0};
+static std::atomic<int> g_flash_poly{2};
 static std::atomic<int> g_gemm_staged{1};
 bool flash_exact_only() { return g_flash_exact_only.load(std::memory_order_relaxed) != 0; }
 int flash_poly() { return g_flash_poly.load(std::memory_order_relaxed); }
@@ -22,7 +22,7 @@ bool gemm_staged() { return g_gemm_staged.load(std::memory_order_relaxed) != 0; 
 struct Entry { const char* key; std::atomic<int>* v; int lo, hi; };
 static const Entry kEntries[] = {
     {"flash_exact_only", &g_flash_exact_only, 0, 1},
-    {"flash_poly", &g_flash_poly, 0, 3},
+    {"flash_poly", &g_flash_poly, 0, 4},
     {"gemm_staged", &g_gemm_staged, 0, 1},
 };
 }  // namespace tuning

@@ -61,6 +61,32 @@ __device__ __forceinline__ float ex2_poly(float x) {
     return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
 }
 
+// Two exp2 at once on the FMA pipe with the packed fp32x2 instructions of sm_100 (FADD2 / FFMA2): round-to-
+// nearest split x = n + f, cubic minimax for 2^f (max rel. error 7.6e-5), exponent add with one LEA each:
+// 10 instructions per pair instead of 18 scalar ones.
+__device__ __forceinline__ uint64_t f32x2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void ex2_poly_pair(float x0, float x1, float& y0, float& y1) {
+    const uint64_t x = f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+    const uint64_t magic = f32x2(12582912.f, 12582912.f);                       // 1.5 * 2^23
+    uint64_t t, f, pz;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(magic));             // integer part in the low mantissa bits
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(t), "l"(magic));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(x), "l"(f));                 // f in [-0.5, 0.5]
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pz) : "l"(f32x2(0.05520550534129143f, 0.05520550534129143f)), "l"(f),
+        "l"(f32x2(0.24261397123336792f, 0.24261397123336792f)));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pz) : "l"(pz), "l"(f), "l"(f32x2(0.6932547688484192f, 0.6932547688484192f)));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pz) : "l"(pz), "l"(f), "l"(f32x2(0.9999276995658875f, 0.9999276995658875f)));
+    float p0, p1, t0, t1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(p0), "=f"(p1) : "l"(pz));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+    y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 struct AttParams {
     const uint8_t* key_mask;   // [B, Lk] or null
     float* O; int ldo;         // normalised output (nsplit == 1), nullable
@@ -68,6 +94,7 @@ struct AttParams {
     float* partial;            // [nsplit][rows*32 O | rows*2 (m,l)], rows = B*heads*Lq
     int* flags;                // [grid CTAs] fast pass -> exact pass (cross-attention), nullable
     int B, Lq, Lk, heads, nsplit, tiles_total, write_partial;
+    long long* trace;          // diagnostic event stamps (tools/flash_trace.py), normally null
 };
 
 // Output of one query row: un-normalised partial (O, m, l) or normalised fp32 / split-bf16 row.
@@ -437,18 +464,26 @@ constexpr int OFF_BAR = OFF_MAX + NQT * 2 * 2 * QT * 4;
 constexpr int SMEM = OFF_BAR + 256 + 1024;
 constexpr int THREADS = 608;
 constexpr int TM_S = 0;          // S_x at TM_S + 128 x
-constexpr int TM_O = 256;        // O_x at TM_O + 48 x (32 cols), L_x right behind it (16 cols)
+constexpr int TM_P = 256;        // FAST: P_x (bf16 pairs, 64 columns) at TM_P + 64 x -- the A operand of P V
+constexpr int TM_O = 384;        // O_x at TM_O + 48 x (32 cols), L_x right behind it (16 cols)
 constexpr float L_MIN = 8.3e-25f;   // 2^-80
 constexpr float L_MAX = 1.2e30f;    // ~2^100
 
-// POLY of every 8 score elements take ex2_poly (FMA/ALU pipes) instead of MUFU ex2, spread evenly.
+// exponentials of one pair of scores -> packed bf16 pair; POLY of every 4 pairs go to the FMA pipe (ex2_poly_pair)
 template <int POLY>
-__device__ __forceinline__ float ex2_sel(float x, int i) {
-    const bool poly = ((i & 7) * POLY) / 8 != (((i & 7) + 1) * POLY) / 8;
-    return poly ? ex2_poly(x) : ex2(x);
+__device__ __forceinline__ uint32_t exp_pair(float a, float b, int pair) {
+    const int g = pair & 3;
+    const bool poly = (g * POLY) / 4 != ((g + 1) * POLY) / 4;
+    float y0, y1;
+    if (poly) ex2_poly_pair(a, b, y0, y1);
+    else { y0 = ex2(a); y1 = ex2(b); }
+    return pack_bf16x2(y0, y1);
 }
 
-template <bool FAST, int POLY>
+// TRACE: clock64() stamps of CTA 0's pipeline events (tools/flash_trace.py), first 64 key tiles
+#define PETR_TR(role, j, ev) do { if (TRACE && p.trace && cta == 0 && (j) < 64) p.trace[((role) * 64 + (j)) * 8 + (ev)] = clock64(); } while (0)
+
+template <bool FAST, int POLY, bool TRACE = false>
 __global__ void __launch_bounds__(THREADS, 1)
 cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                            const __grid_constant__ CUtensorMap tmV, AttParams p) {
@@ -466,7 +501,10 @@ cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     uint64_t* pv_done = p_ready + 4;                // [x][buf]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the MMA issuers' descriptor
+    // arithmetic in uniform registers (a divergent `if (lane == 0)` issuer costs ~70 clk per tcgen05.mma in
+    // R2UR / ELECT loops: measured 1100 clk to issue the 16 P V MMAs of one key tile, tools/flash_trace.py)
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (NQT * QT);
     const int bh = blockIdx.y;
     const int split = blockIdx.z;
@@ -512,6 +550,7 @@ cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
             for (int j = 0; j < ntiles; ++j) {
                 const int s = j % KV_STAGES;
                 mbar_wait(&kv_empty[s], ((j / KV_STAGES) & 1) ^ 1);
+                PETR_TR(6, j, 0);
                 mbar_arrive_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
                 uint8_t* kd = smem + OFF_KV + s * (K_BYTES + V_BYTES);
                 const int key0 = (t_begin + j) * KT;
@@ -522,50 +561,72 @@ cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     } else if (warp == 1 || warp == 18) {
         // ---------------- MMA issuers: warp 1 drives query tile A, warp 18 tile B ----------------
         const int x = (warp == 1) ? 0 : 1;
-        if (lane == 0 && ntiles > 0 && (x ? lq1 : lq0) > 0) {
+        if (ntiles > 0 && (x ? lq1 : lq0) > 0) {             // whole warp: waits by all lanes, MMAs by the elected one
+            const bool leader = elect_one();
             constexpr uint32_t idesc_qk = make_idesc(QT, KT, 1, 0, 0);     // S[128x128] = Q K^T
             constexpr uint32_t idesc_pv = make_idesc(QT, HD, 1, 0, 1);     // O[128x32] += P V (V MN-major)
             constexpr uint32_t idesc_l = make_idesc(QT, 16, 1, 0, 0);      // L[128x16] += P 1
-            const uint32_t q_addr = smem_u32(smem + OFF_Q + x * Q_BYTES);
-            const uint32_t p_addr = smem_u32(smem + OFF_P + x * 2 * P_BYTES);
-            const uint32_t ones_addr = smem_u32(smem + OFF_ONES);
             const uint32_t kv_addr = smem_u32(smem + OFF_KV);
-            const uint64_t q_desc0 = make_smem_desc(q_addr, 16, 512, LAYOUT_SW64);
+            const uint64_t q_desc0 = make_smem_desc(smem_u32(smem + OFF_Q + x * Q_BYTES), 16, 512, LAYOUT_SW64);
             const uint64_t k_desc0 = make_smem_desc(kv_addr, 16, 512, LAYOUT_SW64);
             const uint64_t v_desc0 = make_smem_desc(kv_addr + K_BYTES, 512, 512, LAYOUT_SW64);
-            uint64_t p_desc[KT / 16], o_desc[KT / 16];
-#pragma unroll
-            for (int kk = 0; kk < KT / 16; ++kk) {
-                p_desc[kk] = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
-                o_desc[kk] = make_smem_desc(ones_addr + (kk >> 2) * 2048 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
-            }
+            const uint64_t p_desc0 = make_smem_desc(smem_u32(smem + OFF_P + x * 2 * P_BYTES), 16, 1024, LAYOUT_SW128);
+            const uint64_t ones_desc = make_smem_desc(smem_u32(smem + OFF_ONES), 16, 1024, LAYOUT_SW128);
             const uint32_t d_s = tmem_base + TM_S + x * 128;
             const uint32_t d_o = tmem_base + TM_O + x * 48, d_l = d_o + 32;
+            const uint32_t p_tmem = tmem_base + TM_P + x * 64;
             auto issue_pv = [&](int t) {
                 const int s = t % KV_STAGES;
                 const uint64_t vd = v_desc0 + (uint64_t)((s * (K_BYTES + V_BYTES)) >> 4);
-                const uint64_t pb = (uint64_t)(((t & 1) * P_BYTES) >> 4);
-                mbar_wait(&p_ready[2 * x + (t & 1)], (t >> 1) & 1);
-                tcgen05_fence_after();
+                if (FAST) {
+                    // P comes straight from tensor memory (A operand in TMEM, 8 columns = 16 keys per MMA)
+                    mbar_wait(&p_ready[2 * x], t & 1);
+                    tcgen05_fence_after();
+                    if (leader) {
+                        PETR_TR(x, t, 3);
 #pragma unroll
-                for (int kk = 0; kk < KT / 16; ++kk) {
-                    umma_f16_ss(d_o, p_desc[kk] + pb, vd + (uint64_t)((kk * 1024) >> 4), idesc_pv, (t | kk) ? 1u : 0u);
-                    umma_f16_ss(d_l, p_desc[kk] + pb, o_desc[kk], idesc_l, (t | kk) ? 1u : 0u);
+                        for (int kk = 0; kk < KT / 16; ++kk) {
+                            umma_f16_ts(d_o, p_tmem + kk * 8, vd + (uint64_t)((kk * 1024) >> 4), idesc_pv, (t | kk) ? 1u : 0u);
+                            umma_f16_ts(d_l, p_tmem + kk * 8, ones_desc, idesc_l, (t | kk) ? 1u : 0u);
+                        }
+                        umma_commit(&pv_done[2 * x]);
+                        umma_commit(&kv_empty[s]);
+                        PETR_TR(x, t, 4);
+                    }
+                } else {
+                    const uint64_t pb = p_desc0 + (uint64_t)(((t & 1) * P_BYTES) >> 4);
+                    mbar_wait(&p_ready[2 * x + (t & 1)], (t >> 1) & 1);
+                    tcgen05_fence_after();
+                    if (leader) {
+#pragma unroll
+                        for (int kk = 0; kk < KT / 16; ++kk) {
+                            const uint64_t pd = pb + (uint64_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
+                            umma_f16_ss(d_o, pd, vd + (uint64_t)((kk * 1024) >> 4), idesc_pv, (t | kk) ? 1u : 0u);
+                            umma_f16_ss(d_l, pd, ones_desc, idesc_l, (t | kk) ? 1u : 0u);
+                        }
+                        umma_commit(&pv_done[2 * x + (t & 1)]);
+                        umma_commit(&kv_empty[s]);
+                    }
                 }
-                umma_commit(&pv_done[2 * x + (t & 1)]);
-                umma_commit(&kv_empty[s]);
+                __syncwarp();
             };
             mbar_wait(q_full, 0);
             for (int j = 0; j < ntiles; ++j) {
                 const int s = j % KV_STAGES;
                 const uint64_t kd = k_desc0 + (uint64_t)((s * (K_BYTES + V_BYTES)) >> 4);
                 mbar_wait(&kv_full[s], (j / KV_STAGES) & 1);
+                if (leader) PETR_TR(x, j, 0);
                 mbar_wait(&s_free[x], (j & 1) ^ 1);
                 tcgen05_fence_after();
+                if (leader) {
+                    PETR_TR(x, j, 1);
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    umma_f16_ss(d_s, q_desc0 + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_qk, k ? 1u : 0u);
-                umma_commit(&s_full[x]);
+                    for (int k = 0; k < HD / 16; ++k)
+                        umma_f16_ss(d_s, q_desc0 + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc_qk, k ? 1u : 0u);
+                    umma_commit(&s_full[x]);
+                    PETR_TR(x, j, 2);
+                }
+                __syncwarp();
                 if (j > 0) issue_pv(j - 1);
             }
             issue_pv(ntiles - 1);
@@ -583,6 +644,7 @@ cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
         const uint32_t s_addr = tmem_base + lane_off + TM_S + x * 128 + hf * 64;
         const uint32_t o_addr = tmem_base + lane_off + TM_O + x * 48;
+        const uint32_t p_addr = tmem_base + lane_off + TM_P + x * 64 + hf * 32;
         float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS) + x * KT;
         float* smax = reinterpret_cast<float*>(smem + OFF_MAX) + x * (4 * QT);
         const uint32_t pbase = smem_u32(smem + OFF_P + x * 2 * P_BYTES + hf * 16384 + (row >> 3) * 1024 + (row & 7) * 128);
@@ -606,12 +668,17 @@ cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
             mbar_wait(&s_full[x], par);
             tcgen05_fence_after();
             uint32_t sr[64];
+            uint32_t pk[32];
+            float* sv = reinterpret_cast<float*>(sr);
+            const int trole = 2 + 2 * x + hf;
+            const bool tr0 = quarter == 0 && lane == 0;
+            if (tr0) PETR_TR(trole, j, 0);
             tmem_ld_x32(s_addr, sr);
             tmem_ld_x32(s_addr + 32, sr + 32);
             tmem_ld_wait();
             tcgen05_fence_before();
             mbar_arrive(&s_free[x]);
-            float* sv = reinterpret_cast<float*>(sr);
+            if (tr0) PETR_TR(trole, j, 1);
             if (need_bias) {
 #pragma unroll
                 for (int i = 0; i < 64; i += 4) {
@@ -619,13 +686,11 @@ cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
                     sv[i] += t.x; sv[i + 1] += t.y; sv[i + 2] += t.z; sv[i + 3] += t.w;
                 }
             }
-            uint32_t pk[32];
             float alpha = 1.f;
             bool grow = false;
             if (FAST) {
 #pragma unroll
-                for (int i = 0; i < 64; i += 2)
-                    pk[i >> 1] = pack_bf16x2(ex2_sel<POLY>(sv[i], i), ex2_sel<POLY>(sv[i + 1], i + 1));
+                for (int i = 0; i < 64; i += 2) pk[i >> 1] = exp_pair<POLY>(sv[i], sv[i + 1], i >> 1);
             } else {
                 float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
 #pragma unroll
@@ -643,6 +708,19 @@ cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 #pragma unroll
                 for (int i = 0; i < 64; i += 2)
                     pk[i >> 1] = pack_bf16x2(ex2(sv[i] - m_eff), ex2(sv[i + 1] - m_eff));
+            }
+            if (FAST) {
+                // P -> tensor memory (the A operand of P V): no shared-memory round trip, no proxy fence
+                if (TRACE) { asm volatile("" :: "r"(pk[0]), "r"(pk[31]) : "memory"); if (tr0) PETR_TR(trole, j, 2); }
+                mbar_wait(&pv_done[2 * x], par ^ 1);                       // PV(j-1) has consumed the P columns
+                if (tr0) PETR_TR(trole, j, 3);
+                tcgen05_fence_after();
+                tmem_st_x32(p_addr, pk);
+                tmem_st_wait();
+                tcgen05_fence_before();
+                mbar_arrive(&p_ready[2 * x]);
+                if (tr0) PETR_TR(trole, j, 4);
+                continue;
             }
             mbar_wait(&pv_done[2 * x + par], ((j >> 1) & 1) ^ 1);          // P buffer j&1 free (PV(j-2) retired)
             const uint32_t pb = pbase + par * P_BYTES;
@@ -678,7 +756,8 @@ cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
             const int q = q0 + x * QT + row;
             float o[32], l = 0.f;
             if (ntiles > 0) {
-                mbar_wait(&pv_done[2 * x + ((ntiles - 1) & 1)], ((ntiles - 1) >> 1) & 1);
+                if (FAST) mbar_wait(&pv_done[2 * x], (ntiles - 1) & 1);
+                else mbar_wait(&pv_done[2 * x + ((ntiles - 1) & 1)], ((ntiles - 1) >> 1) & 1);
                 tcgen05_fence_after();
                 uint32_t orr[48];
                 tmem_ld_x32(o_addr, orr);
@@ -837,10 +916,11 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
     const flash_fn exact_fn = v4::cross_attention_tc4_kernel<false, 0>;
     flash_fn fast_fn;
     switch (tuning::flash_poly()) {
+        case 0: fast_fn = v4::cross_attention_tc4_kernel<true, 0>; break;
         case 1: fast_fn = v4::cross_attention_tc4_kernel<true, 1>; break;
-        case 2: fast_fn = v4::cross_attention_tc4_kernel<true, 2>; break;
         case 3: fast_fn = v4::cross_attention_tc4_kernel<true, 3>; break;
-        default: fast_fn = v4::cross_attention_tc4_kernel<true, 0>; break;
+        case 4: fast_fn = v4::cross_attention_tc4_kernel<true, 4>; break;
+        default: fast_fn = v4::cross_attention_tc4_kernel<true, 2>; break;
     }
     cudaError_t e = cudaFuncSetAttribute(exact_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v4::SMEM);
     if (e == cudaSuccess && fast) e = cudaFuncSetAttribute(fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v4::SMEM);
@@ -870,6 +950,32 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
         return after_launch("petr_attention_merge");
     }
     return 0;
+}
+
+// Diagnostic: the fast pass with pipeline-event time stamps of CTA 0 (7 roles x 64 key tiles x 8 events,
+// clock64) written to `trace`; same arguments as petr_cross_attention_bf16 otherwise.  Not a product path.
+extern "C" int petr_cross_attention_trace(const void* Qs, const void* Kh, const void* Vh, float* partial, void* workspace,
+                                          long long* trace, int B, int Lq, int Lk, int heads, int nsplit, void* stream) {
+    PETR_REQUIRE(Qs && Kh && Vh && partial && workspace && trace, PETR_E_BADARG, "petr_cross_attention_trace: null pointer");
+    const int tiles = (Lk + KT - 1) / KT;
+    if (nsplit > tiles) nsplit = tiles;
+    CUtensorMap tmQ, tmK, tmV;
+    uint64_t dq[3] = {HD, (uint64_t)Lq, (uint64_t)B * heads}, sq[2] = {HD * 2, (uint64_t)Lq * HD * 2};
+    uint64_t dk[3] = {HD, (uint64_t)Lk, (uint64_t)B * heads}, sk[2] = {HD * 2, (uint64_t)Lk * HD * 2};
+    uint32_t bq[3] = {HD, QT, 1}, bk[3] = {HD, KT, 1};
+    int rc = tmap::encode(&tmQ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Qs, dq, sq, bq, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (!rc) rc = tmap::encode(&tmK, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Kh, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (!rc) rc = tmap::encode(&tmV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Vh, dk, sk, bk, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    auto fn = v4::cross_attention_tc4_kernel<true, 2, true>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, v4::SMEM);
+    if (e != cudaSuccess) return fail((int)e, "petr_cross_attention_trace: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    AttParams p{};
+    p.partial = partial; p.flags = (int*)workspace; p.trace = trace;
+    p.B = B; p.Lq = Lq; p.Lk = Lk; p.heads = heads; p.nsplit = nsplit; p.tiles_total = tiles; p.write_partial = 1;
+    dim3 grid((Lq + 2 * QT - 1) / (2 * QT), B * heads, nsplit);
+    fn<<<grid, v4::THREADS, v4::SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    return after_launch("petr_cross_attention_trace");
 }
 
 extern "C" int petr_attention_merge(const float* partial, int nparts, float* O, int ldo, void* O_split,

@@ -47,7 +47,7 @@ def flash(args):
     ws = ops.cross_attention_workspace(B, Lq, Lk, H, ns, DEV)
     flops = 4.0 * Lq * Lk * 256 * B
     ref = None
-    for mode in ["exact", "poly0", "poly1", "poly2", "poly3"]:
+    for mode in args.modes.split(","):
         if mode != "exact":
             _lib.set_tuning("flash_poly", int(mode[4:]))
         fn = lambda: ops.cross_attention_bf16(qs, Kh, Vh, None, B, Lq, Lk, H, ns, partial=part, out_split=o_s,
@@ -59,7 +59,7 @@ def flash(args):
         print(json.dumps(dict(kernel="flash", mode=mode, B=B, Lk=Lk, nsplit=ns, ms_median=med, ms_best=best,
                               tflops=flops / med / 1e9, flagged=int(ws.view(torch.int32).sum()) if mode != "exact" else None,
                               max_diff_vs_exact=float((out - ref).abs().max()))), flush=True)
-    _lib.set_tuning("flash_poly", 0)
+    _lib.set_tuning("flash_poly", 2)
 
 
 def kproj(args):
@@ -90,6 +90,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--keys", type=int, default=24000)
     ap.add_argument("--nsplit", type=int, default=0)
+    ap.add_argument("--modes", default="exact,poly0,poly1,poly2,poly3,poly4")
     args = ap.parse_args()
     if args.what in ("flash", "all"):
         flash(args)
