@@ -28,15 +28,14 @@ sys.path.insert(0, ROOT)
 METRIC = "PETR head 6-view samples/sec at 1600x640, 1/2/4/8 B200; attn % of bf16 peak"
 
 
-FLASH_KERNEL = ("cross_attention_tc2_kernel" if os.environ.get("PETR_FLASH_V3", "1") == "0"
-                else "cross_attention_tc3_kernel")
+FLASH_KERNEL = "cross_attention_tc4_kernel"        # fast (max-free) pass; the exact pass only re-runs flagged CTAs
 
 
 def load_traffic(batch):
     """DRAM bytes per launch of the flash cross-attention kernel from the committed `ncu --set full`
     capture (dram__bytes_read.sum + dram__bytes_write.sum), if one exists for this kernel and
     batch size."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.isfile(p):
         with open(p) as f:
             d = json.load(f)

@@ -177,7 +177,7 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
     float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
     const int qtile = blockIdx.x;
     const int bh = blockIdx.y;
     const int split = blockIdx.z;
@@ -211,30 +211,39 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0 && ntiles > 0) {
-            mbar_arrive_expect_tx(q_full, 2 * Q_BYTES);
-            tma_load_3d(smem + OFF_Q, &tm.qh, q_full, 0, qtile * QT, bh);
-            tma_load_3d(smem + OFF_Q + Q_BYTES, &tm.ql, q_full, 0, qtile * QT, bh);
+        if (ntiles > 0) {                                    // whole warp: waits by all lanes, TMA by the elected one
+            const bool leader = elect_one();
+            if (leader) {
+                mbar_arrive_expect_tx(q_full, 2 * Q_BYTES);
+                tma_load_3d(smem + OFF_Q, &tm.qh, q_full, 0, qtile * QT, bh);
+                tma_load_3d(smem + OFF_Q + Q_BYTES, &tm.ql, q_full, 0, qtile * QT, bh);
+            }
             // K and V of a stage are released separately (K right after Q K^T, V after P V) and the K
             // loads run one tile ahead of the V loads: with one shared barrier the K tile of j + 1 was
             // requested only after P V of j - 1, and its TMA latency stalled the softmax warps on S
             auto load_k = [&](int j) {
                 const int s = j % STAGES;
                 mbar_wait(&k_empty[s], ((j / STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(&k_full[s], 2 * K_BYTES);
-                uint8_t* d = smem + OFF_KV + s * STAGE_BYTES;
-                const int key0 = (t_begin + j) * KT;
-                tma_load_3d(d, &tm.kh, &k_full[s], 0, key0, bh);
-                tma_load_3d(d + K_BYTES, &tm.kl, &k_full[s], 0, key0, bh);
+                if (leader) {
+                    mbar_arrive_expect_tx(&k_full[s], 2 * K_BYTES);
+                    uint8_t* d = smem + OFF_KV + s * STAGE_BYTES;
+                    const int key0 = (t_begin + j) * KT;
+                    tma_load_3d(d, &tm.kh, &k_full[s], 0, key0, bh);
+                    tma_load_3d(d + K_BYTES, &tm.kl, &k_full[s], 0, key0, bh);
+                }
+                __syncwarp();
             };
             auto load_v = [&](int j) {
                 const int s = j % STAGES;
                 mbar_wait(&v_empty[s], ((j / STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(&v_full[s], 2 * V_BYTES);
-                uint8_t* d = smem + OFF_KV + s * STAGE_BYTES + 2 * K_BYTES;
-                const int key0 = (t_begin + j) * KT;
-                tma_load_3d(d, &tm.vh, &v_full[s], 0, key0, bh);
-                tma_load_3d(d + V_BYTES, &tm.vl, &v_full[s], 0, key0, bh);
+                if (leader) {
+                    mbar_arrive_expect_tx(&v_full[s], 2 * V_BYTES);
+                    uint8_t* d = smem + OFF_KV + s * STAGE_BYTES + 2 * K_BYTES;
+                    const int key0 = (t_begin + j) * KT;
+                    tma_load_3d(d, &tm.vh, &v_full[s], 0, key0, bh);
+                    tma_load_3d(d + V_BYTES, &tm.vl, &v_full[s], 0, key0, bh);
+                }
+                __syncwarp();
             };
             load_k(0);
             for (int j = 0; j < ntiles; ++j) {
@@ -243,7 +252,8 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && ntiles > 0) {
+        if (ntiles > 0) {                                    // whole warp; tcgen05.mma / commit by the elected lane
+            const bool leader = elect_one();
             constexpr uint32_t idesc_qk = make_idesc(QT, KT, 1, 0, 0);
             constexpr uint32_t idesc_pv = make_idesc(QT, HD, 1, 0, 1);
             // every descriptor that does not depend on the K/V stage is built once; per-stage ones
@@ -255,10 +265,8 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
             const uint64_t ql_desc = make_smem_desc(q_addr + Q_BYTES, 16, 512, LAYOUT_SW64);
             const uint64_t kh_desc0 = make_smem_desc(kv_addr, 16, 512, LAYOUT_SW64);
             const uint64_t vh_desc0 = make_smem_desc(kv_addr + 2 * K_BYTES, 512, 512, LAYOUT_SW64);
-            uint64_t ph_desc[KT / 16];
-#pragma unroll
-            for (int kk = 0; kk < KT / 16; ++kk)
-                ph_desc[kk] = make_smem_desc(p_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024, LAYOUT_SW128);
+            const uint64_t p_desc0 = make_smem_desc(p_addr, 16, 1024, LAYOUT_SW128);
+            auto ph_desc = [&](int kk) { return p_desc0 + (uint64_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4); };
             auto issue_qk = [&](int t) {
                 const int s = t % STAGES;
                 mbar_wait(&k_full[s], (t / STAGES) & 1);
@@ -267,15 +275,18 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
                 const uint64_t kh = kh_desc0 + (uint64_t)((s * STAGE_BYTES) >> 4);
                 const uint64_t kl = kh + (uint64_t)(K_BYTES >> 4);
                 const uint32_t d = tmem_base + ((t & 1) ? TM_S1 : TM_S0);
-                // (Qh,Kh), (Ql,Kh), (Qh,Kl)
+                if (leader) {
+                    // (Qh,Kh), (Ql,Kh), (Qh,Kl)
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) umma_f16_ss(d, qh_desc + (uint64_t)(k * 2), kh + (uint64_t)(k * 2), idesc_qk, k ? 1u : 0u);
+                    for (int k = 0; k < HD / 16; ++k) umma_f16_ss(d, qh_desc + (uint64_t)(k * 2), kh + (uint64_t)(k * 2), idesc_qk, k ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) umma_f16_ss(d, ql_desc + (uint64_t)(k * 2), kh + (uint64_t)(k * 2), idesc_qk, 1u);
+                    for (int k = 0; k < HD / 16; ++k) umma_f16_ss(d, ql_desc + (uint64_t)(k * 2), kh + (uint64_t)(k * 2), idesc_qk, 1u);
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) umma_f16_ss(d, qh_desc + (uint64_t)(k * 2), kl + (uint64_t)(k * 2), idesc_qk, 1u);
-                umma_commit(&s_full[t & 1]);
-                umma_commit(&k_empty[s]);
+                    for (int k = 0; k < HD / 16; ++k) umma_f16_ss(d, qh_desc + (uint64_t)(k * 2), kl + (uint64_t)(k * 2), idesc_qk, 1u);
+                    umma_commit(&s_full[t & 1]);
+                    umma_commit(&k_empty[s]);
+                }
+                __syncwarp();
             };
             mbar_wait(q_full, 0);
             issue_qk(0);
@@ -289,18 +300,21 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
                 const uint64_t vh = vh_desc0 + (uint64_t)((s * STAGE_BYTES) >> 4);
                 const uint64_t vl = vh + (uint64_t)(V_BYTES >> 4);
                 const uint64_t pl_off = (uint64_t)(P_BYTES >> 4);
-                // (Ph,Vh), (Pl,Vh), (Ph,Vl)
+                if (leader) {
+                    // (Ph,Vh), (Pl,Vh), (Ph,Vl)
 #pragma unroll
-                for (int kk = 0; kk < KT / 16; ++kk)
-                    umma_f16_ss(tmem_base + TM_O, ph_desc[kk] + pb, vh + (uint64_t)((kk * 1024) >> 4), idesc_pv, (j | kk) ? 1u : 0u);
+                    for (int kk = 0; kk < KT / 16; ++kk)
+                        umma_f16_ss(tmem_base + TM_O, ph_desc(kk) + pb, vh + (uint64_t)((kk * 1024) >> 4), idesc_pv, (j | kk) ? 1u : 0u);
 #pragma unroll
-                for (int kk = 0; kk < KT / 16; ++kk)
-                    umma_f16_ss(tmem_base + TM_O, ph_desc[kk] + pb + pl_off, vh + (uint64_t)((kk * 1024) >> 4), idesc_pv, 1u);
+                    for (int kk = 0; kk < KT / 16; ++kk)
+                        umma_f16_ss(tmem_base + TM_O, ph_desc(kk) + pb + pl_off, vh + (uint64_t)((kk * 1024) >> 4), idesc_pv, 1u);
 #pragma unroll
-                for (int kk = 0; kk < KT / 16; ++kk)
-                    umma_f16_ss(tmem_base + TM_O, ph_desc[kk] + pb, vl + (uint64_t)((kk * 1024) >> 4), idesc_pv, 1u);
-                umma_commit(&v_empty[s]);
-                umma_commit(&pv_done[j & 1]);
+                    for (int kk = 0; kk < KT / 16; ++kk)
+                        umma_f16_ss(tmem_base + TM_O, ph_desc(kk) + pb, vl + (uint64_t)((kk * 1024) >> 4), idesc_pv, 1u);
+                    umma_commit(&v_empty[s]);
+                    umma_commit(&pv_done[j & 1]);
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -542,20 +556,26 @@ cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ---------------- TMA producer ----------------
-        if (lane == 0 && ntiles > 0) {
-            mbar_arrive_expect_tx(q_full, NQT * Q_BYTES);
-            tma_load_3d(smem + OFF_Q, &tmQ, q_full, 0, q0, bh);
-            tma_load_3d(smem + OFF_Q + Q_BYTES, &tmQ, q_full, 0, q0 + QT, bh);
+        // ---------------- TMA producer (whole warp walks the loop, the elected lane issues) ----------------
+        if (ntiles > 0) {
+            const bool leader = elect_one();
+            if (leader) {
+                mbar_arrive_expect_tx(q_full, NQT * Q_BYTES);
+                tma_load_3d(smem + OFF_Q, &tmQ, q_full, 0, q0, bh);
+                tma_load_3d(smem + OFF_Q + Q_BYTES, &tmQ, q_full, 0, q0 + QT, bh);
+            }
             for (int j = 0; j < ntiles; ++j) {
                 const int s = j % KV_STAGES;
                 mbar_wait(&kv_empty[s], ((j / KV_STAGES) & 1) ^ 1);
-                PETR_TR(6, j, 0);
-                mbar_arrive_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
-                uint8_t* kd = smem + OFF_KV + s * (K_BYTES + V_BYTES);
-                const int key0 = (t_begin + j) * KT;
-                tma_load_3d(kd, &tmK, &kv_full[s], 0, key0, bh);
-                tma_load_3d(kd + K_BYTES, &tmV, &kv_full[s], 0, key0, bh);
+                if (leader) {
+                    PETR_TR(6, j, 0);
+                    mbar_arrive_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
+                    uint8_t* kd = smem + OFF_KV + s * (K_BYTES + V_BYTES);
+                    const int key0 = (t_begin + j) * KT;
+                    tma_load_3d(kd, &tmK, &kv_full[s], 0, key0, bh);
+                    tma_load_3d(kd + K_BYTES, &tmV, &kv_full[s], 0, key0, bh);
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 1 || warp == 18) {

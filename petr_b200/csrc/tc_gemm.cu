@@ -101,7 +101,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* sbias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);      // [2][BN]
     uint8_t* stage_out = smem + STAGES * STAGE_BYTES + 256 + 2048;                   // [8 warps][32 rows][64 B]
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: ptxas then treats it as warp-uniform and keeps the producer / MMA issuer
+    // loops (descriptors, barrier addresses) in uniform registers instead of R2UR / ELECT loops per instruction
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int num_k = p.K / BK;
     const int num_tiles = p.tiles_m * p.tiles_n;
 
@@ -124,14 +126,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;                                   // global k-block counter of this CTA
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
-                for (int kb = 0; kb < num_k; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
+        // TMA producer: the whole warp walks the loop (waits by all lanes), one elected lane issues
+        const bool leader = elect_one();
+        uint32_t it = 0;                                   // global k-block counter of this CTA
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+            for (int kb = 0; kb < num_k; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                if (leader) {
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                     uint8_t* a = smem + s * STAGE_BYTES;
                     int ka = kb * BK;
@@ -139,33 +143,35 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tma_load_2d(a, &tmA, &full_bar[s], ka, m0);
                     tma_load_2d(a + TILE_A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN, 1, 0, 0);
-            uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t buf = tcount & 1;
-                mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+        const bool leader = elect_one();
+        constexpr uint32_t idesc = make_idesc(BM, BN, 1, 0, 0);
+        const uint64_t desc0 = make_smem_desc(smem_u32(smem), 16, 1024, LAYOUT_SW128);
+        uint32_t it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t buf = tcount & 1;
+            mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1) ^ 1);   // epilogue drained this accumulator
+            tcgen05_fence_after();
+            const uint32_t d = tmem_base + buf * BN;
+            for (int kb = 0; kb < num_k; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&full_bar[s], (it / STAGES) & 1);
                 tcgen05_fence_after();
-                const uint32_t d = tmem_base + buf * BN;
-                for (int kb = 0; kb < num_k; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
-                    tcgen05_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + TILE_A_BYTES;
+                if (leader) {
+                    const uint64_t ad = desc0 + (uint64_t)((s * STAGE_BYTES) >> 4);
+                    const uint64_t bd = ad + (uint64_t)(TILE_A_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024, LAYOUT_SW128);
-                        uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024, LAYOUT_SW128);
-                        umma_f16_ss(d, ad, bd, idesc, (kb | k) ? 1u : 0u);
-                    }
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16_ss(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
                     umma_commit(&empty_bar[s]);                  // smem stage free when these retire
                 }
-                umma_commit(&acc_full[buf]);
+                __syncwarp();
             }
+            if (leader) umma_commit(&acc_full[buf]);
+            __syncwarp();
         }
     } else {
         // epilogue: 8 warps; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) and takes column

@@ -80,7 +80,7 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
     float* sb1 = reinterpret_cast<float*>(smem + OFF_B1);
     float* sb2 = reinterpret_cast<float*>(smem + OFF_B2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
     const int64_t tile0 = (int64_t)blockIdx.x * TM;
 
     for (int i = threadIdx.x; i < HID; i += PE_THREADS) sb1[i] = p.b1[i];
@@ -105,13 +105,17 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
     if (warp == 0) {
         // ---------------- TMA: stream the weights through a 7-stage ring, in the MMA's order ----------------
         // per hidden chunk c: 3 k-blocks of W1[c] (GEMM1), then the 4 half k-blocks of W2[:, c-1] (GEMM2)
-        if (lane == 0) {
+        {                                          // whole warp walks the loop, the elected lane issues
+            const bool leader = elect_one();
             uint32_t it = 0;
             auto load = [&](const CUtensorMap* m, int c0, int c1) {
                 const int st = it % WST;
                 mbar_wait(&w_empty[st], ((it / WST) & 1) ^ 1);
-                mbar_arrive_expect_tx(&w_full[st], WST_BYTES);
-                tma_load_2d(smem + OFF_WR + st * WST_BYTES, m, &w_full[st], c0, c1);
+                if (leader) {
+                    mbar_arrive_expect_tx(&w_full[st], WST_BYTES);
+                    tma_load_2d(smem + OFF_WR + st * WST_BYTES, m, &w_full[st], c0, c1);
+                }
+                __syncwarp();
                 ++it;
             };
             auto load_w2 = [&](int c) {
@@ -126,7 +130,8 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        {                                          // whole warp; tcgen05.mma / commit by the elected lane
+            const bool leader = elect_one();
             constexpr uint32_t idesc = make_idesc(TM, 128, 1, 0, 0);       // every MMA here is 128 x 128 x 16
             const uint64_t a1d = make_smem_desc(smem_u32(smem + OFF_A1), 16, 1024, LAYOUT_SW128);
             const uint64_t wrd = make_smem_desc(smem_u32(smem + OFF_WR), 16, 1024, LAYOUT_SW128);
@@ -139,37 +144,44 @@ position_mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid
                 ++it;
                 return wrd + (uint64_t)((st * WST_BYTES) >> 4);
             };
-            auto release = [&]() { umma_commit(&w_empty[(it - 1) % WST]); };
+            auto release = [&]() { if (leader) umma_commit(&w_empty[(it - 1) % WST]); __syncwarp(); };
             auto gemm2 = [&](int c) {            // O[128 x 256] += Hs[128 x 128] W2[:, c]^T, two 128-column halves
                 mbar_wait(hs_ready, c & 1);
                 tcgen05_fence_after();
                 for (int kb = 0; kb < HC / 64; ++kb)
                     for (int nh = 0; nh < 2; ++nh) {
                         const uint64_t bd = next_stage();
+                        if (leader) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16_ss(tmem_base + TM_O + nh * 128, hsd + (uint64_t)((kb * 16384 + k * 32) >> 4),
-                                        bd + (uint64_t)((k * 32) >> 4), idesc, (c | kb | k) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16_ss(tmem_base + TM_O + nh * 128, hsd + (uint64_t)((kb * 16384 + k * 32) >> 4),
+                                            bd + (uint64_t)((k * 32) >> 4), idesc, (c | kb | k) ? 1u : 0u);
+                        }
                         release();
                     }
-                umma_commit(hs_free);
+                if (leader) umma_commit(hs_free);
+                __syncwarp();
             };
             mbar_wait(a1_ready, 0);
             for (int c = 0; c < NCH; ++c) {
                 mbar_wait(&h_free[c & 1], ((c >> 1) & 1) ^ 1);
                 for (int kb = 0; kb < K1 / 64; ++kb) {
                     const uint64_t bd = next_stage();
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16_ss(tmem_base + TM_H + (c & 1) * HC, a1d + (uint64_t)((kb * 16384 + k * 32) >> 4),
-                                    bd + (uint64_t)((k * 32) >> 4), idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16_ss(tmem_base + TM_H + (c & 1) * HC, a1d + (uint64_t)((kb * 16384 + k * 32) >> 4),
+                                        bd + (uint64_t)((k * 32) >> 4), idesc, (kb | k) ? 1u : 0u);
+                    }
                     release();
                 }
-                umma_commit(&h_full[c & 1]);
+                if (leader) umma_commit(&h_full[c & 1]);
+                __syncwarp();
                 if (c > 0) gemm2(c - 1);
             }
             gemm2(NCH - 1);
-            umma_commit(o_full);
+            if (leader) umma_commit(o_full);
+            __syncwarp();
         }
     } else {
         // ---------------- producer (features) + epilogues: thread <-> token ----------------
