@@ -63,6 +63,9 @@ void petr_launch_count_reset(void);
  * petr_get_tuning returns the current value or -1. */
 int petr_set_tuning(const char* key, int value);
 int petr_get_tuning(const char* key);
+/* Diagnostic: device buffer of int64[4][64][8] that CTA 0 of the tcgen05 GEMM fills with clock64() stamps of
+ * its pipeline events (tools/gemm_trace.py); NULL (default) disables it. */
+void petr_debug_set_trace(void* device_buffer);
 
 /* ---- a4: key-padding masks.  petr_head.py:383-394 (ones(pad) / zero img_shape /
  * F.interpolate nearest / .to(bool)).  img_hw: int32 [B*N*2] = (img_h, img_w) per view.

@@ -25,6 +25,7 @@ SIGNATURES = {
     "petr_launch_count_reset": (None, []),
     "petr_set_tuning": (c_int, [c_char_p, _I]),
     "petr_get_tuning": (c_int, [c_char_p]),
+    "petr_debug_set_trace": (None, [_P]),
     "petr_key_padding_mask": (c_int, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "petr_frustum_features": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P,
                                       _P, _I, _P, _P, _P]),

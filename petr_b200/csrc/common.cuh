@@ -34,6 +34,8 @@ namespace tuning {
 bool flash_exact_only();
 int flash_poly();
 bool gemm_staged();
+bool gemm_coalesce();
+void* debug_trace();
 }  // namespace tuning
 
 #define PETR_REQUIRE(cond, code, ...) \

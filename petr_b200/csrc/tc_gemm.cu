@@ -63,6 +63,8 @@ struct EpiParams {
     void* C; void* C2; int ldc; int out_mode;
     int M, N, K; int a_k_wrap; int kv_Lk; int kv_B; int kv_E;
     int tiles_m, tiles_n;
+    long long* trace;  // diagnostic clock64 stamps of CTA 0 (petr_debug_set_trace), normally null
+    int coalesce;      // transposing (coalesced) epilogue allowed: 16-byte aligned bases, ldc % 4 == 0, N % 4 == 0
     int staged;        // out_mode 2: stage each warp's 32 x 32 bf16 chunk in smem and write it with one bulk copy
 };
 
@@ -88,6 +90,11 @@ __device__ __forceinline__ void store_split_bf16x32(__nv_bfloat16* hp, __nv_bflo
     }
 }
 
+#define GEMM_TR(role, t, ev) do { if (p.trace && blockIdx.x == 0 && (t) < 64) p.trace[((role) * 64 + (t)) * 8 + (ev)] = clock64(); } while (0)
+
+// One instantiation per output mode: with all five store paths in one kernel the epilogue alone was ~70 KB of
+// SASS, far beyond the 32 KB instruction cache (measured: 3 300 clk per 32-column chunk in single-tile GEMMs).
+template <int OM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     EpiParams p) {
@@ -129,13 +136,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // TMA producer: the whole warp walks the loop (waits by all lanes), one elected lane issues
         const bool leader = elect_one();
         uint32_t it = 0;                                   // global k-block counter of this CTA
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t ttile = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ttile) {
             const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
             for (int kb = 0; kb < num_k; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (leader) {
+                    if (kb < 4) GEMM_TR(0, ttile, kb);
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                     uint8_t* a = smem + s * STAGE_BYTES;
                     int ka = kb * BK;
@@ -155,12 +164,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t buf = tcount & 1;
             mbar_wait(&acc_empty[buf], ((tcount >> 1) & 1) ^ 1);   // epilogue drained this accumulator
             tcgen05_fence_after();
+            if (leader) GEMM_TR(1, tcount, 0);
             const uint32_t d = tmem_base + buf * BN;
             for (int kb = 0; kb < num_k; ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&full_bar[s], (it / STAGES) & 1);
                 tcgen05_fence_after();
                 if (leader) {
+                    if (kb < 4) GEMM_TR(1, tcount, 1 + kb);
                     const uint64_t ad = desc0 + (uint64_t)((s * STAGE_BYTES) >> 4);
                     const uint64_t bd = ad + (uint64_t)(TILE_A_BYTES >> 4);
 #pragma unroll
@@ -170,7 +181,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 __syncwarp();
             }
-            if (leader) umma_commit(&acc_full[buf]);
+            if (leader) { umma_commit(&acc_full[buf]); GEMM_TR(1, tcount, 5); }
             __syncwarp();
         }
     } else {
@@ -204,24 +215,45 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (nn < p.N) next_bias = __ldg(p.bias + nn);
                 }
             }
+            const bool tr = lane == 0 && quarter == 0;
+            const int trole = 2 + chalf;
+            if (tr) GEMM_TR(trole, tcount, 0);
             mbar_wait(&acc_full[buf], (tcount >> 1) & 1);
             tcgen05_fence_after();
+            if (tr) GEMM_TR(trole, tcount, 1);
             int kv_b = 0, kv_key = 0;
-            if ((p.out_mode == 2 || p.out_mode == 4) && m < p.M) { kv_b = m / p.kv_Lk; kv_key = m - kv_b * p.kv_Lk; }
+            if ((OM == 2 || OM == 4) && m < p.M) { kv_b = m / p.kv_Lk; kv_key = m - kv_b * p.kv_Lk; }
             // staged output (out_mode 2): decided per warp here, where all 32 lanes are still together
             const int key0w = __shfl_sync(0xffffffffu, kv_key, 0);
             const bool slab = p.staged && (m0 + quarter * 32 + 32 <= p.M) && (key0w + 32 <= p.kv_Lk);
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + chalf * 128;
             uint32_t rbuf[2][32];
             tmem_ld_x32(t_addr, rbuf[0]);
+#pragma unroll 1
+            for (int cpair = 0; cpair < 2; ++cpair) {
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int ci = 0; ci < 2; ++ci) {
+                const int cc = cpair * 2 + ci;
                 const int c = chalf * 4 + cc;
-                uint32_t* r = rbuf[cc & 1];
+                uint32_t* r = rbuf[ci];
+                // residual of this chunk in the coalesced (transposed) pattern, requested before the TMEM wait so
+                // that its L2 latency overlaps the accumulator load and the bias / activation math
+                float4 res4[8];
+                const bool coal = p.coalesce && (n0 + c * 32 + 32 <= p.N) && OM != 2;
+                if (coal && p.residual) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int mr = m0 + quarter * 32 + (q & 3) * 8 + (lane >> 2);
+                        const int col = n0 + c * 32 + (q >> 2) * 16 + (lane & 3) * 4;
+                        res4[q] = (mr < p.M) ? __ldg(reinterpret_cast<const float4*>(p.residual + (int64_t)mr * p.ldc + col))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
                 tmem_ld_wait();
-                if (cc + 1 < 4) tmem_ld_x32(t_addr + (cc + 1) * 32, rbuf[(cc + 1) & 1]);
+                if (tr) GEMM_TR(trole, tcount, 2 + cc);
+                if (cc + 1 < 4) tmem_ld_x32(t_addr + (cc + 1) * 32, rbuf[ci ^ 1]);
                 const int nb = n0 + c * 32;
-                if (m >= p.M || nb >= p.N) continue;
+                if (nb >= p.N) continue;
                 const bool full = (nb + 32 <= p.N);
                 float v[32];
 #pragma unroll
@@ -229,9 +261,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (p.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 t;                                    // explicit ld.shared (the generic form was an LD.E)
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                     : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(sb + (c * 32 + j) * 4));
+                        const float4 t = ld_shared_f32x4(sb + (c * 32 + j) * 4);
                         v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
                     }
                 }
@@ -243,6 +273,62 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
                 }
+                if (coal) {
+                    // Coalesced stores: a thread owns one ROW of the accumulator (TMEM lane), so direct stores put
+                    // 16 bytes into each of 32 different lines per instruction (measured: the epilogue, not the
+                    // MMA, paced every GEMM -- 2 700 clk per 32-column chunk for bf16 rows, 4 300 for fp32 rows).
+                    // The warp's 32 x 32 block is transposed through a 2 KB shared-memory slab (16 columns at a
+                    // time, XOR-swizzled: conflict-free both ways) so that each store / residual-load instruction
+                    // covers 8 rows x 64 contiguous bytes.
+                    const uint32_t sw = smem_u32(stage_out) + (warp - 2) * 2048;
+                    const int mw = m0 + quarter * 32;
+                    const int l = nb / p.kv_E, h = (nb % p.kv_E) >> 5;           // out_mode 4: chunk = one head
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            st_shared_v4(sw + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
+                                         __float_as_uint(v[16 * hh + 4 * j]), __float_as_uint(v[16 * hh + 4 * j + 1]),
+                                         __float_as_uint(v[16 * hh + 4 * j + 2]), __float_as_uint(v[16 * hh + 4 * j + 3]));
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int rl = i * 8 + (lane >> 2), piece = lane & 3;
+                            float4 x = ld_shared_f32x4(sw + rl * 64 + ((piece ^ ((rl >> 1) & 3)) << 4));
+                            const int mr = mw + rl;
+                            if (mr >= p.M) continue;
+                            const int col = nb + hh * 16 + piece * 4;
+                            if (p.residual) {
+                                const float4 q4 = res4[hh * 4 + i];
+                                x.x += q4.x; x.y += q4.y; x.z += q4.z; x.w += q4.w;
+                            }
+                            if (OM == 0) {
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (int64_t)mr * p.ldc + col) = x;
+                            } else if (OM == 1) {
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)mr * p.ldc + col) =
+                                    make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+                            } else {
+                                uint2 hi, lo;
+                                split_bf16x2(x.x, x.y, hi.x, lo.x);
+                                split_bf16x2(x.z, x.w, hi.y, lo.y);
+                                if (OM == 3) {
+                                    if (p.C2) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C2) + (int64_t)mr * p.ldc + col) = x;
+                                    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)mr * (2 * p.N) + col;
+                                    *reinterpret_cast<uint2*>(cp) = hi;
+                                    *reinterpret_cast<uint2*>(cp + p.N) = lo;
+                                } else {                                      // out_mode 4
+                                    const int bb = mr / p.kv_Lk, key = mr - bb * p.kv_Lk;
+                                    const int64_t off = ((((int64_t)l * p.kv_B + bb) * (p.kv_E >> 5) + h) * p.kv_Lk + key) * 32 + (col & 31);
+                                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = hi;
+                                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C2) + off) = lo;
+                                }
+                            }
+                        }
+                    }
+                    continue;
+                }
+                if (m >= p.M) continue;
                 if (p.residual) {
                     const float* rp = p.residual + (int64_t)m * p.ldc + nb;
                     if (full && ((p.ldc & 3) == 0)) {
@@ -256,8 +342,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int j = 0; j < 32; ++j) if (nb + j < p.N) v[j] += rp[j];
                     }
                 }
-                if (p.out_mode == 0 || (p.out_mode == 3 && p.C2)) {
-                    float* cp = reinterpret_cast<float*>(p.out_mode == 0 ? p.C : p.C2) + (int64_t)m * p.ldc + nb;
+                if (OM == 0 || (OM == 3 && p.C2)) {
+                    float* cp = reinterpret_cast<float*>(OM == 0 ? p.C : p.C2) + (int64_t)m * p.ldc + nb;
                     if (full && ((p.ldc & 3) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -267,14 +353,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         for (int j = 0; j < 32; ++j) if (nb + j < p.N) cp[j] = v[j];
                     }
                 }
-                if (p.out_mode == 1) {
+                if (OM == 1) {
                     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m * p.ldc + nb;
                     if (full && ((p.ldc & 7) == 0)) store_bf16x32(cp, v);
                     else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (nb + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
                     }
-                } else if (p.out_mode == 2) {
+                } else if (OM == 2) {
                     // head-split layout [n / E][b][head][key][32]; a 32-column chunk is one head
                     const int l = nb / p.kv_E, h = (nb % p.kv_E) >> 5;
                     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) +
@@ -299,20 +385,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     } else {
                         store_bf16x32(cp, v);
                     }
-                } else if (p.out_mode == 4) {
+                } else if (OM == 4) {
                     // head-split [hi | lo] pair: C = hi array, C2 = lo array, both [n / E][b][head][key][32]
                     const int l = nb / p.kv_E, h = (nb % p.kv_E) >> 5;
                     const int64_t off = ((((int64_t)l * p.kv_B + kv_b) * (p.kv_E >> 5) + h) * p.kv_Lk + kv_key) * 32;
                     store_split_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.C) + off,
                                         reinterpret_cast<__nv_bfloat16*>(p.C2) + off, v);
-                } else if (p.out_mode == 3) {
+                } else if (OM == 3) {
                     // bf16 split [hi | lo] for the bf16x3 GEMMs: row m, hi at [nb], lo at [N + nb]
                     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m * (2 * p.N) + nb;
                     store_split_bf16x32(cp, cp + p.N, v);
                 }
             }
+            }
             tcgen05_fence_before();
             mbar_arrive(&acc_empty[buf]);
+            if (tr) GEMM_TR(trole, tcount, 6);
             if (p.bias) sbias[(buf ^ 1) * BN + et] = next_bias;     // read after the next tile's barrier
         }
         if (p.staged && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -375,6 +463,10 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     p.C = C; p.C2 = C2; p.ldc = ldc; p.out_mode = out_mode;
     p.M = M; p.N = N; p.K = K; p.a_k_wrap = a_k_wrap;
     p.staged = (out_mode == 2 && tuning::gemm_staged()) ? 1 : 0;
+    p.trace = (long long*)tuning::debug_trace();
+    p.coalesce = (tuning::gemm_coalesce() && aligned16(C) && (!C2 || aligned16(C2)) && (!residual || aligned16(residual)) &&
+                  (N % 4) == 0 && ((out_mode == 4) || (ldc % 4) == 0)) ? 1 : 0;
+    if (out_mode != 2 && out_mode != 4) p.kv_E = 256;
     if (out_mode == 2 || out_mode == 4) {
         if (out_mode == 4) PETR_REQUIRE(C2 && aligned16(C2), PETR_E_BADARG, "petr_gemm_bf16_tc: out_mode 4 needs C2 (lo array)");
         PETR_REQUIRE(kv_Lk > 0 && M % kv_Lk == 0 && N % 256 == 0 && !residual, PETR_E_SHAPE,
@@ -395,7 +487,11 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     if (rc) return rc;
     rc = tmap::encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, dB, sB, boxB, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, EpiParams);
+    static const gemm_fn fns[5] = {gemm_bf16_tc_kernel<0>, gemm_bf16_tc_kernel<1>, gemm_bf16_tc_kernel<2>,
+                                   gemm_bf16_tc_kernel<3>, gemm_bf16_tc_kernel<4>};
+    const gemm_fn fn = fns[out_mode];
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     if (e != cudaSuccess) return fail((int)e, "petr_gemm_bf16_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     p.tiles_m = (M + BM - 1) / BM;
     p.tiles_n = (N + BN - 1) / BN;
@@ -404,6 +500,6 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int tiles = p.tiles_m * p.tiles_n;
     int grid = tiles < sms ? tiles : sms;
-    gemm_bf16_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, p);
+    fn<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, p);
     return after_launch("petr_gemm_bf16_tc");
 }

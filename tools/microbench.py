@@ -84,9 +84,36 @@ def kproj(args):
     _lib.set_tuning("gemm_staged", 1)
 
 
+def qside(args):
+    """The query-side bf16x3 GEMM shapes of one decoder layer (M = B * 900 rows)."""
+    M = args.batch * 900
+    g = torch.Generator(device=DEV).manual_seed(1)
+    X = torch.randn(M, 256, generator=g, device=DEV)
+    Xs = ops.split_rows(X)
+    H = torch.randn(M, 2048, generator=g, device=DEV)
+    Hs = ops.split_rows(H)
+    w256 = ops.x3_weight(torch.randn(256, 256, generator=g, device=DEV) / 16)
+    w512 = ops.x3_weight(torch.randn(512, 256, generator=g, device=DEV) / 16)
+    wf1 = ops.x3_weight(torch.randn(2048, 256, generator=g, device=DEV) / 16)
+    wf2 = ops.x3_weight(torch.randn(256, 2048, generator=g, device=DEV) / 45)
+    b256 = torch.randn(256, device=DEV); b512 = torch.randn(512, device=DEV); b2048 = torch.randn(2048, device=DEV)
+    cases = {
+        "proj256_res_f32": lambda: ops.gemm_bf16_tc(Xs, w256, b256, residual=X, x3=True),
+        "qk512_headsplit_pair": lambda: ops.gemm_bf16_tc(Xs, w512, b512, x3=True, headsplit_Lk=900, headsplit_pair=True),
+        "ffn1_relu_split": lambda: ops.gemm_bf16_tc(Xs, wf1, b2048, act=ops.ACT_RELU, x3=True, split_out=True),
+        "ffn2_res_f32": lambda: ops.gemm_bf16_tc(Hs, wf2, b256, residual=X, x3=True),
+    }
+    for coal in (0, 1):
+        _lib.set_tuning("gemm_coalesce", coal)
+        for name, fn in cases.items():
+            med, best = timeit(fn, iters=20)
+            print(json.dumps(dict(kernel="qside", case=name, coalesce=coal, M=M, us_median=med * 1e3, us_best=best * 1e3)), flush=True)
+    _lib.set_tuning("gemm_coalesce", 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["flash", "kproj", "all"])
+    ap.add_argument("what", choices=["flash", "kproj", "qside", "all"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--keys", type=int, default=24000)
     ap.add_argument("--nsplit", type=int, default=0)
@@ -96,6 +123,8 @@ def main():
         flash(args)
     if args.what in ("kproj", "all"):
         kproj(args)
+    if args.what in ("qside", "all"):
+        qside(args)
 
 
 if __name__ == "__main__":
