@@ -163,6 +163,24 @@ int petr_add_rows_bf16(const float* X, const float* add, int add_rows, void* out
 int petr_decode_boxes(float* reg, const float* ref, const float* h_pc_range,
                       const float* time_div, int L, int B, int Q, int code_size, void* stream);
 
+/* ---- f1: NMS-free box decoding.  NMSFreeCoder.decode_single
+ * (core/bbox/coders/nms_free_coder.py:48-101) for every sample of the batch in one launch: sigmoid ->
+ * top-max_num over the Q*C (query, class) scores -> label = idx %% C, query = idx / C -> gather the query's box ->
+ * denormalize_bbox (core/bbox/util.py:63-87: (cx, cy, log w, log l, cz, log h, sin, cos[, vx, vy]) ->
+ * (cx, cy, cz, w, l, h, atan2(sin, cos)[, vx, vy])) -> keep = centre inside h_post_center_range[6] (host)
+ * [&& score > score_threshold when has_score_threshold]; bottom_center != 0 additionally applies
+ * PETRHead.get_bboxes' z -= h / 2 (petr_head.py:744) after the range test.
+ *   cls_scores fp32 [B, Q, C] (logits of the last decoder layer), bbox_preds fp32 [B, Q, code], code 8 or 10.
+ * Outputs are padded to max_num rows per sample, sorted by descending score (ties: lower flat index first):
+ *   out_boxes fp32 [B, max_num, code > 8 ? 9 : 7], out_scores fp32 [B, max_num], out_labels / out_index int64
+ *   [B, max_num] (class, query), out_mask uint8 [B, max_num] (1 = kept), out_count int32 [B] (kept rows).
+ * Labels / indices are integer-exact (ranking on the logits); Q*C <= 16384. */
+int petr_nms_free_decode(const float* cls_scores, const float* bbox_preds, int B, int Q, int C, int code,
+                         int max_num, const float* h_post_center_range, int has_score_threshold,
+                         float score_threshold, int bottom_center, float* out_boxes, float* out_scores,
+                         int64_t* out_labels, int64_t* out_index, uint8_t* out_mask, int32_t* out_count,
+                         void* stream);
+
 /* ---- tcgen05 tier (sm_100a tensor cores, TMA-fed, TMEM accumulators) ----------------- */
 
 /* fp32 NCHW feature maps x[G][C][hw] -> bf16 token-major out[G*hw][C] (A operand of input_proj,
@@ -181,7 +199,10 @@ int petr_nchw_to_tokens_bf16(const float* x, void* out, int G, int C, int hw, vo
  *      key = m % kv_Lk -- the Q/K/V layout petr_cross_attention_bf16 reads;
  *   3: bf16 split C[m*2N + n] = hi, C[m*2N + N + n] = lo, plus (C2 nullable) fp32 C2[m*ldc+n];
  *   4: head-split [hi | lo] pair: C = hi array, C2 = lo array, both in the layout of mode 2 (the
- *      operands of petr_attention_x3_tc).
+ *      operands of petr_attention_x3_tc);
+ *   5: two results from one accumulator: C = bf16 [m*N + n] of alpha*act(acc + bias) WITHOUT the residual and
+ *      C2 = fp32 [m*ldc + n] WITH residual[(m %% kv_Lk)*ldc + n] added -- input_proj emitting the V-projection
+ *      operand and "memory + batch-invariant sine embedding" (the K-side residual of the position MLP) at once.
  * residual (nullable, fp32, ldc) is added after alpha.  Used for the K/V projection of all
  * decoder layers in one launch (petr_transformer.py:341-344,:357-360), the position_encoder /
  * adapt_pos3d MLPs, input_proj and the query-side projections / FFN. */

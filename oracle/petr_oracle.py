@@ -351,3 +351,37 @@ def head_forward(sd: Dict[str, Tensor], feats: Tensor, img_metas: List[dict],
     box[..., 1:2] = box[..., 1:2] * (pc[4] - pc[1]) + pc[1]
     box[..., 4:5] = box[..., 4:5] * (pc[5] - pc[2]) + pc[2]
     return dict(all_cls_scores=cls, all_bbox_preds=box, enc_cls_scores=None, enc_bbox_preds=None)
+
+
+# ------------------------------------------------------------------------------------------
+# NMSFreeCoder.decode / PETRHead.get_bboxes (post-processing right behind the head)
+# ------------------------------------------------------------------------------------------
+def denormalize_bbox(n: Tensor) -> Tensor:
+    """core/bbox/util.py:63-87: (cx, cy, log w, log l, cz, log h, sin, cos[, vx, vy]) ->
+    (cx, cy, cz, w, l, h, rot[, vx, vy])."""
+    rot = torch.atan2(n[..., 6:7], n[..., 7:8])
+    parts = [n[..., 0:1], n[..., 1:2], n[..., 4:5], n[..., 2:3].exp(), n[..., 3:4].exp(), n[..., 5:6].exp(), rot]
+    if n.size(-1) > 8:
+        parts += [n[..., 8:9], n[..., 9:10]]
+    return torch.cat(parts, dim=-1)
+
+
+def nms_free_decode(cls_scores: Tensor, bbox_preds: Tensor, max_num: int, num_classes: int,
+                    post_center_range, score_threshold=None, bottom_center: bool = False) -> List[dict]:
+    """nms_free_coder.py:48-119 (decode_single per sample) [+ petr_head.py:744 when bottom_center].
+    cls_scores (B, Q, C) logits, bbox_preds (B, Q, code).  Also returns the query index of every kept box."""
+    out = []
+    rng = torch.tensor(list(post_center_range), dtype=bbox_preds.dtype)
+    for b in range(cls_scores.shape[0]):
+        scores, indexs = cls_scores[b].sigmoid().view(-1).topk(max_num)
+        labels = indexs % num_classes
+        bbox_index = indexs // num_classes
+        boxes = denormalize_bbox(bbox_preds[b][bbox_index])
+        mask = (boxes[..., :3] >= rng[:3]).all(1) & (boxes[..., :3] <= rng[3:]).all(1)
+        if score_threshold:
+            mask &= scores > score_threshold
+        boxes = boxes[mask]
+        if bottom_center:
+            boxes[:, 2] = boxes[:, 2] - boxes[:, 5] * 0.5
+        out.append(dict(bboxes=boxes, scores=scores[mask], labels=labels[mask], index=bbox_index[mask]))
+    return out

@@ -245,7 +245,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int q = 0; q < 8; ++q) {
                         const int mr = m0 + quarter * 32 + (q & 3) * 8 + (lane >> 2);
                         const int col = n0 + c * 32 + (q >> 2) * 16 + (lane & 3) * 4;
-                        res4[q] = (mr < p.M) ? __ldg(reinterpret_cast<const float4*>(p.residual + (int64_t)mr * p.ldc + col))
+                        const int rr = (OM == 5) ? mr % p.kv_Lk : mr;          // mode 5: residual rows repeat with period kv_Lk
+                        res4[q] = (mr < p.M) ? __ldg(reinterpret_cast<const float4*>(p.residual + (int64_t)rr * p.ldc + col))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
@@ -299,6 +300,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             const int mr = mw + rl;
                             if (mr >= p.M) continue;
                             const int col = nb + hh * 16 + piece * 4;
+                            if (OM == 5) {                                    // bf16 without, fp32 with the residual
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)mr * p.N + col) =
+                                    make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+                                const float4 q4 = res4[hh * 4 + i];
+                                x.x += q4.x; x.y += q4.y; x.z += q4.z; x.w += q4.w;
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C2) + (int64_t)mr * p.ldc + col) = x;
+                                continue;
+                            }
                             if (p.residual) {
                                 const float4 q4 = res4[hh * 4 + i];
                                 x.x += q4.x; x.y += q4.y; x.z += q4.z; x.w += q4.w;
@@ -457,7 +466,7 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     PETR_REQUIRE(lda >= a_k_wrap && ldw >= K && (lda % 8) == 0 && (ldw % 8) == 0 && aligned16(A) && aligned16(W),
                  PETR_E_ALIGN, "petr_gemm_bf16_tc: A/W rows must be 16-byte aligned");
     PETR_REQUIRE(act == PETR_ACT_NONE || act == PETR_ACT_RELU, PETR_E_BADARG, "petr_gemm_bf16_tc: bad act");
-    PETR_REQUIRE(out_mode >= 0 && out_mode <= 4, PETR_E_BADARG, "petr_gemm_bf16_tc: bad out_mode");
+    PETR_REQUIRE(out_mode >= 0 && out_mode <= 5, PETR_E_BADARG, "petr_gemm_bf16_tc: bad out_mode");
     EpiParams p{};
     p.bias = bias; p.residual = residual; p.act = act; p.alpha = alpha;
     p.C = C; p.C2 = C2; p.ldc = ldc; p.out_mode = out_mode;
@@ -488,8 +497,12 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     rc = tmap::encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, dB, sB, boxB, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, EpiParams);
-    static const gemm_fn fns[5] = {gemm_bf16_tc_kernel<0>, gemm_bf16_tc_kernel<1>, gemm_bf16_tc_kernel<2>,
-                                   gemm_bf16_tc_kernel<3>, gemm_bf16_tc_kernel<4>};
+    static const gemm_fn fns[6] = {gemm_bf16_tc_kernel<0>, gemm_bf16_tc_kernel<1>, gemm_bf16_tc_kernel<2>,
+                                   gemm_bf16_tc_kernel<3>, gemm_bf16_tc_kernel<4>, gemm_bf16_tc_kernel<5>};
+    if (out_mode == 5)
+        PETR_REQUIRE(p.coalesce && C2 && residual && kv_Lk > 0 && N % 32 == 0 && ldc >= N && aligned16(C), PETR_E_SHAPE,
+                     "petr_gemm_bf16_tc: out_mode 5 needs C2, a residual with period kv_Lk, N %% 32 == 0 and 16-byte aligned bases");
+    if (out_mode == 5) p.kv_Lk = kv_Lk;
     const gemm_fn fn = fns[out_mode];
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     if (e != cudaSuccess) return fail((int)e, "petr_gemm_bf16_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -129,12 +129,6 @@ def key_side_tc(eng, x, mi: MetaInputs, taps=None, views: slice = None):
     N = x.shape[1]
     Lk = N * H * W
     has_mask = mi.has_mask
-    # input_proj (petr_head.py:390): fp32 NCHW -> bf16 tokens -> tcgen05 GEMM; mem kept in fp32 (for
-    # the K input mem + pos) and as bf16 [hi | lo] whose hi half is the V-projection operand
-    xt = ops.nchw_to_tokens_bf16(x.view(B * N, Cin, H, W))
-    mem = torch.empty((B * Lk, E), dtype=torch.float32, device=dev)
-    mem_split = ops.gemm_bf16_tc(xt, T["in_w"], P["in_b"], split_out=True, out_f32=mem, name="gemm_input_proj")
-    vin = mem_split[:, :E]
     # Sine encoding + adapt_pos3d (petr_head.py:399-402).  It depends on the key masks only; when every
     # sample of the batch has the same img_shape list (all shipped configs: no padding at all) the
     # masks are identical per sample, so the (Lk, 256) result is evaluated once per forward for one
@@ -146,19 +140,28 @@ def key_side_tc(eng, x, mi: MetaInputs, taps=None, views: slice = None):
         sf = sf.view(m_sine.shape[0], N_all, H * W, -1)[:, views].reshape(m_sine.shape[0] * Lk, -1).contiguous()
     h2 = ops.gemm_bf16_tc(sf, T["ad_w1"], P["ad_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_adapt1")
     sin1 = ops.gemm_bf16_tc(h2, T["ad_w2"], P["ad_b2"], name="gemm_adapt2") if dedup else None   # (Lk, E) fp32
+    fused = s.with_position and FUSED_POSITION_MLP and s.D == 64 and tuple(T["pe_w1"].shape) == (1024, 192) and \
+        tuple(T["pe_w2"].shape) == (256, 1024)
+    # input_proj (petr_head.py:390): fp32 NCHW -> bf16 tokens -> tcgen05 GEMM.  One accumulator, two results
+    # (out_mode 5): the bf16 tokens that feed the V projection, and fp32 "memory + broadcast sine embedding", the
+    # single residual of the fused position MLP whose bf16 output is then directly the K-projection input.
+    xt = ops.nchw_to_tokens_bf16(x.view(B * N, Cin, H, W))
+    mem = torch.empty((B * Lk, E), dtype=torch.float32, device=dev)
+    fold_sine = dedup and fused and not s.with_fpe
+    if fold_sine:
+        vin = ops.gemm_bf16_tc(xt, T["in_w"], P["in_b"], residual=sin1, residual_period=Lk, out_f32=mem,
+                               name="gemm_input_proj")
+    else:
+        vin = ops.gemm_bf16_tc(xt, T["in_w"], P["in_b"], split_out=True, out_f32=mem, name="gemm_input_proj")[:, :E]
     kin = None
     if s.with_position:
-        fused = FUSED_POSITION_MLP and s.D == 64 and tuple(T["pe_w1"].shape) == (1024, 192) and \
-            tuple(T["pe_w2"].shape) == (256, 1024)
         res = None if s.with_fpe else mem                       # mem + position MLP in the epilogue
         if fused:
             # K1: frustum -> inverse_sigmoid -> MLP in one tcgen05 kernel, nothing intermediate in HBM
-            if dedup and not s.with_fpe:
-                # ... and with the broadcast sine embedding as a second residual the bf16 output is
-                # directly the K-projection input mem + pos_embed
+            if fold_sine:
                 kin = ops.position_mlp_fused(mi.i2l, H, W, s.D, mi.pad_h, mi.pad_w, s.lid, s.depth_start,
                                              s.bin_size, s.position_range, T["pe_w1"], P["pe_b1"], T["pe_w2"],
-                                             P["pe_b2"], residual=mem, residual2=sin1, want_f32=False,
+                                             P["pe_b2"], residual=mem, want_f32=False,
                                              out_bf16=torch.empty((B * Lk, E), dtype=torch.bfloat16, device=dev))
             else:
                 pos = ops.position_mlp_fused(mi.i2l, H, W, s.D, mi.pad_h, mi.pad_w, s.lid, s.depth_start,
@@ -181,7 +184,7 @@ def key_side_tc(eng, x, mi: MetaInputs, taps=None, views: slice = None):
     Kh = ops.gemm_bf16_tc(kin, T["wk"], T["bk"], headsplit_Lk=Lk, name="gemm_kproj")
     Vh = ops.gemm_bf16_tc(vin, T["wv"], T["bv"], headsplit_Lk=Lk, name="gemm_vproj")
     if taps is not None:
-        taps.update(masks=masks, memory=mem, kin=kin, Kh=Kh, Vh=Vh)
+        taps.update(masks=masks, memory=None if fold_sine else mem, kin=kin, Kh=Kh, Vh=Vh)
     kmask = masks.view(B, Lk) if has_mask else None
     nsplit = choose_nsplit(B, s.heads, s.Lq, Lk)
     partial = None

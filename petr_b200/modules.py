@@ -443,23 +443,12 @@ class LearnedPositionalEncoding3D(BaseModule):
 # ------------------------------------------------------------------------------------------
 # bbox coder (pc_range holder; decode is the first 'next' row of SURVEY.md section 8f)
 # ------------------------------------------------------------------------------------------
-def denormalize_bbox(normalized_bboxes: torch.Tensor) -> torch.Tensor:
-    """core/bbox/util.py:63-87: (cx, cy, log w, log l, cz, log h, sin, cos[, vx, vy]) ->
-    (cx, cy, cz, w, l, h, rot[, vx, vy])."""
-    n = normalized_bboxes
-    rot = torch.atan2(n[..., 6:7], n[..., 7:8])
-    parts = [n[..., 0:1], n[..., 1:2], n[..., 4:5], n[..., 2:3].exp(), n[..., 3:4].exp(), n[..., 5:6].exp(), rot]
-    if n.size(-1) > 8:
-        parts += [n[..., 8:9], n[..., 9:10]]
-    return torch.cat(parts, dim=-1)
-
-
 @BBOX_CODERS.register_module()
 class NMSFreeCoder:
-    """nms_free_coder.py:18-119.  Holds pc_range for the head and decodes the last decoder
-    layer's predictions: sigmoid -> top-`max_num` over queries x classes -> denormalise ->
-    post_center_range (and score) filter.  Post-processing downstream of the hot path (SURVEY 8f
-    row 1): plain torch tensor ops, vectorised over the batch (one top-k for all samples)."""
+    """nms_free_coder.py:18-119.  Holds pc_range for the head and decodes the last decoder layer's
+    predictions: sigmoid -> top-`max_num` over queries x classes -> denormalise -> post_center_range
+    (and score) filter -- ONE kernel launch for the whole batch (petr_nms_free_decode).
+    CUDA tensors only: like every module of this package there is no CPU / PyTorch fallback."""
 
     def __init__(self, pc_range, voxel_size=None, post_center_range=None, max_num=100,
                  score_threshold=None, num_classes=10):
@@ -473,23 +462,25 @@ class NMSFreeCoder:
     def encode(self):
         pass
 
-    def _decode_batch(self, cls_scores: torch.Tensor, bbox_preds: torch.Tensor):
-        """cls_scores (B, Q, C), bbox_preds (B, Q, code) -> list of dicts."""
+    def decode_padded(self, cls_scores: torch.Tensor, bbox_preds: torch.Tensor, bottom_center: bool = False):
+        """Graph-capturable form: fixed-shape outputs (boxes (B,max_num,9), scores, labels, query index, keep-mask,
+        kept-count), rows sorted by descending score; no host synchronisation."""
         if self.post_center_range is None:
             raise NotImplementedError('Need to reorganize output as a batch, only support '
                                       'post_center_range is not None for now!')
-        B = cls_scores.shape[0]
-        scores, indexs = cls_scores.sigmoid().reshape(B, -1).topk(self.max_num, dim=1)
-        labels = indexs % self.num_classes
-        bbox_index = indexs // self.num_classes
-        boxes = torch.gather(bbox_preds, 1, bbox_index[..., None].expand(-1, -1, bbox_preds.shape[-1]))
-        boxes = denormalize_bbox(boxes)
-        rng = torch.as_tensor(self.post_center_range, dtype=boxes.dtype, device=boxes.device)
-        mask = (boxes[..., :3] >= rng[:3]).all(-1) & (boxes[..., :3] <= rng[3:]).all(-1)
-        if self.score_threshold:
-            mask &= scores > self.score_threshold
+        if not cls_scores.is_cuda:
+            raise RuntimeError("petr_b200: NMSFreeCoder.decode needs CUDA tensors (no CPU fallback)")
+        if cls_scores.shape[-1] != self.num_classes:
+            raise ValueError(f"cls_scores has {cls_scores.shape[-1]} classes, coder was built for {self.num_classes}")
+        return ops.nms_free_decode(cls_scores, bbox_preds, self.max_num, self.post_center_range,
+                                   self.score_threshold if self.score_threshold else None, bottom_center)
+
+    def _decode_batch(self, cls_scores: torch.Tensor, bbox_preds: torch.Tensor, bottom_center: bool = False):
+        """cls_scores (B, Q, C), bbox_preds (B, Q, code) -> list of dicts (variable length per sample, as the
+        reference returns them: the boolean selection below is the one data-dependent step)."""
+        boxes, scores, labels, _, mask, _ = self.decode_padded(cls_scores, bbox_preds, bottom_center)
         return [dict(bboxes=boxes[b][mask[b]], scores=scores[b][mask[b]], labels=labels[b][mask[b]])
-                for b in range(B)]
+                for b in range(boxes.shape[0])]
 
     def decode_single(self, cls_scores, bbox_preds):
         return self._decode_batch(cls_scores[None], bbox_preds[None])[0]
@@ -690,11 +681,11 @@ class _PETRHeadBase(BaseModule):
         """petr_head.py:731-751: NMS-free decode of the last layer, gravity centre -> bottom centre,
         wrapped in each sample's `box_type_3d` (left as a plain tensor when img_metas carries none,
         e.g. without mmdet3d)."""
-        preds = self.bbox_coder.decode(preds_dicts)
+        preds = self.bbox_coder._decode_batch(preds_dicts['all_cls_scores'][-1], preds_dicts['all_bbox_preds'][-1],
+                                              bottom_center=True)          # z -= h / 2 inside the kernel
         ret_list = []
         for i, pr in enumerate(preds):
             bboxes = pr['bboxes']
-            bboxes[:, 2] = bboxes[:, 2] - bboxes[:, 5] * 0.5
             box_type = img_metas[i].get('box_type_3d') if img_metas is not None else None
             if box_type is not None:
                 bboxes = box_type(bboxes, bboxes.size(-1))

@@ -224,7 +224,7 @@ OUT_SPLIT = 3
 def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, act=ACT_NONE,
                  alpha: float = 1.0, out=None, out_dtype=torch.float32, headsplit_Lk: int = 0,
                  split_out: bool = False, out_f32=None, x3: bool = False, headsplit_pair: bool = False,
-                 name: str = "gemm_bf16_tc"):
+                 residual_period: int = 0, name: str = "gemm_bf16_tc"):
     """C = alpha * act(A @ W.T + bias) (+ residual) on tcgen05; A (M,Ka) bf16, W (N,K) bf16.
     x3: A is a split (M, 2*K0) [hi | lo] activation and W an x3_weight (N, 3*K0).
     headsplit_Lk > 0: bf16 output in the [N/256][B][8][Lk][32] Q/K/V layout.
@@ -241,6 +241,16 @@ def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, 
     else:
         assert A.shape[1] == K
     C2 = None
+    if residual_period > 0:
+        # out_mode 5: bf16 result without the residual + fp32 result with residual[m % period]
+        assert residual is not None and out_f32 is not None and residual.shape[0] == residual_period
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=A.device)
+        with _Timed(name):
+            call("petr_gemm_bf16_tc", ptr(A), A.stride(0), wrap, ptr(W), W.stride(0), ptr(bias), ptr(residual),
+                 act, float(alpha), ptr(out), ptr(out_f32), out_f32.stride(0), 5, M, N, K, int(residual_period),
+                 stream_ptr(A.device))
+        return out
     if headsplit_Lk > 0 and headsplit_pair:
         # (hi, lo) pair stacked on a leading axis: out[0] = hi, out[1] = lo, each [N/256][B][8][L][32]
         B = M // headsplit_Lk
@@ -382,3 +392,29 @@ def attention_merge(partial: torch.Tensor, nparts: int, B: int, Lq: int, heads: 
     call("petr_attention_merge", ptr(partial), nparts, ptr(out), out.stride(0) if out is not None else 0,
          ptr(out_split), B, Lq, heads, stream_ptr(partial.device))
     return out if out is not None else out_split
+
+
+def nms_free_decode(cls_scores: torch.Tensor, bbox_preds: torch.Tensor, max_num: int, post_center_range,
+                    score_threshold=None, bottom_center: bool = False):
+    """NMSFreeCoder.decode_single for a batch (nms_free_coder.py:48-101), one launch.  cls_scores (B,Q,C) logits,
+    bbox_preds (B,Q,code) fp32 CUDA.  Returns padded (boxes (B,max_num,9|7), scores, labels int64, query index
+    int64, mask bool, count int32); rows are sorted by descending score."""
+    _cuda(cls_scores, "cls_scores")
+    cls_scores = cls_scores.float().contiguous()
+    bbox_preds = bbox_preds.float().contiguous()
+    B, Q, C = cls_scores.shape
+    code = bbox_preds.shape[-1]
+    dev = cls_scores.device
+    nb = code - 1 if code > 8 else 7
+    boxes = torch.empty((B, max_num, nb), dtype=torch.float32, device=dev)
+    scores = torch.empty((B, max_num), dtype=torch.float32, device=dev)
+    labels = torch.empty((B, max_num), dtype=torch.int64, device=dev)
+    index = torch.empty((B, max_num), dtype=torch.int64, device=dev)
+    mask = torch.empty((B, max_num), dtype=torch.uint8, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    thr = score_threshold
+    call("petr_nms_free_decode", ptr(cls_scores), ptr(bbox_preds), B, Q, C, code, int(max_num),
+         host_floats([float(v) for v in post_center_range]), int(thr is not None), float(thr or 0.0),
+         int(bool(bottom_center)), ptr(boxes), ptr(scores), ptr(labels), ptr(index), ptr(mask), ptr(count),
+         stream_ptr(dev))
+    return boxes, scores, labels, index, mask.bool(), count

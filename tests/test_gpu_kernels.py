@@ -486,3 +486,52 @@ def test_position_mlp_fused_broadcast_residual_and_add_rows():
     assert (f32 - exp).abs().max() <= 1e-5 * max(1.0, exp.abs().max().item())
     assert torch.equal(b16, f32.to(torch.bfloat16))
     assert torch.equal(ops.add_rows_bf16(base, res2), exp.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,Q,C,code,max_num,thr", [(3, 900, 10, 10, 300, None), (2, 900, 10, 10, 300, 0.2),
+                                                   (1, 64, 10, 10, 100, None), (2, 100, 10, 8, 300, 0.05),
+                                                   (1, 30, 3, 10, 100, None)])
+def test_nms_free_decode_kernel(B, Q, C, code, max_num, thr):
+    """NMSFreeCoder.decode_single + get_bboxes' bottom-centre shift as ONE kernel launch per batch
+    (nms_free_coder.py:48-119, petr_head.py:731-751) against the CPU oracle: labels and query indices bit-exact,
+    scores / boxes to fp32 rounding of exp / atan2; also through the module API and inside a CUDA graph."""
+    import petr_b200 as pb
+    g = torch.Generator().manual_seed(B * 1000 + Q)
+    cls = torch.randn(B, Q, C, generator=g) - 2.0
+    box = torch.randn(B, Q, code, generator=g)
+    box[..., 0:2] *= 40.0
+    rng = [-61.2, -61.2, -10.0, 61.2, 61.2, 10.0]
+    kmax = min(max_num, Q * C)
+    for bottom in (False, True):
+        ref = po.nms_free_decode(cls, box, kmax, C, rng, thr, bottom_center=bottom)
+        boxes, scores, labels, index, mask, count = ops.nms_free_decode(cls.to(DEV), box.to(DEV), kmax, rng, thr, bottom)
+        assert boxes.shape == (B, kmax, 9 if code > 8 else 7)
+        for b in range(B):
+            m = mask[b].cpu()
+            assert int(count[b]) == int(m.sum()) == ref[b]["labels"].numel()
+            assert torch.equal(labels[b].cpu()[m], ref[b]["labels"]), "labels must be bit-exact"
+            assert torch.equal(index[b].cpu()[m], ref[b]["index"]), "query indices must be bit-exact"
+            assert (scores[b].cpu()[m] - ref[b]["scores"]).abs().max() <= 2e-7
+            assert (scores[b, :-1] >= scores[b, 1:]).all()
+            d = (boxes[b].cpu()[m] - ref[b]["bboxes"]).abs()
+            assert (d <= 1e-5 * ref[b]["bboxes"].abs().clamp(min=1.0)).all()
+    if code == 10 and C == 10:
+        coder = pb.NMSFreeCoder(pc_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], post_center_range=rng,
+                                max_num=kmax, score_threshold=thr, num_classes=C)
+        outs = dict(all_cls_scores=cls[None].to(DEV), all_bbox_preds=box[None].to(DEV))
+        dec = coder.decode(outs)
+        ref = po.nms_free_decode(cls, box, kmax, C, rng, thr)
+        for d, r in zip(dec, ref):
+            assert torch.equal(d["labels"].cpu(), r["labels"]) and d["bboxes"].shape == r["bboxes"].shape
+        # graph capture: features -> boxes without leaving the stream
+        xs, bs = cls.to(DEV), box.to(DEV)
+        coder.decode_padded(xs, bs)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            out = coder.decode_padded(xs, bs, bottom_center=True)
+        gr.replay()
+        torch.cuda.synchronize()
+        eager = coder.decode_padded(xs, bs, bottom_center=True)
+        for a, b_ in zip(out, eager):
+            assert torch.equal(a, b_)

@@ -63,28 +63,28 @@ def test_state_dict_contract(wn):
 
 
 def test_nms_free_coder_and_get_bboxes_match_reference():
-    """Next row: NMSFreeCoder.decode / PETRHead.get_bboxes, vectorised over the batch,
-    against the reference's own coder (nms_free_coder.py:48-119, petr_head.py:731-751)."""
-    import petr_b200 as pb
+    """Next row: the oracle's NMSFreeCoder.decode / PETRHead.get_bboxes restatement against the
+    reference's own coder (nms_free_coder.py:48-119, petr_head.py:731-751); the CUDA kernel is then checked
+    against the oracle on the GPU box (tests/test_gpu_kernels.py::test_nms_free_decode_kernel)."""
     ns = rl.load_reference()
     g = torch.Generator().manual_seed(3)
     B, Q = 3, 900
     outs = dict(all_cls_scores=torch.randn(6, B, Q, 10, generator=g) - 2.0,
                 all_bbox_preds=torch.randn(6, B, Q, 10, generator=g))
     outs["all_bbox_preds"][..., 0:2] *= 40.0
-    kw = dict(pc_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], post_center_range=[-61.2, -61.2, -10.0, 61.2, 61.2, 10.0],
+    rng = [-61.2, -61.2, -10.0, 61.2, 61.2, 10.0]
+    kw = dict(pc_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], post_center_range=rng,
               max_num=300, voxel_size=[0.2, 0.2, 8], num_classes=10)
     for thr in (None, 0.2):
         ref = ns.NMSFreeCoder(score_threshold=thr, **kw).decode(outs)
-        mine = pb.NMSFreeCoder(score_threshold=thr, **kw).decode(outs)
+        mine = po.nms_free_decode(outs["all_cls_scores"][-1], outs["all_bbox_preds"][-1], 300, 10, rng, thr)
         assert len(ref) == len(mine) == B
         for r, m in zip(ref, mine):
             assert torch.equal(r["labels"], m["labels"]) and torch.equal(r["scores"], m["scores"])
             assert torch.equal(r["bboxes"], m["bboxes"])
-    head = pb.build_head(pb.petr_head_cfg(256))
-    res = head.get_bboxes({k: v.clone() for k, v in outs.items()}, [dict() for _ in range(B)])
+    res = po.nms_free_decode(outs["all_cls_scores"][-1], outs["all_bbox_preds"][-1], 300, 10, rng, None, bottom_center=True)
     ref = ns.NMSFreeCoder(**kw).decode(outs)
-    for (bx, sc, lb), r in zip(res, ref):
+    for m, r in zip(res, ref):
         exp = r["bboxes"].clone()
         exp[:, 2] = exp[:, 2] - exp[:, 5] * 0.5
-        assert torch.equal(bx, exp) and torch.equal(sc, r["scores"]) and torch.equal(lb, r["labels"])
+        assert torch.equal(m["bboxes"], exp) and torch.equal(m["scores"], r["scores"]) and torch.equal(m["labels"], r["labels"])
