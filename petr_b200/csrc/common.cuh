@@ -35,6 +35,7 @@ bool flash_exact_only();
 int flash_poly();
 bool gemm_staged();
 bool gemm_coalesce();
+bool gemm_skinny();
 void* debug_trace();
 }  // namespace tuning
 

@@ -786,6 +786,62 @@ extern "C" int petr_pos2posemb3d(const float* ref, const float* dim_t, int Q, in
     return after_launch("petr_pos2posemb3d");
 }
 
+// Skinny-N fp32 GEMM for the last layer of the branches (256 -> 10 over
+// 6 * B * 900 rows, petr_head.py:226-247): the tiled kernel above spends 110 us per launch at B = 16
+// on an 88 MB read (0.8 TB/s).  Here a warp keeps its slice of W in registers (lane l: columns
+// [8 l, 8 l + 8) of all N <= 10 rows of W), streams rows of A with two 16-byte loads per lane, and
+// reduces the N partial sums with shuffles; one row per warp iteration, 8 warps per CTA.
+constexpr int SKINNY_MAX_N = 10;
+__global__ void __launch_bounds__(256)
+gemm_f32_skinny_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
+                       const float* __restrict__ bias, const float* __restrict__ residual,
+                       float* __restrict__ C, int ldc, int M, int N, int relu) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * 8;
+    float w[SKINNY_MAX_N][8];
+#pragma unroll
+    for (int n = 0; n < SKINNY_MAX_N; ++n) {
+        if (n < N) {
+            const float4 a = *reinterpret_cast<const float4*>(W + (int64_t)n * 256 + lane * 8);
+            const float4 b = *reinterpret_cast<const float4*>(W + (int64_t)n * 256 + lane * 8 + 4);
+            w[n][0] = a.x; w[n][1] = a.y; w[n][2] = a.z; w[n][3] = a.w;
+            w[n][4] = b.x; w[n][5] = b.y; w[n][6] = b.z; w[n][7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[n][i] = 0.f;
+        }
+    }
+    const float my_bias = (bias && lane < N) ? bias[lane] : 0.f;
+    for (int m = warp_global; m < M; m += warps_total) {
+        const float* ap = A + (int64_t)m * lda + lane * 8;
+        const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
+        float acc[SKINNY_MAX_N];
+#pragma unroll
+        for (int n = 0; n < SKINNY_MAX_N; ++n) {
+            float t = a0.x * w[n][0];
+            t = fmaf(a0.y, w[n][1], t); t = fmaf(a0.z, w[n][2], t); t = fmaf(a0.w, w[n][3], t);
+            t = fmaf(a1.x, w[n][4], t); t = fmaf(a1.y, w[n][5], t); t = fmaf(a1.z, w[n][6], t);
+            acc[n] = fmaf(a1.w, w[n][7], t);
+        }
+        // butterfly reduction; afterwards every lane holds all N sums
+#pragma unroll
+        for (int n = 0; n < SKINNY_MAX_N; ++n) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+        }
+        float mine = 0.f;                                    // lane n keeps sum n
+#pragma unroll
+        for (int n = 0; n < SKINNY_MAX_N; ++n) mine = (lane == n) ? acc[n] : mine;
+        if (lane < N) {
+            float v = mine + my_bias;
+            if (relu) v = fmaxf(v, 0.f);
+            if (residual) v += residual[(int64_t)m * ldc + lane];
+            C[(int64_t)m * ldc + lane] = v;
+        }
+    }
+}
+
 extern "C" int petr_gemm_f32(const float* A, int lda, int a_layout, int hw, const float* A2,
                              int a2_rows, const float* W, const float* bias, const float* residual,
                              const float* gate, int act, float* C, void* C_bf16, int ldc, int M,
@@ -800,6 +856,18 @@ extern "C" int petr_gemm_f32(const float* A, int lda, int a_layout, int hw, cons
         PETR_REQUIRE(lda >= K, PETR_E_BADARG, "petr_gemm_f32: lda < K");
     if (A2) PETR_REQUIRE(a2_rows > 0, PETR_E_BADARG, "petr_gemm_f32: a2_rows <= 0");
     if (act == PETR_ACT_SIGMOID_GATE) PETR_REQUIRE(gate, PETR_E_BADARG, "petr_gemm_f32: gate is null");
+    // the 256 -> <= 10 tails of the branches: streaming kernel with W in registers
+    if (tuning::gemm_skinny() && a_layout == PETR_A_ROWMAJOR && K == 256 && N <= SKINNY_MAX_N && M >= 4096 && !A2 && !gate &&
+        !C_bf16 && C && (act == PETR_ACT_NONE || act == PETR_ACT_RELU) && (lda % 4) == 0 && aligned16(A) &&
+        aligned16(W)) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int ctas = (M + 7) / 8 < sms * 8 ? (M + 7) / 8 : sms * 8;
+        gemm_f32_skinny_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(A, lda, W, bias, residual, C, ldc, M, N,
+                                                                     act == PETR_ACT_RELU ? 1 : 0);
+        return after_launch("petr_gemm_f32");
+    }
     GemmParams p{A, lda, a_layout, hw, A2, a2_rows, W, bias, residual, gate, act, C,
                  (__nv_bfloat16*)C_bf16, ldc, M, N, K};
     dim3 grid((M + GBM - 1) / GBM, (N + GBN - 1) / GBN);

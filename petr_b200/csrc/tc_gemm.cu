@@ -422,21 +422,33 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
-// fp32 NCHW feature maps (G, C, hw) -> bf16 token-major (G*hw, C): A operand of input_proj
+// fp32 NCHW feature maps (G, C, hw) -> bf16 token-major (G*hw, C): A operand of input_proj.
+// One CTA moves a 32-pixel x 64-channel block: every global read is a 128-byte row segment (32 pixels of one
+// channel), every global write a 128-byte row segment (64 bf16 channels of one pixel); 8 independent loads per
+// thread are in flight before the first use (HBM-bound: 4 B in + 2 B out per element).
 __global__ void __launch_bounds__(256)
 nchw_to_tokens_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int hw) {
-    __shared__ float tile[32][33];
-    const int g = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    __shared__ float tile[64][33];
+    const int g = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;          // 8 warps
     const float* xg = x + (int64_t)g * C * hw;
-    for (int i = ty; i < 32; i += 8) {
-        int c = c0 + i, pp = p0 + tx;
-        tile[i][tx] = (c < C && pp < hw) ? xg[(int64_t)c * hw + pp] : 0.f;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + w * 8 + i, pp = p0 + lane;
+        v[i] = (c < C && pp < hw) ? __ldg(xg + (int64_t)c * hw + pp) : 0.f;
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tile[w * 8 + i][lane] = v[i];
     __syncthreads();
-    for (int i = ty; i < 32; i += 8) {
-        int pp = p0 + i, c = c0 + tx;
-        if (pp < hw && c < C) out[((int64_t)g * hw + pp) * C + c] = __float2bfloat16_rn(tile[tx][i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int pl = w * 4 + i, pp = p0 + pl, c = c0 + 2 * lane;
+        if (pp < hw && c < C) {
+            __nv_bfloat16* o = out + ((int64_t)g * hw + pp) * C + c;
+            if (c + 1 < C) *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(tile[2 * lane][pl], tile[2 * lane + 1][pl]);
+            else *o = __float2bfloat16_rn(tile[2 * lane][pl]);
+        }
     }
 }
 
@@ -448,7 +460,8 @@ using namespace petr;
 extern "C" int petr_nchw_to_tokens_bf16(const float* x, void* out, int G, int C, int hw, void* stream) {
     PETR_REQUIRE(x && out, PETR_E_BADARG, "petr_nchw_to_tokens_bf16: null pointer");
     PETR_REQUIRE(G > 0 && C > 0 && hw > 0 && G <= 65535, PETR_E_BADARG, "petr_nchw_to_tokens_bf16: bad dimension");
-    dim3 grid((hw + 31) / 32, (C + 31) / 32, G);
+    PETR_REQUIRE((C % 2) == 0, PETR_E_SHAPE, "petr_nchw_to_tokens_bf16: C must be even, got %d", C);
+    dim3 grid((hw + 31) / 32, (C + 63) / 64, G);
     nchw_to_tokens_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, C, hw);
     return after_launch("petr_nchw_to_tokens_bf16");
 }
