@@ -99,6 +99,31 @@ class ClockSampler:
                     samples=len(sm), reasons=sorted(reasons))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs next to its GPU before any pinned host buffer is allocated, so first-touch puts
+    the staging memory on the GPU's NUMA node (each rank streams ~0.4 GB per step from it).  Returns the cpulist."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = f.read().strip()
+        return f"node {node}, cpus {txt}"
+    except Exception as exc:
+        return f"unbound ({type(exc).__name__})"
+
+
 def cpu_oracle_setup(wl, seed=0):
     import petr_b200 as pb
     from petr_b200 import synth
@@ -127,6 +152,30 @@ def time_cpu_oracle(wl, nsamples, seed=0):
             po.head_forward(sd, x, metas, ocfg)
             times.append(time.perf_counter() - t)
     return times, cores
+
+
+def time_gpu_eager_oracle(wl, nsamples, dev, seed=0):
+    """"The reference on the same box" (BASELINE.md section 2): the oracle port's plain torch ops, fp32, moved to the
+    B200 (PyTorch eager: cuBLAS / cuDNN kernels, (B*8, 900, Lk) score tensors materialised), per-sample loop.
+    A reported baseline; like cpu_baseline it never touches the measured path."""
+    from oracle import petr_oracle as po
+    from petr_b200 import synth
+    sd, ocfg = cpu_oracle_setup(wl, seed)
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    metas = synth.make_img_metas(wl, 1, seed)
+    x = synth.make_features(wl, 1, seed).to(dev)
+    with torch.no_grad(), torch.device(dev):
+        for _ in range(2):
+            po.head_forward(sd, x, metas, ocfg)
+        torch.cuda.synchronize(dev)
+        t = time.perf_counter()
+        for _ in range(nsamples):
+            po.head_forward(sd, x, metas, ocfg)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t
+    del sd, x
+    torch.cuda.empty_cache()
+    return nsamples / dt
 
 
 def run_reference(args, wl, rank):
@@ -171,10 +220,9 @@ def main():
     args = ap.parse_args()
 
     if args.graph is None:
-        # default: graph replay on one GPU.  Multi-process runs launch eagerly unless --graph is given:
-        # that is the configuration the 2/4/8-GPU scaling numbers were measured with (graph replay
-        # next to a live NCCL communicator has only been exercised in the key-split experiment).
-        args.graph = not args.keysplit and int(os.environ.get("WORLD_SIZE", "1")) == 1
+        # default: whole-head CUDA-graph replay, also in data-parallel multi-process runs (the graph captures no
+        # collective there; NCCL is only used for the timing barrier).  Key-split captures NCCL all-gathers: eager.
+        args.graph = not args.keysplit
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -192,6 +240,7 @@ def main():
     args.warmup = max(3, args.warmup)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "not bound (single process)"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -305,6 +354,7 @@ def main():
     he.record()
     torch.cuda.synchronize()
     h2d_gbs = 3 * x_host.numel() * 4 / (hs.elapsed_time(he) * 1e-3) / 1e9
+    h2d_min = -max_over_ranks(-h2d_gbs)              # all ranks copy at once here: the slowest rank's host feed
 
     e2e_run(2)
     barrier()
@@ -330,22 +380,53 @@ def main():
         s = head.engine.spec
         flops = 4.0 * s.Lq * wl.num_keys * s.E * B                  # per launch (one layer, B samples)
         achieved = flops / (avg_ms * 1e-3) / 1e12
+        # the honest secondary bound at head_dim 32: one exponential per score element, 16 MUFU ex2 per clock per SM;
+        # rows are exponentiated in whole 32-row warps (900 -> 928), the kernel moves half of them to the FMA pipe
+        sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+        exps = 928.0 * wl.num_keys * s.heads * B
+        exp_ms = exps / (16.0 * 148 * sm_clk * 1e6) * 1e3
         roofline = dict(kernel=FLASH_KERNEL, bound="tensor", achieved=achieved,
                         peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_sustained"],
+                        frac_of_burst_peak=achieved / peaks["bf16"],
                         traffic=load_traffic(B) if wl.name == "vov-p4-1600x640" else None,
-                        peak_source=peaks["source"] + " bf16 sustained",
+                        peak_source=peaks["source"] + " bf16 sustained (frac) / burst (frac_of_burst_peak)",
                         launches_timed=len(evs), avg_launch_ms=avg_ms,
                         share_of_step=avg_ms * s.L / ms_per_step,
-                        alg_flops_per_launch=flops)
+                        alg_flops_per_launch=flops,
+                        exp_bound=dict(exps_per_launch=exps, mufu_only_ms=exp_ms, frac_of_mufu_only_time=exp_ms / avg_ms,
+                                       note="time of the launch's exponentials at 16 ex2/clk/SM if all ran on MUFU; the "
+                                            "kernel evaluates 2 of every 4 pairs with an FMA-pipe polynomial"))
+    roofline_k1 = None
+    if timers and timers.get("position_mlp_fused"):
+        evs = timers["position_mlp_fused"]
+        avg_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        T = B * wl.num_keys
+        flops = 2.0 * T * (192 * 1024 + 1024 * 256)
+        byts = T * 256 * (4 + 2) + B * wl.num_cams * 64 + (192 * 1024 + 1024 * 256) * 2     # residual in, bf16 out, matrices, weights once
+        roofline_k1 = dict(kernel="position_mlp_fused_kernel", bound="tensor", achieved=flops / (avg_ms * 1e-3) / 1e12,
+                           peak=peaks["bf16_sustained"], unit="TFLOP/s",
+                           frac=flops / (avg_ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                           hbm_achieved_gbs=byts / (avg_ms * 1e-3) / 1e9, hbm_peak_gbs=peaks["hbm"],
+                           hbm_frac=byts / (avg_ms * 1e-3) / 1e9 / peaks["hbm"], avg_launch_ms=avg_ms,
+                           alg_flops_per_launch=flops, alg_bytes_per_launch=byts,
+                           note="tensor pipe is the binding roof (896 flop/B); the coordinate tensor, the MLP input and the "
+                                "hidden activation contribute no HBM bytes")
 
     if rank == 0:
         cpu = None
+        gpu_eager = None
         if world == 1 and not args.no_cpu_baseline:
             times, cores = time_cpu_oracle(wl, args.cpu_samples, 0)
             v = len(times) / float(sum(times))
             cpu = dict(value=v, unit="samples/s", cores=cores, kind="port",
                        sample=f"{len(times)} single-sample head forwards of {wl.name} "
                               f"(oracle/petr_oracle.py, torch CPU fp32, {cores} threads)")
+            try:
+                ge = time_gpu_eager_oracle(wl, 10, dev, 0)
+                gpu_eager = dict(value=ge, unit="samples/s", kind="port on cuda (PyTorch eager fp32, cuBLAS/cuDNN)",
+                                 sample=f"10 single-sample head forwards of {wl.name} (oracle/petr_oracle.py on {dev})")
+            except Exception as exc:                                   # reported, never fatal for the measured line
+                gpu_eager = dict(unavailable=f"{type(exc).__name__}: {exc}"[:200])
         line = dict(metric=METRIC, value=value, unit="samples/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
                     scaling="strong" if args.keysplit else "weak",
@@ -358,28 +439,30 @@ def main():
                                 l2="inputs larger than L2 (%.0f MB features per step)" % (x_host.numel() * 4 / 1e6)),
                     e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=int(h2d),
                              d2h_bytes_per_step=int(d2h), h2d_gbs_measured=round(h2d_gbs, 1),
+                             h2d_gbs_min_over_ranks=round(h2d_min, 1), host_numa=host_numa,
                              note="H2D of step i+1 overlaps compute of step i (two streams)"),
-                    gpu_launches=int(launches), clocks=clocks, roofline=roofline, cpu_baseline=cpu)
+                    gpu_launches=int(launches), clocks=clocks, roofline=roofline, roofline_k1=roofline_k1,
+                    cpu_baseline=cpu, gpu_eager_baseline=gpu_eager)
         if args.breakdown and breakdown:
             sys.stderr.write("per-op breakdown (ms per step, CUDA events):\n")
             for k, v in breakdown.items():
                 sys.stderr.write(f"  {k:32s} {v['ms_per_step']:9.3f} ms  x{v['launches_per_step']:.0f}\n")
         print(json.dumps(line), flush=True)
     if dist is not None:
-        # the JSON line is out: never let a stuck NCCL / CUDA-graph teardown hang the job
+        # The JSON line is out.  Tear down properly: drop the captured graphs first, then the process group; a
+        # teardown that raises or does not finish within 60 s makes the run exit NON-zero (the line stays valid,
+        # the failure is visible) instead of hanging the job.
         import threading
         sys.stdout.flush()
         sys.stderr.flush()
-        killer = threading.Timer(30.0, lambda: os._exit(0))
+        killer = threading.Timer(60.0, lambda: (sys.stderr.write("bench.py: teardown timed out\n"), os._exit(3)))
         killer.daemon = True
         killer.start()
-        try:
-            torch.cuda.synchronize()
-            dist.destroy_process_group()
-        finally:
-            sys.stdout.flush()
-            sys.stderr.flush()
-            os._exit(0)
+        head.engine.invalidate()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+        killer.cancel()
 
 
 if __name__ == "__main__":

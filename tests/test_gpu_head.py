@@ -33,14 +33,17 @@ def _layers_to_check(name):
     return slice(0, 1) if name == "tiny_sharp" else slice(None)
 
 
-# bf16 tolerance policy (DESIGN.md "precision"): the 2e-2 bound of BASELINE.json holds for the
-# diffuse attention of random-init weights at realistic key counts (bf16 rounding of V / P / position
-# embeddings averages out as 1/sqrt(keys)).  The 80-key tiny cases get a looser bound; peaked
-# attention (small_sharp, Wq/Wk x3) is outside what ANY bf16-operand attention can hold to 2e-2 in
-# cx/cy metres (a bf16 emulation of the oracle itself is off by 0.45 there, tests/precision_study.py)
-# and is bounded loosely here -- its softmax mechanics are checked exactly at kernel level
-# (test_cross_attention_bf16) and its fp32 path tightly above.
-BF16_TOL = {"small_sharp": 1.0, "tiny": 5e-2, "tiny_padded": 5e-2, "tiny_range": 5e-2, "tiny_v2": 5e-2}
+# bf16 tolerance policy (DESIGN.md "precision").  The 2e-2 bound of BASELINE.json is held on every realistic key
+# count: the full-size BASELINE configurations (test_full_size_oracle_parity), the 1 500-key `small*` cases, the
+# 6 000-key vov_800x320 golden and tiny_v2.  Exceptions, each bounded by its MEASURED error + 25 % as a regression
+# guard (the bound of a case is a property of bf16 operands, not of this implementation -- a bf16 emulation of the
+# oracle itself shows the same figures, tests/precision_study.py):
+#   * the 80-key `tiny*` cases: bf16 rounding of V / P / position embeddings averages out as 1/sqrt(keys), and 80
+#     keys are too few (measured 0.030 / 0.026 / 0.028 m in cx, cy);
+#   * small_sharp (cross-attention Wq/Wk x3: peaked attention): measured 0.44 m; its softmax mechanics are checked
+#     exactly at kernel level (test_cross_attention_bf16), its fp32 path to 2e-3 above and its decoder layers
+#     teacher-forced below.
+BF16_TOL = {"small_sharp": 0.55, "tiny": 0.0375, "tiny_padded": 0.0325, "tiny_range": 0.035}
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))
@@ -76,7 +79,7 @@ def test_head_bf16_path_within_tolerance(name):
 
 @pytest.mark.parametrize("name,precision,tol", [
     ("tiny_sharp", "fp32", 2e-3), ("tiny_padded", "fp32", 2e-3), ("small_sharp", "fp32", 2e-3),
-    ("small_padded", "bf16", 2e-2), ("small", "bf16", 2e-2), ("small_sharp", "bf16", 1.0)])
+    ("small_padded", "bf16", 2e-2), ("small", "bf16", 2e-2), ("small_sharp", "bf16", 0.55)])
 def test_decoder_layers_teacher_forced(name, precision, tol):
     """Each decoder layer fed with the ORACLE's input to that layer (no error compounding), then
     post_norm + branches: cls/box of every layer within tolerance even with peaked attention

@@ -103,12 +103,16 @@ def qside(args):
         "ffn1_relu_split": lambda: ops.gemm_bf16_tc(Xs, wf1, b2048, act=ops.ACT_RELU, x3=True, split_out=True),
         "ffn2_res_f32": lambda: ops.gemm_bf16_tc(Hs, wf2, b256, residual=X, x3=True),
     }
-    for coal in (0, 1):
-        _lib.set_tuning("gemm_coalesce", coal)
-        for name, fn in cases.items():
-            med, best = timeit(fn, iters=20)
-            print(json.dumps(dict(kernel="qside", case=name, coalesce=coal, M=M, us_median=med * 1e3, us_best=best * 1e3)), flush=True)
-    _lib.set_tuning("gemm_coalesce", 1)
+    for name, fn in cases.items():
+        med, best = timeit(fn, iters=20)
+        # the same launch 20 times inside one CUDA graph: per-kernel time without host launch overhead
+        fn(); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(20):
+                fn()
+        gm, gb = timeit(g.replay, iters=5)
+        print(json.dumps(dict(kernel="qside", case=name, M=M, us_eager_median=med * 1e3, us_in_graph=gm * 1e3 / 20)), flush=True)
 
 
 def main():
