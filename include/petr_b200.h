@@ -267,12 +267,13 @@ int petr_cross_attention_trace(const void* Qs, const void* Kh, const void* Vh, f
  * BaseTransformerLayer with q = k = query + query_pos, v = query).  Every operand is a bf16
  * [hi | lo] pair (out_mode 4 of petr_gemm_bf16_tc), all bf16 [B, heads, L, 32]:
  *   S = Qh Kh^T + Ql Kh^T + Qh Kl^T,  P = Ph + Pl,  O = Ph Vh + Pl Vh + Ph Vl   (~2^-16 accuracy).
- * `scale` (head_dim^-1/2) is applied inside the softmax.  Outputs / splits / masks as
- * petr_cross_attention_bf16. */
+ * `scale` (head_dim^-1/2) is applied inside the softmax.  Outputs / splits / masks / workspace (fast max-free pass +
+ * exact pass on flagged CTAs; petr_attention_x3_workspace_bytes) as petr_cross_attention_bf16. */
 int petr_attention_x3_tc(const void* Qh, const void* Ql, const void* Kh, const void* Kl,
                          const void* Vh, const void* Vl, const uint8_t* key_mask, float* O,
-                         int ldo, void* O_split, float* partial, int B, int Lq, int Lk,
+                         int ldo, void* O_split, float* partial, void* workspace, int B, int Lq, int Lk,
                          int heads, float scale, int nsplit, int write_partial, void* stream);
+int64_t petr_attention_x3_workspace_bytes(int B, int Lq, int Lk, int heads, int nsplit);
 
 /* Merge `nparts` partial attention results (on-GPU split-KV or key-split across GPUs after an
  * all-gather):  m = max m_r;  O = sum e^{m_r-m} O_r / sum e^{m_r-m} l_r.

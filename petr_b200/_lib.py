@@ -48,7 +48,8 @@ SIGNATURES = {
     "petr_cross_attention_bf16": (c_int, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "petr_cross_attention_workspace_bytes": (c_int64, [_I, _I, _I, _I, _I]),
     "petr_cross_attention_trace": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "petr_attention_x3_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P]),
+    "petr_attention_x3_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P]),
+    "petr_attention_x3_workspace_bytes": (c_int64, [_I, _I, _I, _I, _I]),
     "petr_attention_merge": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
     "petr_attention_partial_floats": (c_int64, [_I, _I, _I]),
 }

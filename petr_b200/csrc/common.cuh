@@ -36,6 +36,7 @@ int flash_poly();
 bool gemm_staged();
 bool gemm_coalesce();
 bool gemm_skinny();
+bool gemm_band();
 void* debug_trace();
 }  // namespace tuning
 

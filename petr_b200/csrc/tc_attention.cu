@@ -160,8 +160,16 @@ constexpr int THREADS = 320;        // TMA, MMA, 2 x 4 softmax (two threads per 
 
 struct Maps { CUtensorMap qh, ql, kh, kl, vh, vl; };
 
+constexpr int TM_PH = 320, TM_PL = 384;       // FAST: P hi / lo (bf16 pairs, 64 columns each) in tensor memory
+
+// FAST: the max-free pass (p = 2^s, no running maximum, no half-row max exchange, no O rescale; P hi / lo go to
+// tensor memory and feed P.V as TS-mode A operands) with the row-sum window check of the cross-attention kernel;
+// !FAST: the exact online softmax, restricted to the CTAs the fast pass flagged when p.flags is set.
+template <bool FAST>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale_log2) {
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (!FAST && p.flags && p.flags[cta] == 0) return;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -190,6 +198,7 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm.qh); tma_prefetch_desc(&tm.ql); tma_prefetch_desc(&tm.kh);
         tma_prefetch_desc(&tm.kl); tma_prefetch_desc(&tm.vh); tma_prefetch_desc(&tm.vl);
+        if (FAST && p.flags) p.flags[cta] = 0;
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -294,13 +303,29 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
                 if (j + 1 < ntiles) issue_qk(j + 1);
                 const int s = j % STAGES;
                 mbar_wait(&v_full[s], (j / STAGES) & 1);
-                mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+                if (FAST) mbar_wait(&p_ready[0], j & 1);
+                else mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
                 tcgen05_fence_after();
                 const uint64_t pb = (uint64_t)(((j & 1) * 2 * P_BYTES) >> 4);          // P buffer of tile j
                 const uint64_t vh = vh_desc0 + (uint64_t)((s * STAGE_BYTES) >> 4);
                 const uint64_t vl = vh + (uint64_t)(V_BYTES >> 4);
                 const uint64_t pl_off = (uint64_t)(P_BYTES >> 4);
-                if (leader) {
+                if (FAST) {
+                    if (leader) {
+                        // (Ph,Vh), (Pl,Vh), (Ph,Vl) with P from tensor memory: 8 columns = 16 keys per MMA
+#pragma unroll
+                        for (int kk = 0; kk < KT / 16; ++kk)
+                            umma_f16_ts(tmem_base + TM_O, tmem_base + TM_PH + kk * 8, vh + (uint64_t)((kk * 1024) >> 4), idesc_pv, (j | kk) ? 1u : 0u);
+#pragma unroll
+                        for (int kk = 0; kk < KT / 16; ++kk)
+                            umma_f16_ts(tmem_base + TM_O, tmem_base + TM_PL + kk * 8, vh + (uint64_t)((kk * 1024) >> 4), idesc_pv, 1u);
+#pragma unroll
+                        for (int kk = 0; kk < KT / 16; ++kk)
+                            umma_f16_ts(tmem_base + TM_O, tmem_base + TM_PH + kk * 8, vl + (uint64_t)((kk * 1024) >> 4), idesc_pv, 1u);
+                        umma_commit(&v_empty[s]);
+                        umma_commit(&pv_done[0]);
+                    }
+                } else if (leader) {
                     // (Ph,Vh), (Pl,Vh), (Ph,Vl)
 #pragma unroll
                     for (int kk = 0; kk < KT / 16; ++kk)
@@ -326,7 +351,7 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
         const uint32_t o_addr = tmem_base + lane_off + TM_O + hf * 16;     // this half rescales 16 O columns
         uint8_t* prow = smem + OFF_P + hf * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
         float* smax = reinterpret_cast<float*>(smem + OFF_MAX);            // [parity][half][128]
-        float m_use = -INFINITY, l = 0.f;            // m_use in the scaled (log2) domain; l: this half's share
+        float m_use = FAST ? 0.f : -INFINITY, l = 0.f;   // m_use in the scaled (log2) domain; l: this half's share
         const bool use_mask = (p.key_mask != nullptr);
         for (int j = 0; j < ntiles; ++j) {
             const int bsel = j & 1;
@@ -357,6 +382,25 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
             if (need_bias) {
 #pragma unroll
                 for (int i = 0; i < 64; ++i) sv[i] += sbias[hf * 64 + i];
+            }
+            if (FAST) {
+                float lsum0 = 0.f, lsum1 = 0.f;
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float p0 = ex2(sv[2 * i]), p1 = ex2(sv[2 * i + 1]);
+                    lsum0 += p0; lsum1 += p1;
+                    split_bf16x2(p0, p1, hi[i], lo[i]);
+                }
+                l += lsum0 + lsum1;
+                mbar_wait(&pv_done[0], (j & 1) ^ 1);             // P.V of the previous key tile has consumed P
+                tcgen05_fence_after();
+                tmem_st_x32(tmem_base + lane_off + TM_PH + hf * 32, hi);
+                tmem_st_x32(tmem_base + lane_off + TM_PL + hf * 32, lo);
+                tmem_st_wait();
+                tcgen05_fence_before();
+                mbar_arrive(&p_ready[0]);
+                continue;
             }
             float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
 #pragma unroll
@@ -415,7 +459,8 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
             const int q = qtile * QT + row;
             float o[32];
             if (ntiles > 0) {
-                mbar_wait(&pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
+                if (FAST) mbar_wait(&pv_done[0], (ntiles - 1) & 1);
+                else mbar_wait(&pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
                 tcgen05_fence_after();
                 uint32_t orr[32];
                 tmem_ld_x32(tmem_base + lane_off + TM_O, orr);
@@ -425,6 +470,11 @@ attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) o[i] = 0.f;
+                if (FAST) m_use = -INFINITY;                 // empty split: neutral element of the merge
+            }
+            if (FAST && p.flags) {
+                const bool bad = q < p.Lq && ntiles > 0 && !(l > 8.3e-25f && l < 1.2e30f);   // [2^-80, 2^100], NaN fails
+                if (__any_sync(0xffffffffu, bad) && lane == 0) p.flags[cta] = 1;
             }
             if (q < p.Lq) write_attention_row(p, o, m_use, l, b, h, bh, q, split);
         }
@@ -875,6 +925,14 @@ extern "C" int64_t petr_attention_partial_floats(int B, int Lq, int heads) {
     return (int64_t)B * heads * Lq * 34;
 }
 
+// one int32 flag per CTA of the self-attention grid (fast pass -> exact pass hand-over)
+extern "C" int64_t petr_attention_x3_workspace_bytes(int B, int Lq, int Lk, int heads, int nsplit) {
+    if (B <= 0 || Lq <= 0 || Lk <= 0 || heads <= 0 || nsplit <= 0) return 0;
+    const int tiles = (Lk + KT - 1) / KT;
+    if (nsplit > tiles) nsplit = tiles;
+    return (int64_t)((Lq + QT - 1) / QT) * B * heads * nsplit * (int64_t)sizeof(int);
+}
+
 // one int32 flag per CTA of the cross-attention grid (fast pass -> exact pass hand-over)
 extern "C" int64_t petr_cross_attention_workspace_bytes(int B, int Lq, int Lk, int heads, int nsplit) {
     if (B <= 0 || Lq <= 0 || Lk <= 0 || heads <= 0 || nsplit <= 0) return 0;
@@ -1011,7 +1069,7 @@ extern "C" int petr_attention_merge(const float* partial, int nparts, float* O, 
 
 extern "C" int petr_attention_x3_tc(const void* Qh, const void* Ql, const void* Kh, const void* Kl,
                                     const void* Vh, const void* Vl, const uint8_t* key_mask, float* O,
-                                    int ldo, void* O_split, float* partial, int B, int Lq, int Lk,
+                                    int ldo, void* O_split, float* partial, void* workspace, int B, int Lq, int Lk,
                                     int heads, float scale, int nsplit, int write_partial, void* stream) {
     PETR_REQUIRE(Qh && Ql && Kh && Kl && Vh && Vl, PETR_E_BADARG, "petr_attention_x3_tc: null pointer");
     PETR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0 && nsplit > 0, PETR_E_BADARG, "petr_attention_x3_tc: bad dimension");
@@ -1036,15 +1094,25 @@ extern "C" int petr_attention_x3_tc(const void* Qh, const void* Ql, const void* 
         int rc = tmap::encode(maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptrs[i], d, st, box, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
     }
-    cudaError_t e = cudaFuncSetAttribute(x3::attention_x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, x3::SMEM);
+    const bool fast = workspace != nullptr && !tuning::flash_exact_only();
+    cudaError_t e = cudaFuncSetAttribute(x3::attention_x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, x3::SMEM);
+    if (e == cudaSuccess && fast)
+        e = cudaFuncSetAttribute(x3::attention_x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, x3::SMEM);
     if (e != cudaSuccess) return fail((int)e, "petr_attention_x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     AttParams p{};
     p.key_mask = key_mask; p.O = O; p.ldo = ldo; p.O_split = (__nv_bfloat16*)O_split; p.partial = partial;
     p.B = B; p.Lq = Lq; p.Lk = Lk; p.heads = heads; p.nsplit = nsplit; p.tiles_total = tiles;
     p.write_partial = part ? 1 : 0;
+    p.flags = fast ? (int*)workspace : nullptr;
     dim3 grid((Lq + QT - 1) / QT, B * heads, nsplit);
-    x3::attention_x3_tc_kernel<<<grid, x3::THREADS, x3::SMEM, (cudaStream_t)stream>>>(tm, p, scale * 1.4426950408889634f);
-    int rc = after_launch("petr_attention_x3_tc");
+    int rc = 0;
+    if (fast) {
+        x3::attention_x3_tc_kernel<true><<<grid, x3::THREADS, x3::SMEM, (cudaStream_t)stream>>>(tm, p, scale * 1.4426950408889634f);
+        rc = after_launch("petr_attention_x3_tc (fast pass)");
+        if (rc) return rc;
+    }
+    x3::attention_x3_tc_kernel<false><<<grid, x3::THREADS, x3::SMEM, (cudaStream_t)stream>>>(tm, p, scale * 1.4426950408889634f);
+    rc = after_launch("petr_attention_x3_tc");
     if (rc) return rc;
     if (part && !write_partial) {
         const int64_t total = (int64_t)B * heads * Lq * 8;

@@ -62,7 +62,7 @@ struct EpiParams {
     const float* bias; const float* residual; int act; float alpha;
     void* C; void* C2; int ldc; int out_mode;
     int M, N, K; int a_k_wrap; int kv_Lk; int kv_B; int kv_E;
-    int tiles_m, tiles_n;
+    int tiles_m, tiles_n, band;
     long long* trace;  // diagnostic clock64 stamps of CTA 0 (petr_debug_set_trace), normally null
     int coalesce;      // transposing (coalesced) epilogue allowed: 16-byte aligned bases, ldc % 4 == 0, N % 4 == 0
     int staged;        // out_mode 2: stage each warp's 32 x 32 bf16 chunk in smem and write it with one bulk copy
@@ -90,6 +90,22 @@ __device__ __forceinline__ void store_split_bf16x32(__nv_bfloat16* hp, __nv_bflo
     }
 }
 
+// tile index -> (m tile, n tile).  band == 0: n fastest (an A tile is reused from L2 by neighbouring CTAs).  band > 0
+// (store-bound GEMMs with several n tiles, i.e. the K / V projection): bands of `band` m tiles, inside a band m fastest,
+// so one wave of CTAs writes CONSECUTIVE key tiles of one layer (contiguous DRAM pages) and the band's A tiles stay in
+// L2 for its tiles_n passes.
+struct TileMap {
+    int tiles_m, tiles_n, band;
+    __device__ __forceinline__ void operator()(int tile, int& mt, int& nt) const {
+        if (band <= 0) { mt = tile / tiles_n; nt = tile - mt * tiles_n; return; }
+        const int per_band = band * tiles_n;
+        const int bd = tile / per_band, r = tile - bd * per_band;
+        const int rows = min(band, tiles_m - bd * band);           // the last band may be short
+        nt = r / rows;
+        mt = bd * band + (r - nt * rows);
+    }
+};
+
 #define GEMM_TR(role, t, ev) do { if (p.trace && blockIdx.x == 0 && (t) < 64) p.trace[((role) * 64 + (t)) * 8 + (ev)] = clock64(); } while (0)
 
 // One instantiation per output mode: with all five store paths in one kernel the epilogue alone was ~70 KB of
@@ -113,6 +129,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int num_k = p.K / BK;
     const int num_tiles = p.tiles_m * p.tiles_n;
+    const TileMap tmap_{p.tiles_m, p.tiles_n, p.band};
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -138,7 +155,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t it = 0;                                   // global k-block counter of this CTA
         uint32_t ttile = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ttile) {
-            const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+            int mt, nt;
+            tmap_(tile, mt, nt);
+            const int m0 = mt * BM, n0 = nt * BN;
             for (int kb = 0; kb < num_k; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -198,20 +217,26 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int et = threadIdx.x - 64;                             // 0..255 among the epilogue warps
         const uint32_t sbias_u32 = smem_u32(sbias);
         if (p.bias && (int)blockIdx.x < num_tiles) {
-            const int n0 = ((int)blockIdx.x % p.tiles_n) * BN;
+            int mt, nt;
+            tmap_((int)blockIdx.x, mt, nt);
+            const int n0 = nt * BN;
             sbias[et] = (n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
         }
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-            const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+            int mt, nt;
+            tmap_(tile, mt, nt);
+            const int m0 = mt * BM, n0 = nt * BN;
             const uint32_t buf = tcount & 1;
             const int m = m0 + row;
             const uint32_t sb = sbias_u32 + buf * BN * 4;
             float next_bias = 0.f;
             if (p.bias) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");      // this tile's bias visible; previous tile's readers done
-                const int nt = tile + gridDim.x;
-                if (nt < num_tiles) {
-                    const int nn = (nt % p.tiles_n) * BN + et;
+                const int ntile = tile + gridDim.x;
+                if (ntile < num_tiles) {
+                    int mt2, nt2;
+                    tmap_(ntile, mt2, nt2);
+                    const int nn = nt2 * BN + et;
                     if (nn < p.N) next_bias = __ldg(p.bias + nn);
                 }
             }
@@ -526,6 +551,7 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int tiles = p.tiles_m * p.tiles_n;
     int grid = tiles < sms ? tiles : sms;
+    p.band = (out_mode == 2 && p.tiles_n > 1 && tuning::gemm_band()) ? grid : 0;      // measured slower (0.509 vs 0.466 ms): off by default
     fn<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, p);
     return after_launch("petr_gemm_bf16_tc");
 }

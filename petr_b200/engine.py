@@ -15,6 +15,8 @@ Two precision paths, both CUDA-only:
 from __future__ import annotations
 
 import math
+import threading
+import warnings
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -58,8 +60,13 @@ class _PinnedRing:
     def __init__(self, depth: int = 8):
         self.depth = depth
         self.slots = {}
+        self.lock = threading.Lock()       # the ring is shared by every head of the process
 
     def stage(self, t: torch.Tensor, device) -> torch.Tensor:
+        with self.lock:
+            return self._stage(t, device)
+
+    def _stage(self, t: torch.Tensor, device) -> torch.Tensor:
         key = (tuple(t.shape), t.dtype, str(device))
         ring = self.slots.setdefault(key, dict(i=0, bufs=[], evs=[]))
         if len(ring["bufs"]) < self.depth:
@@ -227,6 +234,8 @@ class HeadEngine:
         self._packed: Dict[torch.device, dict] = {}
         self._graphs: Dict[tuple, tuple] = {}
         self.graph_replayed_launches = 0
+        self.graph_captures = 0              # how often a graph had to be (re)captured: a growing count means the
+                                             # caller keeps passing new input buffers / shapes (see _graph_forward)
 
     # -------------------------------------------------------------------------------------
     def invalidate(self):
@@ -462,9 +471,11 @@ class HeadEngine:
 
     def _graph_forward(self, x, host, precision, keysplit):
         """Whole head as one CUDA graph per (input buffer, shape, mask-ness): ~100 launches replayed
-        with one call.  The captured graph reads `x` at its current address (re-captured if the
-        caller passes a different buffer) and static meta buffers that are refreshed per call; the
-        returned tensors are the graph's static outputs, valid until the next call."""
+        with one call.  Contract: the captured graph reads `x` AT ITS CURRENT ADDRESS (pass the same
+        device buffer every step and refill it in place; a new address or shape captures a new graph, 8 are
+        kept, `graph_captures` counts them and a warning is raised when captures keep happening) and static
+        meta buffers that are refreshed per call; the returned tensors are the graph's static outputs:
+        they are OVERWRITTEN by the next call on this head, clone them to keep them."""
         dev = x.device
         ksk = None if not keysplit else (keysplit["world"], keysplit.get("rank"), bool(keysplit.get("emulate")))
         key = (x.data_ptr(), tuple(x.shape), x.dtype, precision, host["has_mask"], host["uniform_masks"],
@@ -485,6 +496,11 @@ class HeadEngine:
                 out = self._run(x, mi, precision, None, keysplit)
             ent = (g, mi, out, ops.launch_count() - n0)
             self._graphs[key] = ent
+            self.graph_captures += 1
+            if self.graph_captures in (16, 64, 256):
+                warnings.warn(f"petr_b200: {self.graph_captures} CUDA-graph captures on one head -- the input buffer "
+                              "address or shape changes between calls; reuse one device buffer (or set "
+                              "use_cuda_graph = False)")
         g, mi, out, nlaunch = ent
         stage_meta(host, dev, into=mi)
         g.replay()

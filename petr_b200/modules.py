@@ -655,7 +655,10 @@ class _PETRHeadBase(BaseModule):
 
     @torch.no_grad()
     def forward(self, mlvl_feats, img_metas):
-        """petr_head.py:366-468 / petrv2_head.py:429-540."""
+        """petr_head.py:366-468 / petrv2_head.py:429-540.  With `use_cuda_graph = True` the returned tensors are
+        the static outputs of the captured graph: valid until the next call on this head (clone to keep), and the
+        feature tensor must be the same device buffer every call (see HeadEngine._graph_forward).  Not thread-safe:
+        one head object per host thread."""
         _require_eval(self)
         x = mlvl_feats[self.position_level]
         return self.engine.forward(x, img_metas, precision=self.precision, keysplit=self.keysplit,

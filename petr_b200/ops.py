@@ -366,10 +366,16 @@ def cross_attention_bf16(Qs, Kh, Vh, key_mask, B: int, Lq: int, Lk: int, heads: 
 
 def attention_x3_tc(Qp, Kp, Vp, key_mask, B: int, Lq: int, Lk: int, heads: int, nsplit: int = 1,
                     out=None, out_split=None, partial=None, write_partial: bool = False,
-                    want_f32: bool = True):
-    """fp32-class attention on tcgen05.  Qp/Kp/Vp: bf16 (2, B, heads, L, 32) = (hi, lo) pairs."""
+                    want_f32: bool = True, workspace=None, exact_only: bool = False):
+    """fp32-class attention on tcgen05.  Qp/Kp/Vp: bf16 (2, B, heads, L, 32) = (hi, lo) pairs.  workspace: flag
+    scratch of the fast pass (allocated here when None); exact_only skips the max-free fast pass."""
     _cuda(Qp, "Qp")
     nsplit = max(1, min(int(nsplit), (Lk + 127) // 128))
+    if exact_only:
+        workspace = None
+    elif workspace is None:
+        n = int(_lib.lib().petr_attention_x3_workspace_bytes(B, Lq, Lk, heads, nsplit))
+        workspace = torch.empty((max(n, 4),), dtype=torch.uint8, device=Qp.device)
     if (nsplit > 1 or write_partial) and partial is None:
         partial = torch.empty((nsplit * attention_partial_floats(B, Lq, heads),), dtype=torch.float32,
                               device=Qp.device)
@@ -378,7 +384,7 @@ def attention_x3_tc(Qp, Kp, Vp, key_mask, B: int, Lq: int, Lk: int, heads: int, 
     with _Timed("attention_x3_tc"):
         call("petr_attention_x3_tc", ptr(Qp[0]), ptr(Qp[1]), ptr(Kp[0]), ptr(Kp[1]), ptr(Vp[0]), ptr(Vp[1]),
              ptr(key_mask), ptr(out), out.stride(0) if out is not None else 0, ptr(out_split), ptr(partial),
-             B, Lq, Lk, heads, 1.0 / math.sqrt(32.0), nsplit, int(write_partial), stream_ptr(Qp.device))
+             ptr(workspace), B, Lq, Lk, heads, 1.0 / math.sqrt(32.0), nsplit, int(write_partial), stream_ptr(Qp.device))
     if write_partial:
         return partial
     return out if out is not None else out_split

@@ -311,10 +311,12 @@ def test_attention_x3_tc_fp32_class(B, Lq, Lk, scale, nsplit):
     qh = (qp[0, 0].float() + qp[1, 0].float()).permute(0, 2, 1, 3).reshape(B * Lq, E)
     assert (qh - q).abs().max() <= 1e-4 * max(1.0, q.abs().max().item())
     sp = torch.empty(B * Lq, 2 * E, dtype=torch.bfloat16, device=DEV)
-    got = ops.attention_x3_tc(qp[:, 0], kp[:, 0], vp[:, 0], mask, B, Lq, Lk, 8, nsplit, out_split=sp)
-    err = (got - ref).abs().max().item()
-    assert err <= 3e-4 * max(1.0, ref.abs().max().item()), err
-    assert (sp[:, :E].float() + sp[:, E:].float() - got).abs().max() <= 2e-5 * max(1.0, got.abs().max().item())
+    for exact_only in (False, True):                 # max-free fast pass (+ exact pass on flagged CTAs) and exact alone
+        got = ops.attention_x3_tc(qp[:, 0], kp[:, 0], vp[:, 0], mask, B, Lq, Lk, 8, nsplit, out_split=sp,
+                                  exact_only=exact_only)
+        err = (got - ref).abs().max().item()
+        assert err <= 3e-4 * max(1.0, ref.abs().max().item()), (exact_only, err)
+        assert (sp[:, :E].float() + sp[:, E:].float() - got).abs().max() <= 2e-5 * max(1.0, got.abs().max().item())
 
 
 def test_gemm_bf16_tc_headsplit():

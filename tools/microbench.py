@@ -69,8 +69,9 @@ def kproj(args):
     W = (torch.randn(N, K, device=DEV) / 16).to(torch.bfloat16)
     b = torch.randn(N, device=DEV)
     ref = None
-    for staged in (0, 1):
+    for staged, band in ((0, 0), (1, 0), (1, 1)):
         _lib.set_tuning("gemm_staged", staged)
+        _lib.set_tuning("gemm_band", band)
         out = [None]
 
         def fn():
@@ -78,7 +79,7 @@ def kproj(args):
         med, best = timeit(fn)
         if ref is None:
             ref = out[0].clone()
-        print(json.dumps(dict(kernel="kproj", staged=staged, M=M, ms_median=med, ms_best=best,
+        print(json.dumps(dict(kernel="kproj", staged=staged, band=band, M=M, ms_median=med, ms_best=best,
                               tflops=2.0 * M * N * K / med / 1e9, write_gbs=M * N * 2 / med / 1e6,
                               equal=bool(torch.equal(ref, out[0])))), flush=True)
     _lib.set_tuning("gemm_staged", 1)
