@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PETR_B200_ABI_VERSION 2
+#define PETR_B200_ABI_VERSION 3
 
 #define PETR_E_BADARG   (-1)   /* null pointer / non-positive dimension */
 #define PETR_E_SHAPE    (-2)   /* unsupported shape (see each function) */
@@ -121,9 +121,15 @@ int petr_gemm_f32(const float* A, int lda, int a_layout, int hw,
  * key_mask nullable uint8 [B,Lk], 1 = ignore.  A row whose keys are all masked yields NaN,
  * like the reference (zeroed later by nan_to_num, petr_head.py:435).  head_dim must be 32.
  * O (fp32, nullable) and/or O_split (nullable: bf16 rows [hi | lo] of width 2*heads*head_dim, the
- * A operand of a bf16x3 petr_gemm_bf16_tc) receive the result. */
+ * A operand of a bf16x3 petr_gemm_bf16_tc) receive the result.
+ * attn_bias (nullable): the `attn_mask` of torch.nn.MultiheadAttention (petr_transformer.py:357-362) as an additive
+ * fp32 array [Lq, Lk] (bias_per_head 0) or [B*heads, Lq, Lk] (bias_per_head 1); -inf entries mask.
+ * Training (section 8f row 3): lse (nullable) fp32 [B, heads, Lq] receives log2-sum-exp2 of the scaled scores for
+ * petr_attention_f32_bwd; drop_p > 0 applies attention-probability dropout (nn.MultiheadAttention's `dropout`) decided
+ * by a counter-based hash of (seed, row, key) that the backward kernel re-evaluates. */
 int petr_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
-                       const uint8_t* key_mask, float* O, int ldo, void* O_split,
+                       const uint8_t* key_mask, const float* attn_bias, int bias_per_head,
+                       float* O, int ldo, void* O_split, float* lse, float drop_p, uint64_t seed,
                        int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
 
 /* ---- nn.LayerNorm over the last dim (eps 1e-5 on this path), optional fused ReLU
@@ -203,11 +209,13 @@ int petr_nchw_to_tokens_bf16(const float* x, void* out, int G, int C, int hw, vo
  *   5: two results from one accumulator: C = bf16 [m*N + n] of alpha*act(acc + bias) WITHOUT the residual and
  *      C2 = fp32 [m*ldc + n] WITH residual[(m %% kv_Lk)*ldc + n] added -- input_proj emitting the V-projection
  *      operand and "memory + batch-invariant sine embedding" (the K-side residual of the position MLP) at once.
- * residual (nullable, fp32, ldc) is added after alpha.  Used for the K/V projection of all
+ * residual (nullable, fp32, ldc) is added after alpha.  act PETR_ACT_SIGMOID_GATE (out_mode 0/1/3) multiplies
+ * sigmoid(acc + bias) by gate[m*ldc + n] (fp32) before the residual: the PETRv2 SELayer
+ * (petrv2_head.py:48-60) as a GEMM epilogue.  Used for the K/V projection of all
  * decoder layers in one launch (petr_transformer.py:341-344,:357-360), the position_encoder /
  * adapt_pos3d MLPs, input_proj and the query-side projections / FFN. */
 int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const void* W, int ldw,
-                      const float* bias, const float* residual, int act, float alpha,
+                      const float* bias, const float* residual, const float* gate, int act, float alpha,
                       void* C, void* C2, int ldc, int out_mode, int M, int N, int K,
                       int kv_Lk, void* stream);
 
@@ -283,6 +291,39 @@ int petr_attention_merge(const float* partial, int nparts, float* O, int ldo, vo
                          int B, int Lq, int heads, void* stream);
 
 int64_t petr_attention_partial_floats(int B, int Lq, int heads);
+
+/* ---- Either side of the main path (reference branches no shipped config takes) ---- */
+
+/* mmdet SinePositionalEncoding (mmdet 2.24.1, un-vendored; called per camera by the with_multiview=False branch,
+ * petr_head.py:403-409,:414-420).  mask uint8 [G,H,W] -> out [G*H*W, 2*num_feats] = [pos_y | pos_x]; inside a half,
+ * even channel j = sin(v / dim_t[j]), odd = cos(v / dim_t[j]). */
+int petr_sine2d_features(const uint8_t* mask, const float* dim_t, int G, int H, int W, int num_feats,
+                         int normalize, float scale, float eps, float offset, void* out, int out_dtype,
+                         void* stream);
+
+/* LearnedPositionalEncoding3D.forward (positional_encoding.py:137-160): out fp32 [G*H*W, 2*num_feats] =
+ * [col_embed[w] | row_embed[h]]. */
+int petr_learned_pos_features(const float* row_embed, int row_num, const float* col_embed, int col_num,
+                              int G, int H, int W, int num_feats, float* out, void* stream);
+
+/* token-major fp32 [G*hw, C] -> NCHW fp32 [G, C, hw] (the layout the reference's modules return). */
+int petr_tokens_to_nchw_f32(const float* x, float* out, int G, int C, int hw, void* stream);
+
+/* CPFPN top-down step (cp_fpn.py:176-184, F.interpolate nearest + add) on token-major maps:
+ * dst[g,y,x,:] += src[g, floor(y*h/H), floor(x*w/W), :].  dst fp32 [G,H,W,C], src fp32 [G,h,w,C]. */
+int petr_upsample_add_tokens(float* dst, const float* src, int G, int H, int W, int h, int w, int C,
+                             void* stream);
+
+/* im2col of CPFPN's level-0 3x3 / pad 1 conv (cp_fpn.py:126-136,:188-190) over a token-major fp32 map [G,H,W,C]:
+ * out[t, tap*C + c], tap = 3*ky + kx; out_mode 0 fp32, 1 bf16, 2 bf16 [hi | lo] halves (bf16x3 GEMM operand).  The
+ * conv then is one petr_gemm_* with the weight repacked to [Cout][tap][Cin]. */
+int petr_im2col3x3_tokens(const float* x, void* out, int out_mode, int G, int H, int W, int C, void* stream);
+
+/* mmdet NormedLinear operand scaling (petr_head.py:231-232): out = x * mult / (||x||^power + eps), the norm taken
+ * over the query axis of [B,Q,E] (along_queries 1: what `x.norm(dim=1)` does to the head's 3-D activations) or
+ * over each row of [B*Q, E] (along_queries 0: the weight). */
+int petr_norm_scale_f32(const float* x, float* out, int B, int Q, int E, int along_queries, float power,
+                        float eps, float mult, void* stream);
 
 #ifdef __cplusplus
 }

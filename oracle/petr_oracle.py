@@ -157,6 +157,48 @@ def sine_positional_encoding_3d(mask: Tensor, num_feats=128, temperature=10000, 
     return torch.cat((pos_n, pos_y, pos_x), dim=4).permute(0, 1, 4, 2, 3)
 
 
+def sine_positional_encoding_2d(mask: Tensor, num_feats=128, temperature=10000, normalize=True,
+                                scale=2 * math.pi, eps=1e-6, offset=0.0) -> Tensor:
+    """mmdet 2.24.1 SinePositionalEncoding.forward (mmdet/models/utils/positional_encoding.py; un-vendored,
+    restated -- parity of this piece is unpinned).  mask bool (B,H,W) -> (B, 2*num_feats, H, W) = [pos_y | pos_x]."""
+    not_mask = 1 - mask.to(torch.int)
+    y_embed = not_mask.cumsum(1, dtype=torch.float32)
+    x_embed = not_mask.cumsum(2, dtype=torch.float32)
+    if normalize:
+        y_embed = (y_embed + offset) / (y_embed[:, -1:, :] + eps) * scale
+        x_embed = (x_embed + offset) / (x_embed[:, :, -1:] + eps) * scale
+    dim_t = torch.arange(num_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * (dim_t // 2) / num_feats)
+    pos_x = x_embed[:, :, :, None] / dim_t
+    pos_y = y_embed[:, :, :, None] / dim_t
+    B, H, W = mask.shape
+    pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).view(B, H, W, -1)
+    pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).view(B, H, W, -1)
+    return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
+
+
+def learned_positional_encoding_3d(sd, p: str, mask: Tensor) -> Tensor:
+    """positional_encoding.py:137-160.  mask (B,h,w) -> (B, 2F, h, w) = [col_embed(x) | row_embed(y)]."""
+    h, w = mask.shape[-2:]
+    x_embed = sd[p + "col_embed.weight"][:w]
+    y_embed = sd[p + "row_embed.weight"][:h]
+    pos = torch.cat((x_embed.unsqueeze(0).repeat(h, 1, 1), y_embed.unsqueeze(1).repeat(1, w, 1)), dim=-1)
+    return pos.permute(2, 0, 1).unsqueeze(0).repeat(mask.shape[0], 1, 1, 1)
+
+
+def cpfpn_forward(sd, inputs: Sequence[Tensor], start_level: int = 0) -> List[Tensor]:
+    """CPFPN.forward cp_fpn.py:159-210 (no norm / activation, nearest top-down, 3x3 conv on level 0 only, no extra
+    levels).  inputs NCHW; sd keys `lateral_convs.{i}.conv.*`, `fpn_convs.0.conv.*`."""
+    n = len([k for k in sd if k.startswith("lateral_convs.") and k.endswith(".conv.weight")])
+    lat = [F.conv2d(inputs[i + start_level], sd[f"lateral_convs.{i}.conv.weight"], sd[f"lateral_convs.{i}.conv.bias"])
+           for i in range(n)]
+    for i in range(n - 1, 0, -1):
+        lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], mode="nearest")
+    outs = [F.conv2d(lat[0], sd["fpn_convs.0.conv.weight"], sd["fpn_convs.0.conv.bias"], padding=1)
+            if (i == 0 and "fpn_convs.0.conv.weight" in sd) else lat[i] for i in range(n)]
+    return outs
+
+
 def pos2posemb3d(pos: Tensor, num_pos_feats=128, temperature=10000) -> Tensor:
     """petr_head.py:31-43.  (.., 3) -> (.., 384) in (y, x, z) order."""
     pos = pos * (2 * math.pi)
@@ -173,7 +215,7 @@ def pos2posemb3d(pos: Tensor, num_pos_feats=128, temperature=10000) -> Tensor:
 # transformer
 # --------------------------------------------------------------------------------------
 def multihead_attention(sd: Dict[str, Tensor], prefix: str, query, key, value, identity,
-                        query_pos, key_pos, key_padding_mask, num_heads=8) -> Tensor:
+                        query_pos, key_pos, key_padding_mask, num_heads=8, attn_mask=None) -> Tensor:
     """petr_transformer.py:280-367 (== mmcv MultiheadAttention), eval mode, seq-first.
     Calls the same torch functional as nn.MultiheadAttention (need_weights=True as the
     reference leaves it)."""
@@ -185,7 +227,7 @@ def multihead_attention(sd: Dict[str, Tensor], prefix: str, query, key, value, i
         sd[prefix + "attn.in_proj_weight"], sd[prefix + "attn.in_proj_bias"],
         None, None, False, 0.0,
         sd[prefix + "attn.out_proj.weight"], sd[prefix + "attn.out_proj.bias"],
-        training=False, key_padding_mask=key_padding_mask, need_weights=True)
+        training=False, key_padding_mask=key_padding_mask, need_weights=True, attn_mask=attn_mask)
     return identity + out
 
 
@@ -240,13 +282,23 @@ def transformer(sd, x: Tensor, mask: Tensor, query_embed: Tensor, pos_embed: Ten
 # --------------------------------------------------------------------------------------
 # branches
 # --------------------------------------------------------------------------------------
-def cls_branch(sd, p: str, x: Tensor, num_reg_fcs=2) -> Tensor:
-    """petr_head.py:226-236: (Linear, LayerNorm, ReLU) x num_reg_fcs, Linear."""
+def normed_linear(x: Tensor, w: Tensor, b: Optional[Tensor], tempearture=20, power=1.0, eps=1e-6) -> Tensor:
+    """mmdet 2.24.1 NormedLinear.forward (mmdet/models/utils/normed_predictor.py; un-vendored, restated -- parity of
+    this piece is unpinned): both norms run over dim 1, which for the head's (B, Lq, E) activations is the query axis."""
+    w_ = w / (w.norm(dim=1, keepdim=True).pow(power) + eps)
+    x_ = x / (x.norm(dim=1, keepdim=True).pow(power) + eps)
+    return F.linear(x_ * tempearture, w_, b)
+
+
+def cls_branch(sd, p: str, x: Tensor, num_reg_fcs=2, normedlinear=False) -> Tensor:
+    """petr_head.py:226-236: (Linear, LayerNorm, ReLU) x num_reg_fcs, Linear | NormedLinear."""
     E = x.shape[-1]
     for i in range(num_reg_fcs):
         x = F.linear(x, sd[f"{p}{3 * i}.weight"], sd[f"{p}{3 * i}.bias"])
         x = F.relu(F.layer_norm(x, (E,), sd[f"{p}{3 * i + 1}.weight"], sd[f"{p}{3 * i + 1}.bias"], 1e-5))
     j = 3 * num_reg_fcs
+    if normedlinear:
+        return normed_linear(x, sd[f"{p}{j}.weight"], sd[f"{p}{j}.bias"])
     return F.linear(x, sd[f"{p}{j}.weight"], sd[f"{p}{j}.bias"])
 
 
@@ -292,27 +344,44 @@ def head_forward(sd: Dict[str, Tensor], feats: Tensor, img_metas: List[dict],
     masks = key_padding_masks(img_metas, B, N, H, W)
     x = F.conv2d(feats.flatten(0, 1), sd["input_proj.weight"], sd["input_proj.bias"])
     x = x.view(B, N, *x.shape[-3:])
-    assert c["with_position"] and c["with_multiview"], "oracle covers the shipped configs"
-    feat, cmask, _ = position_features(img_metas, B, N, H, W, masks, c["depth_num"],
-                                       c["depth_start"], c["position_range"], c["LID"])
-    pos = conv1x1_mlp(feat, sd["position_encoder.0.weight"], sd["position_encoder.0.bias"],
-                      sd["position_encoder.2.weight"], sd["position_encoder.2.bias"])
+    # positional encoding of the key masks: SinePositionalEncoding3D over all views (with_multiview), else a 2-D
+    # encoding evaluated per camera and concatenated (petr_head.py:403-409,:414-420)
+    kind = c.get("pos_kind", "sine3d")
+    if c["with_multiview"]:
+        assert kind == "sine3d"
+        sin = sine_positional_encoding_3d(masks, c["num_feats"], normalize=c["normalize"]).flatten(0, 1)
+    else:
+        per_cam = []
+        for i in range(N):
+            if kind == "sine2d":
+                per_cam.append(sine_positional_encoding_2d(masks[:, i], c["num_feats"], normalize=c["normalize"]).unsqueeze(1))
+            else:
+                per_cam.append(learned_positional_encoding_3d(sd, "positional_encoding.", masks[:, i]).unsqueeze(1))
+        sin = torch.cat(per_cam, 1).flatten(0, 1)
+    if c["with_multiview"] or c["with_position"]:
+        sin = conv1x1_mlp(sin, sd["adapt_pos3d.0.weight"], sd["adapt_pos3d.0.bias"],
+                          sd["adapt_pos3d.2.weight"], sd["adapt_pos3d.2.bias"])
+    sin = sin.view(x.shape)
     if taps is not None:
-        taps["coords_position_embeding"] = pos.view(x.shape)
-        taps["coords_mask"] = cmask
         taps["masks"] = masks
         taps["memory"] = x
-    if c["with_fpe"]:
-        # SELayer petrv2_head.py:48-60, called at petrv2_head.py:464-466
-        xf = x.flatten(0, 1)
-        se = F.conv2d(F.relu(F.conv2d(xf, sd["fpe.conv_reduce.weight"], sd["fpe.conv_reduce.bias"])),
-                      sd["fpe.conv_expand.weight"], sd["fpe.conv_expand.bias"])
-        pos = pos * torch.sigmoid(se)
-    pos = pos.view(x.shape)
-    sin = sine_positional_encoding_3d(masks, c["num_feats"], normalize=c["normalize"])
-    sin = conv1x1_mlp(sin.flatten(0, 1), sd["adapt_pos3d.0.weight"], sd["adapt_pos3d.0.bias"],
-                      sd["adapt_pos3d.2.weight"], sd["adapt_pos3d.2.bias"]).view(x.shape)
-    pos_embed = pos + sin
+    if c["with_position"]:
+        feat, cmask, _ = position_features(img_metas, B, N, H, W, masks, c["depth_num"],
+                                           c["depth_start"], c["position_range"], c["LID"])
+        pos = conv1x1_mlp(feat, sd["position_encoder.0.weight"], sd["position_encoder.0.bias"],
+                          sd["position_encoder.2.weight"], sd["position_encoder.2.bias"])
+        if taps is not None:
+            taps["coords_position_embeding"] = pos.view(x.shape)
+            taps["coords_mask"] = cmask
+        if c["with_fpe"]:
+            # SELayer petrv2_head.py:48-60, called at petrv2_head.py:464-466
+            xf = x.flatten(0, 1)
+            se = F.conv2d(F.relu(F.conv2d(xf, sd["fpe.conv_reduce.weight"], sd["fpe.conv_reduce.bias"])),
+                          sd["fpe.conv_expand.weight"], sd["fpe.conv_expand.bias"])
+            pos = pos * torch.sigmoid(se)
+        pos_embed = pos.view(x.shape) + sin
+    else:
+        pos_embed = sin
     ref = sd["reference_points.weight"]
     qe = pos2posemb3d(ref)
     qe = F.linear(F.relu(F.linear(qe, sd["query_embedding.0.weight"], sd["query_embedding.0.bias"])),
@@ -334,7 +403,8 @@ def head_forward(sd: Dict[str, Tensor], feats: Tensor, img_metas: List[dict],
         mean_ts = (ts[:, 1, :] - ts[:, 0, :]).mean(-1)
     cls_out, reg_out = [], []
     for l in range(outs_dec.shape[0]):
-        cls_out.append(cls_branch(sd, f"cls_branches.{l}.", outs_dec[l], c["num_reg_fcs"]))
+        cls_out.append(cls_branch(sd, f"cls_branches.{l}.", outs_dec[l], c["num_reg_fcs"],
+                                  normedlinear=c.get("normedlinear", False)))
         if c["with_multi"]:
             tmp = reg_layer_multi(sd, f"reg_branches.{l}.", outs_dec[l], c["num_reg_fcs"])
         else:

@@ -26,6 +26,7 @@ import warnings
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 REF_ROOT = os.environ.get("PETR_REFERENCE_ROOT", "/root/reference")
 _PLUGIN = os.path.join(REF_ROOT, "projects", "mmdet3d_plugin")
@@ -171,6 +172,7 @@ def _install_stubs():
         HEADS=_Registry("head"),
         LOSSES=_Registry("loss"),
         BBOX_CODERS=_Registry("bbox_coder"),
+        NECKS=_Registry("neck"),
     )
 
     mmcv = mod("mmcv")
@@ -185,6 +187,20 @@ def _install_stubs():
     base_module = mod("mmcv.runner.base_module")
     utils = mod("mmcv.utils")
 
+    class ConvModule(nn.Module):
+        """mmcv ConvModule restricted to what cp_fpn.py builds in every PETR config (norm_cfg = act_cfg = None):
+        a bare nn.Conv2d held as `.conv`."""
+
+        def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, conv_cfg=None, norm_cfg=None,
+                     act_cfg=None, inplace=True, **kwargs):
+            super().__init__()
+            assert conv_cfg is None and norm_cfg is None and act_cfg is None
+            self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding)
+
+        def forward(self, x):
+            return self.conv(x)
+
+    cnn.ConvModule = ConvModule
     cnn.Conv2d = nn.Conv2d
     cnn.Linear = nn.Linear
     cnn.build_activation_layer = _build_activation_layer
@@ -446,9 +462,22 @@ def _install_stubs():
             super().__init__(init_cfg)
 
     class NormedLinear(nn.Linear):
-        pass
+        """mmdet 2.24.1 normed_predictor.NormedLinear (published semantics; attribute spelling as upstream)."""
+
+        def __init__(self, *args, tempearture=20, power=1.0, eps=1e-6, **kwargs):
+            super().__init__(*args, **kwargs)
+            self.tempearture, self.power, self.eps = tempearture, power, eps
+            nn.init.normal_(self.weight, mean=0, std=0.01)
+            if self.bias is not None:
+                nn.init.constant_(self.bias, 0)
+
+        def forward(self, x):
+            weight_ = self.weight / (self.weight.norm(dim=1, keepdim=True).pow(self.power) + self.eps)
+            x_ = x / (x.norm(dim=1, keepdim=True).pow(self.power) + self.eps)
+            return F.linear(x_ * self.tempearture, weight_, self.bias)
 
     models.HEADS = R["HEADS"]
+    models.NECKS = R["NECKS"]
     models.build_loss = build_loss
     mutils.build_transformer = R["TRANSFORMER"].build
     mutils.NormedLinear = NormedLinear
@@ -497,7 +526,7 @@ def load_reference():
     for name in ("projects", "projects.mmdet3d_plugin", "projects.mmdet3d_plugin.core",
                  "projects.mmdet3d_plugin.core.bbox", "projects.mmdet3d_plugin.core.bbox.coders",
                  "projects.mmdet3d_plugin.models", "projects.mmdet3d_plugin.models.utils",
-                 "projects.mmdet3d_plugin.models.dense_heads"):
+                 "projects.mmdet3d_plugin.models.dense_heads", "projects.mmdet3d_plugin.models.necks"):
         if name not in sys.modules:
             m = types.ModuleType(name)
             m.__path__ = []
@@ -513,6 +542,7 @@ def load_reference():
     tfm = _load_by_path(p + "models.utils.petr_transformer", "models/utils/petr_transformer.py")
     head = _load_by_path(p + "models.dense_heads.petr_head", "models/dense_heads/petr_head.py")
     headv2 = _load_by_path(p + "models.dense_heads.petrv2_head", "models/dense_heads/petrv2_head.py")
+    cpfpn = _load_by_path(p + "models.necks.cp_fpn", "models/necks/cp_fpn.py")
     ns = types.SimpleNamespace(
         registries=R, PETRHead=head.PETRHead, PETRv2Head=headv2.PETRv2Head,
         PETRTransformer=tfm.PETRTransformer, PETRMultiheadAttention=tfm.PETRMultiheadAttention,
@@ -520,7 +550,7 @@ def load_reference():
         PETRTransformerDecoderLayer=tfm.PETRTransformerDecoderLayer,
         SinePositionalEncoding3D=posenc.SinePositionalEncoding3D,
         LearnedPositionalEncoding3D=posenc.LearnedPositionalEncoding3D,
-        NMSFreeCoder=coder.NMSFreeCoder, pos2posemb3d=head.pos2posemb3d,
+        NMSFreeCoder=coder.NMSFreeCoder, pos2posemb3d=head.pos2posemb3d, CPFPN=cpfpn.CPFPN,
         inverse_sigmoid=_inverse_sigmoid, head_module=head, headv2_module=headv2)
     _LOADED = ns
     return ns

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
 
 import torch
 
@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpetr_b200.so")
 
 _P, _I, _F = c_void_p, c_int, c_float
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); mirrors include/petr_b200.h one to one
 SIGNATURES = {
@@ -32,14 +32,15 @@ SIGNATURES = {
     "petr_sine3d_features": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _I, _P]),
     "petr_pos2posemb3d": (c_int, [_P, _P, _I, _I, _P, _P]),
     "petr_gemm_f32": (c_int, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
-    "petr_attention_f32": (c_int, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "petr_attention_f32": (c_int, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _P, _I, _P, _P, _F, c_uint64,
+                                   _I, _I, _I, _I, _I, _F, _P]),
     "petr_layernorm_multi_f32": (c_int, [_P, _P, _P, _F, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "petr_split_rows_bf16": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
     "petr_nchw_to_tokens_bf16": (c_int, [_P, _P, _I, _I, _I, _P]),
     "petr_layernorm_f32": (c_int, [_P, _P, _P, _P, _I, _I, _F, _I, _I, _P]),
     "petr_nms_free_decode": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P]),
     "petr_decode_boxes": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "petr_gemm_bf16_tc": (c_int, [_P, _I, _I, _P, _I, _P, _P, _I, _F, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "petr_gemm_bf16_tc": (c_int, [_P, _I, _I, _P, _I, _P, _P, _P, _I, _F, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "petr_position_mlp_fused": (c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P,
                                         _I, _I, _P, _P, _I, _P, _P, _P]),
     "petr_stage_small": (c_int, [_P, _P, _I, _P]),
@@ -52,6 +53,12 @@ SIGNATURES = {
     "petr_attention_x3_workspace_bytes": (c_int64, [_I, _I, _I, _I, _I]),
     "petr_attention_merge": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
     "petr_attention_partial_floats": (c_int64, [_I, _I, _I]),
+    "petr_sine2d_features": (c_int, [_P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _I, _P]),
+    "petr_learned_pos_features": (c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "petr_tokens_to_nchw_f32": (c_int, [_P, _P, _I, _I, _I, _P]),
+    "petr_upsample_add_tokens": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "petr_im2col3x3_tokens": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "petr_norm_scale_f32": (c_int, [_P, _P, _I, _I, _I, _I, _F, _F, _F, _P]),
 }
 
 _lib = None

@@ -43,6 +43,15 @@ void* debug_trace();
 #define PETR_REQUIRE(cond, code, ...) \
     do { if (!(cond)) return ::petr::fail((code), __VA_ARGS__); } while (0)
 
+// Counter-based dropout decision shared by forward and backward kernels: splitmix64 of (seed, element index).
+__host__ __device__ inline bool dropout_keep(uint64_t seed, uint64_t idx, float p) {
+    uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.f / 16777216.f) >= p;
+}
+
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace petr

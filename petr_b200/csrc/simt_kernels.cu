@@ -379,7 +379,8 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk,
                      const float* __restrict__ V, int ldv, const uint8_t* __restrict__ key_mask,
                      float* __restrict__ O, int ldo, __nv_bfloat16* __restrict__ O_split, int E,
-                     int Lq, int Lk, float scale_log2) {
+                     int Lq, int Lk, float scale_log2, const float* __restrict__ attn_bias,
+                     int64_t bias_bh_stride, float* __restrict__ lse, float drop_p, uint64_t seed) {
     // rows padded to 36 floats: the four lanes of a quad read four different rows per LDS.128 and
     // a 32-float pitch would put them on the same banks
     __shared__ __align__(16) float sK[ATT_KT][36];
@@ -401,6 +402,12 @@ attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restri
         }
     }
     float m = -INFINITY, l = 0.f;
+    // attn_mask of torch.nn.MultiheadAttention as an additive fp32 bias [Lq, Lk] (bias_bh_stride 0) or
+    // [B*heads, Lq, Lk]; attention-probability dropout (training) is a counter-based hash of (row, key)
+    const int bh = b * gridDim.y + head;
+    const float* brow = attn_bias ? attn_bias + (int64_t)bh * bias_bh_stride + (int64_t)(live ? q : 0) * Lk : nullptr;
+    const uint64_t drop_row = ((uint64_t)bh * Lq + (live ? q : 0)) * (uint64_t)Lk;
+    const float drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     const float* Kb = K + (int64_t)b * Lk * ldk + head * 32;
     const float* Vb = V + (int64_t)b * Lk * ldv + head * 32;
     for (int k0 = 0; k0 < Lk; k0 += ATT_KT) {
@@ -438,6 +445,7 @@ attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restri
                     a1 = fmaf(qv[i + 6], k1v.z, a1); a1 = fmaf(qv[i + 7], k1v.w, a1);
                 }
                 s[j] = (a0 + a1) + sBias[r];
+                if (brow && k0 + r < Lk) s[j] += brow[k0 + r] * 1.4426950408889634f;
                 mx = fmaxf(mx, s[j]);
             }
             if (mx == -INFINITY) continue;             // everything so far masked
@@ -451,6 +459,7 @@ attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restri
                 const int r = g * 32 + j * 4 + sub;
                 float pj = exp2f(s[j] - mx);
                 l += pj;
+                if (drop_p > 0.f) pj = dropout_keep(seed, drop_row + (uint64_t)(k0 + r), drop_p) ? pj * drop_scale : 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     float4 vv = *reinterpret_cast<const float4*>(&sV[r][i]);
@@ -476,6 +485,8 @@ attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restri
         }
         m = mn;
     }
+    if (live && lse && sub == 0)                       // log2-domain log-sum-exp of the scaled scores (backward)
+        lse[((int64_t)bh) * Lq + q] = m + log2f(l);
     if (live) {
         const float inv = 1.f / l;                     // l == 0 (all keys masked) -> NaN, as torch
         // lane `sub` writes dims [8*sub, 8*sub+8)
@@ -876,18 +887,20 @@ extern "C" int petr_gemm_f32(const float* A, int lda, int a_layout, int hw, cons
 }
 
 extern "C" int petr_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V,
-                                  int ldv, const uint8_t* key_mask, float* O, int ldo, void* O_split,
+                                  int ldv, const uint8_t* key_mask, const float* attn_bias, int bias_per_head,
+                                  float* O, int ldo, void* O_split, float* lse, float drop_p, uint64_t seed,
                                   int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream) {
     PETR_REQUIRE(Q && K && V && (O || O_split), PETR_E_BADARG, "petr_attention_f32: null pointer");
     PETR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0, PETR_E_BADARG, "petr_attention_f32: bad dimension");
     PETR_REQUIRE(head_dim == 32, PETR_E_SHAPE, "petr_attention_f32: head_dim must be 32, got %d", head_dim);
+    PETR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, PETR_E_BADARG, "petr_attention_f32: drop_p must be in [0, 1)");
     PETR_REQUIRE((ldk & 3) == 0 && (ldv & 3) == 0 && aligned16(K) && aligned16(V) && (ldq & 3) == 0 && aligned16(Q),
                  PETR_E_ALIGN, "petr_attention_f32: Q/K/V rows must be 16-byte aligned");
     if (O) PETR_REQUIRE((ldo & 3) == 0 && aligned16(O), PETR_E_ALIGN, "petr_attention_f32: O rows must be 16-byte aligned");
     dim3 grid((Lq + ATT_QPB - 1) / ATT_QPB, heads, B);
     attention_f32_kernel<<<grid, ATT_THREADS, 0, (cudaStream_t)stream>>>(
         Q, ldq, K, ldk, V, ldv, key_mask, O, ldo, (__nv_bfloat16*)O_split, heads * 32, Lq, Lk,
-        scale * 1.4426950408889634f);
+        scale * 1.4426950408889634f, attn_bias, bias_per_head ? (int64_t)Lq * Lk : 0, lse, drop_p, seed);
     return after_launch("petr_attention_f32");
 }
 

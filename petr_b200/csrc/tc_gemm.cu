@@ -59,7 +59,7 @@ constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers
 constexpr int GEMM_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 
 struct EpiParams {
-    const float* bias; const float* residual; int act; float alpha;
+    const float* bias; const float* residual; const float* gate; int act; float alpha;
     void* C; void* C2; int ldc; int out_mode;
     int M, N, K; int a_k_wrap; int kv_Lk; int kv_B; int kv_E;
     int tiles_m, tiles_n, band;
@@ -295,6 +295,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
+                if (p.act == PETR_ACT_SIGMOID_GATE) {                  // PETRv2 SELayer: gate[m,n] * sigmoid(acc + bias)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+                }
                 if (p.alpha != 1.f) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
@@ -333,6 +337,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C2) + (int64_t)mr * p.ldc + col) = x;
                                 continue;
                             }
+                            if (p.gate) {
+                                const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gate + (int64_t)mr * p.ldc + col));
+                                x.x *= g4.x; x.y *= g4.y; x.z *= g4.z; x.w *= g4.w;
+                            }
                             if (p.residual) {
                                 const float4 q4 = res4[hh * 4 + i];
                                 x.x += q4.x; x.y += q4.y; x.z += q4.z; x.w += q4.w;
@@ -363,6 +371,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     continue;
                 }
                 if (m >= p.M) continue;
+                if (p.gate) {
+                    const float* gp = p.gate + (int64_t)m * p.ldc + nb;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (nb + j < p.N) v[j] *= gp[j];
+                }
                 if (p.residual) {
                     const float* rp = p.residual + (int64_t)m * p.ldc + nb;
                     if (full && ((p.ldc & 3) == 0)) {
@@ -492,7 +505,7 @@ extern "C" int petr_nchw_to_tokens_bf16(const float* x, void* out, int G, int C,
 }
 
 extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const void* W, int ldw,
-                                 const float* bias, const float* residual, int act, float alpha,
+                                 const float* bias, const float* residual, const float* gate, int act, float alpha,
                                  void* C, void* C2, int ldc, int out_mode, int M, int N, int K,
                                  int kv_Lk, void* stream) {
     PETR_REQUIRE(A && W && C, PETR_E_BADARG, "petr_gemm_bf16_tc: null pointer");
@@ -503,10 +516,15 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
                  "petr_gemm_bf16_tc: a_k_wrap must be a multiple of 64 with K/2 <= a_k_wrap <= K");
     PETR_REQUIRE(lda >= a_k_wrap && ldw >= K && (lda % 8) == 0 && (ldw % 8) == 0 && aligned16(A) && aligned16(W),
                  PETR_E_ALIGN, "petr_gemm_bf16_tc: A/W rows must be 16-byte aligned");
-    PETR_REQUIRE(act == PETR_ACT_NONE || act == PETR_ACT_RELU, PETR_E_BADARG, "petr_gemm_bf16_tc: bad act");
+    PETR_REQUIRE(act == PETR_ACT_NONE || act == PETR_ACT_RELU || act == PETR_ACT_SIGMOID_GATE, PETR_E_BADARG,
+                 "petr_gemm_bf16_tc: bad act");
+    PETR_REQUIRE((act == PETR_ACT_SIGMOID_GATE) == (gate != nullptr), PETR_E_BADARG,
+                 "petr_gemm_bf16_tc: PETR_ACT_SIGMOID_GATE needs a gate array (and only it)");
+    if (gate) PETR_REQUIRE((out_mode == 0 || out_mode == 1 || out_mode == 3) && aligned16(gate) && ldc >= N, PETR_E_SHAPE,
+                           "petr_gemm_bf16_tc: a gate needs out_mode 0, 1 or 3 and a 16-byte aligned [M, ldc] array");
     PETR_REQUIRE(out_mode >= 0 && out_mode <= 5, PETR_E_BADARG, "petr_gemm_bf16_tc: bad out_mode");
     EpiParams p{};
-    p.bias = bias; p.residual = residual; p.act = act; p.alpha = alpha;
+    p.bias = bias; p.residual = residual; p.gate = gate; p.act = act; p.alpha = alpha;
     p.C = C; p.C2 = C2; p.ldc = ldc; p.out_mode = out_mode;
     p.M = M; p.N = N; p.K = K; p.a_k_wrap = a_k_wrap;
     p.staged = (out_mode == 2 && tuning::gemm_staged()) ? 1 : 0;

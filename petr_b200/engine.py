@@ -201,8 +201,9 @@ class HeadSpec:
 
     def __init__(self, head):
         self.E = head.embed_dims
-        self.heads = head.transformer.decoder.layers[0].attentions[1].num_heads
-        self.L = len(head.transformer.decoder.layers)
+        tr = getattr(head, "transformer", None)            # None: a head used for position_embeding only (DepthrHead)
+        self.heads = tr.decoder.layers[0].attentions[1].num_heads if tr is not None else 8
+        self.L = len(tr.decoder.layers) if tr is not None else 0
         self.Lq = head.num_query
         self.D = head.depth_num
         self.lid = bool(head.LID)
@@ -219,8 +220,19 @@ class HeadSpec:
         self.with_multi = getattr(head, "with_multi", False)
         self.shared_branches = head.cls_branches[0] is head.cls_branches[-1]
         pe = head.positional_encoding
-        self.sine = dict(num_feats=pe.num_feats, temperature=pe.temperature, normalize=pe.normalize,
-                         scale=pe.scale, eps=pe.eps, offset=pe.offset)
+        # 'sine3d' (SinePositionalEncoding3D, with_multiview=True), or the per-camera 2-D encodings of the
+        # with_multiview=False branch (petr_head.py:403-409): 'sine2d' (mmdet SinePositionalEncoding) / 'learned'
+        self.pos_kind = getattr(pe, "kind", "sine3d")
+        if self.with_multiview != (self.pos_kind == "sine3d"):
+            raise ValueError(f"with_multiview={self.with_multiview} needs a "
+                             f"{'3-D' if self.with_multiview else '2-D (per camera)'} positional encoding, "
+                             f"got {type(pe).__name__} (the reference fails on the mask rank here too)")
+        self.normedlinear = bool(getattr(head, "normedlinear", False))
+        if self.pos_kind == "learned":
+            self.sine = None
+        else:
+            self.sine = dict(num_feats=pe.num_feats, temperature=pe.temperature, normalize=pe.normalize,
+                             scale=pe.scale, eps=pe.eps, offset=pe.offset)
         if self.lid:
             self.bin_size = (self.position_range[3] - self.depth_start) / (self.D * (1 + self.D))
         else:
@@ -282,9 +294,14 @@ class HeadEngine:
                 f2_w=sd[p + "ffns.0.layers.1.weight"], f2_b=sd[p + "ffns.0.layers.1.bias"],
                 ln=[(sd[p + f"norms.{i}.weight"], sd[p + f"norms.{i}.bias"]) for i in range(3)]))
         P["layers"] = layers
-        P["post_norm"] = (sd["transformer.decoder.post_norm.weight"], sd["transformer.decoder.post_norm.bias"])
+        if s.L:
+            P["post_norm"] = (sd["transformer.decoder.post_norm.weight"], sd["transformer.decoder.post_norm.bias"])
         P["ref"] = sd["reference_points.weight"]
-        P["dim_t_sine"] = sine_dim_t(s.sine["num_feats"], s.sine["temperature"]).to(device)
+        if s.sine is not None:
+            P["dim_t_sine"] = sine_dim_t(s.sine["num_feats"], s.sine["temperature"]).to(device)
+        else:
+            P["row_embed"] = sd["positional_encoding.row_embed.weight"]
+            P["col_embed"] = sd["positional_encoding.col_embed.weight"]
         P["dim_t_query"] = sine_dim_t(128, 10000).to(device)
         if s.with_multi:
             for l in range(s.L):
@@ -315,6 +332,18 @@ class HeadEngine:
         h = ops.gemm_f32(feat, P["pe_w1"], P["pe_b1"], act=ACT_RELU)
         pos = ops.gemm_f32(h, P["pe_w2"], P["pe_b2"])
         return pos, cmask
+
+    def pos_features(self, P, masks: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+        """The positional-encoding features of petr_head.py:399-420 as tokens: SinePositionalEncoding3D over all
+        views (with_multiview), else the 2-D encoding evaluated per camera.  masks uint8 (b,N,H,W)."""
+        s = self.spec
+        b, N, H, W = masks.shape
+        if s.pos_kind == "sine3d":
+            return ops.sine3d_features(masks, P["dim_t_sine"], dtype=dtype, **_sine_args(s))
+        if s.pos_kind == "sine2d":
+            return ops.sine2d_features(masks.view(b * N, H, W), P["dim_t_sine"], dtype=dtype, **_sine_args(s))
+        out = ops.learned_pos_features(P["row_embed"], P["col_embed"], b * N, H, W)
+        return out if dtype == torch.float32 else ops.add_rows_bf16(out, torch.zeros_like(out[:1]))
 
     def query_embeds(self, P) -> torch.Tensor:
         sd = P["sd"]
@@ -348,13 +377,25 @@ class HeadEngine:
         return ops.layernorm(y, *lw["ln"][2], out=y)
 
     # branches -----------------------------------------------------------------------------
-    def _cls_branch(self, sd, p, x):
+    def _cls_branch(self, sd, p, x, B=None):
         s = self.spec
         for i in range(s.num_reg_fcs):
             x = ops.gemm_f32(x, sd[f"{p}{3 * i}.weight"], sd[f"{p}{3 * i}.bias"])
             x = ops.layernorm(x, sd[f"{p}{3 * i + 1}.weight"], sd[f"{p}{3 * i + 1}.bias"], relu=True, out=x)
         j = 3 * s.num_reg_fcs
-        return ops.gemm_f32(x, sd[f"{p}{j}.weight"], sd[f"{p}{j}.bias"])
+        return self.cls_last(sd, p, x, B)
+
+    def cls_last(self, sd, p, x, B, out=None):
+        """Last layer of the cls branch: Linear, or mmdet NormedLinear when normedlinear=True (petr_head.py:231-234;
+        its x.norm(dim=1) runs over the QUERY axis of the (B, Lq, E) activations the head passes)."""
+        s = self.spec
+        j = 3 * s.num_reg_fcs
+        w, b = sd[f"{p}{j}.weight"], sd[f"{p}{j}.bias"]
+        if s.normedlinear:
+            nl = self._head.cls_branches[0][-1]
+            w = ops.norm_scale(w, 1, w.shape[0], False, nl.power, nl.eps, 1.0)
+            x = ops.norm_scale(x.contiguous(), x.shape[0] // s.Lq, s.Lq, True, nl.power, nl.eps, nl.tempearture)
+        return ops.gemm_f32(x, w, b, out=out)
 
     def _reg_branch(self, P, l, p, x):
         s = self.spec
@@ -422,7 +463,12 @@ class HeadEngine:
         P = self.packed(dev)
         masks = self.masks(mi, H, W)
         mem = ops.gemm_f32(x, P["in_w"], P["in_b"], nchw_hw=H * W)                  # (T,E)
-        sf = ops.sine3d_features(masks, P["dim_t_sine"], **_sine_args(s))
+        sf = self.pos_features(P, masks)
+        if not s.with_position and not s.with_multiview:
+            pos = sf                                      # petr_head.py:414-420: no adapt_pos3d on this branch
+            if taps is not None:
+                taps.update(masks=masks, memory=mem, pos_embed=pos)
+            return dict(precision="fp32", B=B, Lk=Lk, mem=mem, pos=pos, kmask=masks.view(B, Lk))
         h2 = ops.gemm_f32(sf, P["ad_w1"], P["ad_b1"], act=ACT_RELU)
         if s.with_position:
             pos, _ = self.position_embedding_tokens(P, mi, B, N, H, W, masks)
@@ -457,8 +503,6 @@ class HeadEngine:
         if precision not in ("fp32", "bf16"):
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
         s = self.spec
-        if not s.with_multiview:
-            raise NotImplementedError("petr_b200 implements with_multiview=True (all shipped configs)")
         B, N, Cin, H, W = x.shape
         host = host_prep(img_metas, N, H, W, s.with_time)
         if use_graph and taps is None:

@@ -53,6 +53,9 @@ def packed_tc(eng, device) -> dict:
     if s.with_position:
         T["pe_w1"] = P["pe_w1"].to(bf).contiguous()
         T["pe_w2"] = P["pe_w2"].to(bf).contiguous()
+    if s.with_fpe:
+        T["fpe_wr"] = x3(P["fpe_wr"])
+        T["fpe_we"] = x3(P["fpe_we"])
     T["ad_w1"] = P["ad_w1"].to(bf).contiguous()
     T["ad_w2"] = P["ad_w2"].to(bf).contiguous()
     T["wk"] = torch.cat([lw["ca_in_w"][E:2 * E] for lw in P["layers"]], 0).to(bf).contiguous()
@@ -135,11 +138,16 @@ def key_side_tc(eng, x, mi: MetaInputs, taps=None, views: slice = None):
     # sample and broadcast over the batch instead of B times.
     dedup = DEDUP_SINE and mi.uniform_masks and B > 1
     m_sine = masks_all[:1] if dedup else masks_all
-    sf = ops.sine3d_features(m_sine, P["dim_t_sine"], dtype=torch.bfloat16, **_sine_args(s))
+    raw_pos = not s.with_position and not s.with_multiview      # petr_head.py:414-420: encoding used as is
+    sf = eng.pos_features(P, m_sine, torch.float32 if raw_pos else torch.bfloat16)
     if views is not None:
         sf = sf.view(m_sine.shape[0], N_all, H * W, -1)[:, views].reshape(m_sine.shape[0] * Lk, -1).contiguous()
-    h2 = ops.gemm_bf16_tc(sf, T["ad_w1"], P["ad_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_adapt1")
-    sin1 = ops.gemm_bf16_tc(h2, T["ad_w2"], P["ad_b2"], name="gemm_adapt2") if dedup else None   # (Lk, E) fp32
+    if raw_pos:
+        h2, sin1 = None, sf                                                              # (Lk | B*Lk, E) fp32
+        dedup = True                                     # add_rows_bf16 below takes either period
+    else:
+        h2 = ops.gemm_bf16_tc(sf, T["ad_w1"], P["ad_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_adapt1")
+        sin1 = ops.gemm_bf16_tc(h2, T["ad_w2"], P["ad_b2"], name="gemm_adapt2") if dedup else None   # (Lk, E) fp32
     fused = s.with_position and FUSED_POSITION_MLP and s.D == 64 and tuple(T["pe_w1"].shape) == (1024, 192) and \
         tuple(T["pe_w2"].shape) == (256, 1024)
     # input_proj (petr_head.py:390): fp32 NCHW -> bf16 tokens -> tcgen05 GEMM.  One accumulator, two results
@@ -147,12 +155,13 @@ def key_side_tc(eng, x, mi: MetaInputs, taps=None, views: slice = None):
     # single residual of the fused position MLP whose bf16 output is then directly the K-projection input.
     xt = ops.nchw_to_tokens_bf16(x.view(B * N, Cin, H, W))
     mem = torch.empty((B * Lk, E), dtype=torch.float32, device=dev)
-    fold_sine = dedup and fused and not s.with_fpe
+    fold_sine = dedup and fused and not s.with_fpe and not raw_pos and sin1.shape[0] == Lk
     if fold_sine:
         vin = ops.gemm_bf16_tc(xt, T["in_w"], P["in_b"], residual=sin1, residual_period=Lk, out_f32=mem,
                                name="gemm_input_proj")
     else:
-        vin = ops.gemm_bf16_tc(xt, T["in_w"], P["in_b"], split_out=True, out_f32=mem, name="gemm_input_proj")[:, :E]
+        vin_split = ops.gemm_bf16_tc(xt, T["in_w"], P["in_b"], split_out=True, out_f32=mem, name="gemm_input_proj")
+        vin = vin_split[:, :E]
     kin = None
     if s.with_position:
         res = None if s.with_fpe else mem                       # mem + position MLP in the epilogue
@@ -172,8 +181,12 @@ def key_side_tc(eng, x, mi: MetaInputs, taps=None, views: slice = None):
             h1 = ops.gemm_bf16_tc(feat, T["pe_w1"], P["pe_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_pe1")
             pos = ops.gemm_bf16_tc(h1, T["pe_w2"], P["pe_b2"], residual=res, name="gemm_pe2")
         if s.with_fpe:
-            se = ops.gemm_f32(mem, P["fpe_wr"], P["fpe_br"], act=ACT_RELU)
-            pos = ops.gemm_f32(se, P["fpe_we"], P["fpe_be"], act=ACT_SIGMOID_GATE, gate=pos, residual=mem)
+            # SELayer (petrv2_head.py:48-60,:464-466) as two bf16x3 tcgen05 GEMMs on the [hi | lo] tokens input_proj
+            # already emitted; the gate x position embedding product and the "+ memory" are the second epilogue
+            se = ops.gemm_bf16_tc(vin_split, T["fpe_wr"], P["fpe_br"], act=ACT_RELU, x3=True, split_out=True,
+                                  name="gemm_fpe")
+            pos = ops.gemm_bf16_tc(se, T["fpe_we"], P["fpe_be"], act=ACT_SIGMOID_GATE, gate=pos, residual=mem, x3=True,
+                                   name="gemm_fpe")
     else:
         pos = mem
     if kin is None:
@@ -280,7 +293,7 @@ def branches_tc(eng, P, outs, outs_split, B: int, time_div=None):
             yf = torch.empty((n, E), dtype=torch.float32, device=dev)
             ops.layernorm_multi(y, sd[f"{c}{3 * i + 1}.weight"], sd[f"{c}{3 * i + 1}.bias"], Y=yf, Y_split=h, relu=True)
         j = 3 * s.num_reg_fcs
-        ops.gemm_f32(yf, sd[f"{c}{j}.weight"], sd[f"{c}{j}.bias"], out=cls[rows])
+        eng.cls_last(sd, c, yf, B, out=cls[rows])
         if s.with_multi:
             h = xs
             for i in range(s.num_reg_fcs):

@@ -50,6 +50,17 @@ def _rows(t: torch.Tensor, batch_first: bool):
     return t.contiguous().view(B * L, E), B, L
 
 
+def set_precision(module: nn.Module, precision: str) -> nn.Module:
+    """Sets the precision path ('bf16' = tcgen05 kernels, 'fp32' = exact FFMA kernels) of every attention / FFN brick,
+    neck and head below `module`."""
+    if precision not in ("fp32", "bf16"):
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+    for m in module.modules():
+        if hasattr(type(m), "precision") or "precision" in m.__dict__:
+            m.precision = precision
+    return module
+
+
 class BaseModule(nn.Module):
     def __init__(self, init_cfg=None):
         super().__init__()
@@ -90,14 +101,33 @@ class PETRMultiheadAttention(BaseModule):
         self.proj_drop = nn.Dropout(proj_drop)
         self.dropout_layer = nn.Dropout(dropout_layer['drop_prob']) if dropout_layer else nn.Identity()
 
+    # 'bf16': projections as bf16x3 tcgen05 GEMMs, the core as the flash (cross) / x3 (self) tcgen05 kernels --
+    # the same kernels the head engine launches; 'fp32': the exact fp32 kernels.  Shapes the tensor-core kernels
+    # are not specialised for (embed_dims != 256 or 8 heads of 32) always take the fp32 kernels.
+    precision = 'bf16'
+
+    @staticmethod
+    def _attn_bias(attn_mask, B, heads, Lq, Lk):
+        """torch.nn.MultiheadAttention's attn_mask (bool: True = masked, or additive float; (Lq,Lk) or
+        (B*heads,Lq,Lk)) -> contiguous additive fp32."""
+        if attn_mask is None:
+            return None
+        if attn_mask.dtype == torch.bool or attn_mask.dtype == torch.uint8:
+            attn_mask = torch.zeros(attn_mask.shape, dtype=torch.float32, device=attn_mask.device).masked_fill_(
+                attn_mask.bool(), float('-inf'))
+        attn_mask = attn_mask.float().contiguous()
+        if tuple(attn_mask.shape) not in ((Lq, Lk), (B * heads, Lq, Lk)):
+            raise RuntimeError(f"attn_mask shape {tuple(attn_mask.shape)} must be {(Lq, Lk)} or {(B * heads, Lq, Lk)}")
+        return attn_mask
+
     @torch.no_grad()
     def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None,
                 attn_mask=None, key_padding_mask=None, **kwargs):
         _require_eval(self)
-        if attn_mask is not None:
-            raise NotImplementedError("attn_mask is never passed on the PETR path (petr_transformer.py:357-362)")
         if not query.is_cuda:
             raise RuntimeError("petr_b200: CUDA tensors required (no CPU fallback)")
+        self_attn = key is None or key is query
+        same_kq_pos = key_pos is query_pos or (key_pos is None and query_pos is not None)
         if key is None:
             key = query
         if value is None:
@@ -119,17 +149,66 @@ class PETRMultiheadAttention(BaseModule):
         idn, _, _ = _rows(identity.float(), bf)
         qp = _rows(query_pos.float().expand_as(query), bf)[0] if query_pos is not None else None
         kp = _rows(key_pos.float().expand_as(key), bf)[0] if key_pos is not None else None
-        w = self.attn.in_proj_weight.detach().float().contiguous()
-        b = self.attn.in_proj_bias.detach().float().contiguous()
-        Q = ops.gemm_f32(q, w[:E], b[:E], A2=qp)
-        K = ops.gemm_f32(k, w[E:2 * E], b[E:2 * E], A2=kp)
-        V = ops.gemm_f32(v, w[2 * E:], b[2 * E:])
         km = key_padding_mask.to(torch.uint8).contiguous() if key_padding_mask is not None else None
-        o = ops.attention_f32(Q, K, V, km, B, Lq, Lk, self.num_heads)
-        out = ops.gemm_f32(o, self.attn.out_proj.weight.detach().float().contiguous(),
-                           self.attn.out_proj.bias.detach().float().contiguous(), residual=idn)
+        bias = self._attn_bias(attn_mask, B, self.num_heads, Lq, Lk)
+        tc_ok = self.precision == 'bf16' and E == 256 and self.num_heads == 8 and bias is None
+        if tc_ok:
+            out = self._forward_tc(q, k, v, idn, qp, kp, km, B, Lq, Lk, self_attn and value is key,
+                                   self_attn and same_kq_pos and (kp is None) == (qp is None))
+        else:
+            w = self.attn.in_proj_weight.detach().float().contiguous()
+            b = self.attn.in_proj_bias.detach().float().contiguous()
+            Q = ops.gemm_f32(q, w[:E], b[:E], A2=qp)
+            K = ops.gemm_f32(k, w[E:2 * E], b[E:2 * E], A2=kp)
+            V = ops.gemm_f32(v, w[2 * E:], b[2 * E:])
+            o = ops.attention_f32(Q, K, V, km, B, Lq, Lk, self.num_heads, attn_bias=bias)
+            out = ops.gemm_f32(o, self.attn.out_proj.weight.detach().float().contiguous(),
+                               self.attn.out_proj.bias.detach().float().contiguous(), residual=idn)
         out = out.view(B, Lq, E)
         return out if bf else out.transpose(0, 1)
+
+    def _tc_weights(self):
+        """[hi|hi|lo] / bf16 packs of the projection weights, rebuilt when a parameter's version changes."""
+        sig = tuple((p.data_ptr(), p._version) for p in (self.attn.in_proj_weight, self.attn.in_proj_bias,
+                                                         self.attn.out_proj.weight, self.attn.out_proj.bias))
+        c = getattr(self, "_tc_cache", None)
+        if c is None or c[0] != sig:
+            E = self.embed_dims
+            w = self.attn.in_proj_weight.detach().float()
+            b = self.attn.in_proj_bias.detach().float()
+            d = dict(q=ops.x3_weight(w[:E]), k=ops.x3_weight(w[E:2 * E]), v=ops.x3_weight(w[2 * E:]),
+                     k16=w[E:2 * E].to(torch.bfloat16).contiguous(), v16=w[2 * E:].to(torch.bfloat16).contiguous(),
+                     bq=b[:E].contiguous(), bk=b[E:2 * E].contiguous(), bv=b[2 * E:].contiguous(),
+                     o=ops.x3_weight(self.attn.out_proj.weight.detach().float()),
+                     bo=self.attn.out_proj.bias.detach().float().contiguous())
+            self._tc_cache = c = (sig, d)
+        return c[1]
+
+    def _forward_tc(self, q, k, v, idn, qp, kp, km, B, Lq, Lk, self_attn, same_kq):
+        """Tensor-core path on (B*L, E) rows.  Self-attention (short key axis, fp32-class accuracy needed on the
+        residual stream): hi/lo-split x3 kernel; cross-attention: bf16 K / V and the flash kernel."""
+        from .engine_tc import Q_SCALE, choose_nsplit
+        T = self._tc_weights()
+        g = ops.gemm_bf16_tc
+        heads = self.num_heads
+        dev = q.device
+        o_s = torch.empty((B * Lq, 2 * self.embed_dims), dtype=torch.bfloat16, device=dev)
+        qs = ops.split_rows(q, add=qp)
+        if self_attn:
+            ks = qs if same_kq else ops.split_rows(k, add=kp)
+            Qp = g(qs, T["q"], T["bq"], x3=True, headsplit_Lk=Lq, headsplit_pair=True, name="gemm_q_side")
+            Kp = g(ks, T["k"], T["bk"], x3=True, headsplit_Lk=Lk, headsplit_pair=True, name="gemm_q_side")
+            Vp = g(ops.split_rows(v), T["v"], T["bv"], x3=True, headsplit_Lk=Lk, headsplit_pair=True, name="gemm_q_side")
+            ops.attention_x3_tc(Qp[:, 0], Kp[:, 0], Vp[:, 0], km, B, Lq, Lk, heads, out_split=o_s, want_f32=False)
+        else:
+            Qh = g(qs, T["q"], T["bq"], x3=True, alpha=Q_SCALE, headsplit_Lk=Lq, name="gemm_q_side")
+            kin = ops.add_rows_bf16(k, kp) if kp is not None else ops.add_rows_bf16(k, torch.zeros_like(k[:1]))
+            vin = kin if (v is k and kp is None) else ops.add_rows_bf16(v, torch.zeros_like(v[:1]))
+            Kh = g(kin, T["k16"], T["bk"], headsplit_Lk=Lk, name="gemm_kproj")
+            Vh = g(vin, T["v16"], T["bv"], headsplit_Lk=Lk, name="gemm_vproj")
+            ops.cross_attention_bf16(Qh[0], Kh[0], Vh[0], km, B, Lq, Lk, heads, choose_nsplit(B, heads, Lq, Lk),
+                                     out_split=o_s, want_f32=False)
+        return g(o_s, T["o"], T["bo"], residual=idn.contiguous(), x3=True, name="gemm_q_side")
 
 
 @ATTENTION.register_module()
@@ -163,12 +242,29 @@ class FFN(BaseModule):
         self.embed_dims = embed_dims
         self.num_fcs = num_fcs
 
+    precision = 'bf16'        # bf16x3 tcgen05 GEMMs (fp32-class accuracy); 'fp32': exact fp32 FFMA kernels
+
     @torch.no_grad()
     def forward(self, x, identity=None):
         _require_eval(self)
+        if not x.is_cuda:
+            raise RuntimeError("petr_b200: CUDA tensors required (no CPU fallback)")
         shape = x.shape
         h = x.float().contiguous().view(-1, shape[-1])
         idn = h if identity is None else identity.float().contiguous().view(-1, shape[-1])
+        lins = [self.layers[i][0] for i in range(self.num_fcs - 1)] + [self.layers[self.num_fcs - 1]]
+        if self.precision == 'bf16' and all(l.in_features % 64 == 0 and l.out_features % 32 == 0 for l in lins):
+            sig = tuple((l.weight.data_ptr(), l.weight._version) for l in lins)
+            c = getattr(self, "_tc_cache", None)
+            if c is None or c[0] != sig:
+                self._tc_cache = c = (sig, [ops.x3_weight(l.weight.detach().float()) for l in lins])
+            hs = ops.split_rows(h)
+            for i, l in enumerate(lins[:-1]):
+                hs = ops.gemm_bf16_tc(hs, c[1][i], l.bias.detach().float(), act=ACT_RELU, x3=True, split_out=True,
+                                      name="gemm_q_side")
+            out = ops.gemm_bf16_tc(hs, c[1][-1], lins[-1].bias.detach().float(),
+                                   residual=idn if self.add_identity else None, x3=True, name="gemm_q_side")
+            return out.view(shape)
         for i in range(self.num_fcs - 1):
             lin = self.layers[i][0]
             h = ops.gemm_f32(h, lin.weight.detach().contiguous(), lin.bias.detach(), act=ACT_RELU)
@@ -245,13 +341,21 @@ class BaseTransformerLayer(BaseModule):
         _require_eval(self)
         norm_index = attn_index = ffn_index = 0
         identity = query
-        if attn_masks is not None:
-            raise NotImplementedError("attn_masks are never passed on the PETR path")
+        # multi_atten_decoder_layer.py:215-232
+        if attn_masks is None:
+            attn_masks = [None for _ in range(self.num_attn)]
+        elif isinstance(attn_masks, torch.Tensor):
+            attn_masks = [copy.deepcopy(attn_masks) for _ in range(self.num_attn)]
+            warnings.warn(f'Use same attn_mask in all attentions in {self.__class__.__name__} ')
+        else:
+            assert len(attn_masks) == self.num_attn, f'The length of attn_masks {len(attn_masks)} must be equal ' \
+                f'to the number of attention in operation_order {self.num_attn}'
         for layer in self.operation_order:
             if layer == 'self_attn':
                 query = self.attentions[attn_index](
                     query, query, query, identity if self.pre_norm else None, query_pos=query_pos,
-                    key_pos=query_pos, key_padding_mask=query_key_padding_mask, **kwargs)
+                    key_pos=query_pos, attn_mask=attn_masks[attn_index],
+                    key_padding_mask=query_key_padding_mask, **kwargs)
                 attn_index += 1
                 identity = query
             elif layer == 'norm':
@@ -260,7 +364,8 @@ class BaseTransformerLayer(BaseModule):
             elif layer == 'cross_attn':
                 query = self.attentions[attn_index](
                     query, key, value, identity if self.pre_norm else None, query_pos=query_pos,
-                    key_pos=key_pos, key_padding_mask=key_padding_mask, **kwargs)
+                    key_pos=key_pos, attn_mask=attn_masks[attn_index], key_padding_mask=key_padding_mask,
+                    **kwargs)
                 attn_index += 1
                 identity = query
             elif layer == 'ffn':
@@ -391,6 +496,7 @@ class PETRTransformer(BaseModule):
 @POSITIONAL_ENCODING.register_module()
 class SinePositionalEncoding3D(BaseModule):
     """positional_encoding.py:15-110."""
+    kind = "sine3d"
 
     def __init__(self, num_feats, temperature=10000, normalize=False, scale=2 * math.pi, eps=1e-6,
                  offset=0., init_cfg=None):
@@ -435,9 +541,58 @@ class LearnedPositionalEncoding3D(BaseModule):
         self.row_num_embed = row_num_embed
         self.col_num_embed = col_num_embed
 
+    kind = "learned"
+
+    @torch.no_grad()
     def forward(self, mask):
-        raise NotImplementedError("LearnedPositionalEncoding3D is not on the PETR hot path "
-                                  "(no shipped config uses it); out of scope, see DESIGN.md")
+        """positional_encoding.py:137-160: mask (bs, h, w) -> (bs, 2*num_feats, h, w) = [col_embed(x) | row_embed(y)]."""
+        if not mask.is_cuda:
+            raise RuntimeError("petr_b200: CUDA tensors required (no CPU fallback)")
+        G = int(mask.shape[0])
+        h, w = mask.shape[-2:]
+        tok = ops.learned_pos_features(self.row_embed.weight.detach().float().contiguous(),
+                                       self.col_embed.weight.detach().float().contiguous(), G, h, w)
+        return ops.tokens_to_nchw(tok, G, h * w).view(G, 2 * self.num_feats, h, w)
+
+    def __repr__(self):
+        return (f'{self.__class__.__name__}(num_feats={self.num_feats}, row_num_embed={self.row_num_embed}, '
+                f'col_num_embed={self.col_num_embed})')
+
+
+@POSITIONAL_ENCODING.register_module()
+class SinePositionalEncoding(BaseModule):
+    """mmdet 2.24.1 `SinePositionalEncoding` (un-vendored): the 2-D encoding the head's default
+    `positional_encoding` dict names (petr_head.py:96-99) and the with_multiview=False branch evaluates per camera
+    (petr_head.py:403-409).  mask (bs, h, w) -> (bs, 2*num_feats, h, w) = [pos_y | pos_x], sin/cos interleaved."""
+    kind = "sine2d"
+
+    def __init__(self, num_feats, temperature=10000, normalize=False, scale=2 * math.pi, eps=1e-6,
+                 offset=0., init_cfg=None):
+        super().__init__(init_cfg)
+        if normalize:
+            assert isinstance(scale, (float, int)), 'when normalize is set, scale should be ' \
+                f'provided and in float or int type, found {type(scale)}'
+        self.num_feats = num_feats
+        self.temperature = temperature
+        self.normalize = normalize
+        self.scale = scale
+        self.eps = eps
+        self.offset = offset
+
+    @torch.no_grad()
+    def forward(self, mask):
+        if not mask.is_cuda:
+            raise RuntimeError("petr_b200: CUDA tensors required (no CPU fallback)")
+        from .engine import sine_dim_t
+        G, H, W = mask.shape
+        dim_t = sine_dim_t(self.num_feats, self.temperature).to(mask.device)
+        tok = ops.sine2d_features(mask.to(torch.uint8).contiguous(), dim_t, self.num_feats, self.normalize,
+                                  self.scale, self.eps, self.offset)
+        return ops.tokens_to_nchw(tok, G, H * W).view(G, 2 * self.num_feats, H, W)
+
+    def __repr__(self):
+        return (f'{self.__class__.__name__}(num_feats={self.num_feats}, temperature={self.temperature}, '
+                f'normalize={self.normalize}, scale={self.scale}, eps={self.eps})')
 
 
 # ------------------------------------------------------------------------------------------
@@ -492,6 +647,38 @@ class NMSFreeCoder:
 # ------------------------------------------------------------------------------------------
 # heads
 # ------------------------------------------------------------------------------------------
+class NormedLinear(nn.Linear):
+    """mmdet 2.24.1 `NormedLinear` (un-vendored; petr_head.py:231-232 when normedlinear=True): weight rows and the
+    activations are divided by (their L2 norm over dim 1)^power + eps, the activations multiplied by the temperature
+    (the published attribute name `tempearture` is kept).  Parameter container + standalone forward; inside the head
+    the engine launches the same kernels."""
+
+    def __init__(self, *args, tempearture=20, power=1.0, eps=1e-6, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.tempearture = tempearture
+        self.power = power
+        self.eps = eps
+        nn.init.normal_(self.weight, mean=0, std=0.01)
+        if self.bias is not None:
+            nn.init.constant_(self.bias, 0)
+
+    @torch.no_grad()
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("petr_b200: CUDA tensors required (no CPU fallback)")
+        w = self.weight.detach().float().contiguous()
+        w = ops.norm_scale(w, 1, w.shape[0], False, self.power, self.eps, 1.0)
+        xf = x.float().contiguous()
+        if xf.dim() == 2:       # norm(dim=1) of a 2-D input is per row
+            xs = ops.norm_scale(xf, 1, xf.shape[0], False, self.power, self.eps, self.tempearture)
+        else:                   # ... of an N-D input it runs over axis 1
+            Bn, Q = xf.shape[0], xf.shape[1]
+            inner = xf.numel() // (Bn * Q)
+            xs = ops.norm_scale(xf.view(Bn, Q, inner), Bn, Q, True, self.power, self.eps, self.tempearture)
+        out = ops.gemm_f32(xs.view(-1, xf.shape[-1]), w, self.bias.detach().float() if self.bias is not None else None)
+        return out.view(*x.shape[:-1], self.out_features)
+
+
 class _LossCfg:
     """Holds a loss config; only ``use_sigmoid`` is needed by the forward (petr_head.py:200)."""
 
@@ -502,6 +689,7 @@ class _LossCfg:
 
 class _PETRHeadBase(BaseModule):
     _version = 2
+    _optional_transformer = False
 
     def _common_init(self, num_classes, in_channels, num_query, num_reg_fcs, transformer,
                      sync_cls_avg_factor, positional_encoding, code_weights, bbox_coder, loss_cls,
@@ -512,8 +700,6 @@ class _PETRHeadBase(BaseModule):
         self._code_weights_list = list(cw)[:self.code_size]
         self.bg_cls_weight = 0
         self.sync_cls_avg_factor = sync_cls_avg_factor
-        if normedlinear:
-            raise NotImplementedError("normedlinear=True is not used by any shipped config")
         self.num_query = num_query
         self.num_classes = num_classes
         self.in_channels = in_channels
@@ -542,7 +728,10 @@ class _PETRHeadBase(BaseModule):
         self.loss_iou = _LossCfg(loss_iou)
         self.cls_out_channels = num_classes if self.loss_cls.use_sigmoid else num_classes + 1
         self.positional_encoding = build_positional_encoding(positional_encoding)
-        self.transformer = build_transformer(transformer)
+        if transformer is not None and TRANSFORMER.get(transformer.get('type')) is None and self._optional_transformer:
+            self.transformer, self.transformer_cfg = None, copy.deepcopy(transformer)    # DepthrHead, see there
+        else:
+            self.transformer = build_transformer(transformer)
         self.code_weights = nn.Parameter(torch.tensor(self._code_weights_list, requires_grad=False),
                                          requires_grad=False)
         self.bbox_coder = build_bbox_coder(bbox_coder)
@@ -562,7 +751,10 @@ class _PETRHeadBase(BaseModule):
         for _ in range(self.num_reg_fcs):
             layers += [nn.Linear(self.embed_dims, self.embed_dims), nn.LayerNorm(self.embed_dims),
                        nn.ReLU(inplace=True)]
-        layers.append(nn.Linear(self.embed_dims, self.cls_out_channels))
+        if self.normedlinear:
+            layers.append(NormedLinear(self.embed_dims, self.cls_out_channels))
+        else:
+            layers.append(nn.Linear(self.embed_dims, self.cls_out_channels))
         return nn.Sequential(*layers)
 
     def _make_reg_branch(self):
@@ -588,7 +780,8 @@ class _PETRHeadBase(BaseModule):
 
     def init_weights(self):
         """petr_head.py:276-284."""
-        self.transformer.init_weights()
+        if self.transformer is not None:
+            self.transformer.init_weights()
         nn.init.uniform_(self.reference_points.weight.data, 0, 1)
         if self.loss_cls.use_sigmoid:
             bias_init = float(-math.log((1 - 0.01) / 0.01))
@@ -802,3 +995,27 @@ class PETRv2Head(_PETRHeadBase):
         self.reg_branches = nn.ModuleList([copy.deepcopy(reg_branch) for _ in range(self.num_pred)])
         if self.with_fpe:
             self.fpe = SELayer(self.embed_dims)
+
+
+@HEADS.register_module()
+class DepthrHead(PETRHead):
+    """depthr_head.py:65-1001, the part SURVEY.md section 8f row 4 names: `position_embeding` (:338-386, identical
+    arithmetic to PETRHead's) on the same kernels, with the reference's constructor kwargs and the state_dict keys
+    of the layers it shares with PETRHead (input_proj, adapt_pos3d, position_encoder, reference_points,
+    query_embedding, cls / reg branches).  The depth-specific transformer (`DepthrTransformer`,
+    `MultiAttentionDecoderLayer`) and `DepthGTEncoder` belong to a model family outside this path: their configs
+    are kept (`transformer_cfg`, `depth_gt_encoder_cfg`) and `forward` says so instead of running."""
+    _remap_legacy = True
+    _optional_transformer = True
+
+    def __init__(self, num_classes, in_channels, depth_gt_encoder=None, **kw):
+        self.depth_gt_encoder_cfg = copy.deepcopy(depth_gt_encoder)
+        self.depth_gt_encoder = None
+        super().__init__(num_classes, in_channels, **kw)
+
+    def forward(self, mlvl_feats, img_metas, gt_bboxes_3d=None):
+        if self.transformer is None or self.depth_gt_encoder_cfg is not None:
+            raise NotImplementedError(
+                "DepthrHead.forward needs DepthrTransformer / DepthGTEncoder, a model family outside the PETR head hot "
+                "path (DESIGN.md section 8); position_embeding() is the shared piece and runs on the CUDA path")
+        return super().forward(mlvl_feats, img_metas)

@@ -131,18 +131,26 @@ def gemm_f32(A: torch.Tensor, W: torch.Tensor, bias=None, *, A2=None, residual=N
 
 
 def attention_f32(Q, K, V, key_mask, B: int, Lq: int, Lk: int, heads: int, out=None,
-                  out_split=None, want_f32: bool = True) -> torch.Tensor:
+                  out_split=None, want_f32: bool = True, attn_bias=None, lse=None, drop_p: float = 0.0,
+                  seed: int = 0) -> torch.Tensor:
     """softmax(Q K^T / sqrt(d) + mask) V; Q rows b*Lq+q, K/V rows b*Lk+k, head_dim 32.
-    out_split: optional bf16 (B*Lq, 2E) [hi | lo] copy of the result."""
+    out_split: optional bf16 (B*Lq, 2E) [hi | lo] copy of the result.  attn_bias: additive fp32 (Lq, Lk) or
+    (B*heads, Lq, Lk).  lse / drop_p / seed: training (see petr_attention_f32_bwd)."""
     _cuda(Q, "Q")
     d = 32
     E = heads * d
     if out is None and want_f32:
         out = torch.empty((B * Lq, E), dtype=torch.float32, device=Q.device)
+    per_head = 0
+    if attn_bias is not None:
+        assert attn_bias.dtype == torch.float32 and attn_bias.is_contiguous()
+        assert tuple(attn_bias.shape) in ((Lq, Lk), (B * heads, Lq, Lk)), attn_bias.shape
+        per_head = int(attn_bias.dim() == 3)
     with _Timed("attention_f32"):
         call("petr_attention_f32", ptr(Q), Q.stride(0), ptr(K), K.stride(0), ptr(V), V.stride(0),
-             ptr(key_mask), ptr(out), out.stride(0) if out is not None else 0, ptr(out_split),
-             B, Lq, Lk, heads, d, 1.0 / math.sqrt(d), stream_ptr(Q.device))
+             ptr(key_mask), ptr(attn_bias), per_head, ptr(out), out.stride(0) if out is not None else 0,
+             ptr(out_split), ptr(lse), float(drop_p), int(seed), B, Lq, Lk, heads, d, 1.0 / math.sqrt(d),
+             stream_ptr(Q.device))
     return out if out is not None else out_split
 
 
@@ -221,7 +229,7 @@ def x3_weight(W: torch.Tensor) -> torch.Tensor:
 OUT_SPLIT = 3
 
 
-def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, act=ACT_NONE,
+def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, gate=None, act=ACT_NONE,
                  alpha: float = 1.0, out=None, out_dtype=torch.float32, headsplit_Lk: int = 0,
                  split_out: bool = False, out_f32=None, x3: bool = False, headsplit_pair: bool = False,
                  residual_period: int = 0, name: str = "gemm_bf16_tc"):
@@ -247,7 +255,7 @@ def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, 
         if out is None:
             out = torch.empty((M, N), dtype=torch.bfloat16, device=A.device)
         with _Timed(name):
-            call("petr_gemm_bf16_tc", ptr(A), A.stride(0), wrap, ptr(W), W.stride(0), ptr(bias), ptr(residual),
+            call("petr_gemm_bf16_tc", ptr(A), A.stride(0), wrap, ptr(W), W.stride(0), ptr(bias), ptr(residual), None,
                  act, float(alpha), ptr(out), ptr(out_f32), out_f32.stride(0), 5, M, N, K, int(residual_period),
                  stream_ptr(A.device))
         return out
@@ -274,10 +282,11 @@ def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, 
             out = torch.empty((M, N), dtype=out_dtype, device=A.device)
         mode = OUT_F32 if out.dtype == torch.float32 else OUT_BF16
         ldc = out.stride(0)
-    if residual is not None:
-        assert residual.dtype == torch.float32 and residual.stride(0) == ldc and residual.stride(1) == 1
+    for t in (residual, gate):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.stride(0) == ldc and t.stride(1) == 1
     with _Timed(name):
-        call("petr_gemm_bf16_tc", ptr(A), A.stride(0), wrap, ptr(W), W.stride(0), ptr(bias), ptr(residual),
+        call("petr_gemm_bf16_tc", ptr(A), A.stride(0), wrap, ptr(W), W.stride(0), ptr(bias), ptr(residual), ptr(gate),
              act, float(alpha), ptr(out), ptr(C2), ldc, mode, M, N, K, int(headsplit_Lk),
              stream_ptr(A.device))
     return out
@@ -424,3 +433,64 @@ def nms_free_decode(cls_scores: torch.Tensor, bbox_preds: torch.Tensor, max_num:
          int(bool(bottom_center)), ptr(boxes), ptr(scores), ptr(labels), ptr(index), ptr(mask), ptr(count),
          stream_ptr(dev))
     return boxes, scores, labels, index, mask.bool(), count
+
+
+# ---- either side of the main path (2-D positional encodings, CPFPN tail, NormedLinear) -----------------------
+def sine2d_features(mask: torch.Tensor, dim_t: torch.Tensor, num_feats: int, normalize: bool, scale: float,
+                    eps: float, offset: float, dtype=torch.float32) -> torch.Tensor:
+    """mmdet SinePositionalEncoding.  mask uint8 (G,H,W) -> (G*H*W, 2*num_feats)."""
+    _cuda(mask, "mask")
+    G, H, W = mask.shape
+    out = torch.empty((G * H * W, 2 * num_feats), dtype=dtype, device=mask.device)
+    call("petr_sine2d_features", ptr(mask), ptr(dim_t), G, H, W, num_feats, int(bool(normalize)), float(scale),
+         float(eps), float(offset), ptr(out), _dt(dtype), stream_ptr(mask.device))
+    return out
+
+
+def learned_pos_features(row_embed: torch.Tensor, col_embed: torch.Tensor, G: int, H: int, W: int) -> torch.Tensor:
+    """positional_encoding.py:137-160 -> (G*H*W, 2F) fp32 tokens."""
+    _cuda(row_embed, "row_embed")
+    Fn = row_embed.shape[1]
+    out = torch.empty((G * H * W, 2 * Fn), dtype=torch.float32, device=row_embed.device)
+    call("petr_learned_pos_features", ptr(row_embed), row_embed.shape[0], ptr(col_embed), col_embed.shape[0],
+         G, H, W, Fn, ptr(out), stream_ptr(row_embed.device))
+    return out
+
+
+def tokens_to_nchw(x: torch.Tensor, G: int, hw: int) -> torch.Tensor:
+    """fp32 (G*hw, C) -> (G, C, hw)."""
+    _cuda(x, "x")
+    assert x.is_contiguous() and x.dtype == torch.float32
+    C = x.shape[-1]
+    out = torch.empty((G, C, hw), dtype=torch.float32, device=x.device)
+    call("petr_tokens_to_nchw_f32", ptr(x), ptr(out), G, C, hw, stream_ptr(x.device))
+    return out
+
+
+def upsample_add_tokens(dst: torch.Tensor, src: torch.Tensor, G: int, H: int, W: int, h: int, w: int):
+    """dst (G*H*W, C) += nearest-upsampled src (G*h*w, C), in place."""
+    _cuda(dst, "dst")
+    assert dst.is_contiguous() and src.is_contiguous()
+    call("petr_upsample_add_tokens", ptr(dst), ptr(src), G, H, W, h, w, dst.shape[-1], stream_ptr(dst.device))
+    return dst
+
+
+def im2col3x3_tokens(x: torch.Tensor, G: int, H: int, W: int, mode: str = "f32") -> torch.Tensor:
+    """fp32 tokens (G*H*W, C) -> (G*H*W, 9C) fp32 | bf16, or (G*H*W, 18C) bf16 [hi | lo] (mode 'split')."""
+    _cuda(x, "x")
+    assert x.is_contiguous() and x.dtype == torch.float32
+    C = x.shape[-1]
+    om = {"f32": 0, "bf16": 1, "split": 2}[mode]
+    out = torch.empty((G * H * W, 9 * C * (2 if om == 2 else 1)),
+                      dtype=torch.float32 if om == 0 else torch.bfloat16, device=x.device)
+    call("petr_im2col3x3_tokens", ptr(x), ptr(out), om, G, H, W, C, stream_ptr(x.device))
+    return out
+
+
+def norm_scale(x: torch.Tensor, B: int, Q: int, along_queries: bool, power: float, eps: float, mult: float):
+    _cuda(x, "x")
+    assert x.is_contiguous() and x.dtype == torch.float32
+    out = torch.empty_like(x)
+    call("petr_norm_scale_f32", ptr(x), ptr(out), B, Q, x.shape[-1], int(bool(along_queries)), float(power),
+         float(eps), float(mult), stream_ptr(x.device))
+    return out

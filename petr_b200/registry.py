@@ -48,6 +48,7 @@ POSITIONAL_ENCODING = Registry("position encoding")
 TRANSFORMER = Registry("Transformer")
 HEADS = Registry("head")
 BBOX_CODERS = Registry("bbox_coder")
+NECKS = Registry("neck")
 
 build_attention = ATTENTION.build
 build_feedforward_network = FEEDFORWARD_NETWORK.build
@@ -57,6 +58,7 @@ build_positional_encoding = POSITIONAL_ENCODING.build
 build_transformer = TRANSFORMER.build
 build_head = HEADS.build
 build_bbox_coder = BBOX_CODERS.build
+build_neck = NECKS.build
 
 
 def register_into_mm(verbose=False) -> bool:
@@ -66,12 +68,14 @@ def register_into_mm(verbose=False) -> bool:
         from mmdet.models.utils.builder import TRANSFORMER as MM_TRANSFORMER   # type: ignore
         from mmdet.models import HEADS as MM_HEADS                # type: ignore
         from mmdet.core.bbox.builder import BBOX_CODERS as MM_CODERS  # type: ignore
+        from mmdet.models import NECKS as MM_NECKS                # type: ignore
     except Exception:
         return False
     pairs = [(ATTENTION, mmcv_reg.ATTENTION), (TRANSFORMER_LAYER, mmcv_reg.TRANSFORMER_LAYER),
              (TRANSFORMER_LAYER_SEQUENCE, mmcv_reg.TRANSFORMER_LAYER_SEQUENCE),
              (POSITIONAL_ENCODING, mmcv_reg.POSITIONAL_ENCODING),
-             (TRANSFORMER, MM_TRANSFORMER), (HEADS, MM_HEADS), (BBOX_CODERS, MM_CODERS)]
+             (TRANSFORMER, MM_TRANSFORMER), (HEADS, MM_HEADS), (BBOX_CODERS, MM_CODERS),
+             (NECKS, MM_NECKS)]
     for ours, theirs in pairs:
         for name, cls in ours.module_dict.items():
             if name in ("MultiheadAttention", "FFN"):

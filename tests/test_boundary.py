@@ -97,7 +97,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     for name in declared:
         assert hasattr(L, name), f"{name} declared in petr_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.lib().petr_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.lib().petr_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_argument_errors_are_reported_not_thrown(lib_built):

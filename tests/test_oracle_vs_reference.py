@@ -88,3 +88,46 @@ def test_nms_free_coder_and_get_bboxes_match_reference():
         exp = r["bboxes"].clone()
         exp[:, 2] = exp[:, 2] - exp[:, 5] * 0.5
         assert torch.equal(m["bboxes"], exp) and torch.equal(m["scores"], r["scores"]) and torch.equal(m["labels"], r["labels"])
+
+
+@pytest.mark.parametrize("with_position", [True, False])
+def test_with_multiview_false_and_normedlinear_branches(with_position):
+    """petr_head.py:403-420 (per-camera 2-D encoding; LearnedPositionalEncoding3D is the reference's own 2-D-capable
+    module) and normedlinear=True (mmdet NormedLinear stand-in with the published forward)."""
+    wl = WORKLOADS["tiny"]
+    pe = dict(type='LearnedPositionalEncoding3D', num_feats=128, row_num_embed=50, col_num_embed=50)
+    head = rl.build_reference_head(CFGS["vov-p4-800x320"], in_channels=wl.in_channels, num_query=64,
+                                   with_multiview=False, with_position=with_position, normedlinear=True,
+                                   positional_encoding=pe)
+    sd = {k: v.detach() for k, v in head.state_dict().items()}
+    metas = synth.make_img_metas(wl, 2, seed=0)
+    x = synth.make_features(wl, 2, seed=0)
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = head([x], metas)
+        out = po.head_forward(sd, x, metas, dict(num_query=64, with_multiview=False, with_position=with_position,
+                                                 pos_kind="learned", normedlinear=True))
+    assert torch.equal(ref["all_cls_scores"], out["all_cls_scores"])
+    assert (ref["all_bbox_preds"] - out["all_bbox_preds"]).abs().max() <= 2e-5
+    import petr_b200 as pb
+    from petr_b200.configs import petr_head_cfg
+    mine = pb.build_head(dict(petr_head_cfg(wl.in_channels), num_query=64, with_multiview=False,
+                              with_position=with_position, normedlinear=True, positional_encoding=pe))
+    assert {k: tuple(v.shape) for k, v in mine.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+
+
+def test_cpfpn_oracle_bit_equal_and_state_dict():
+    ns = rl.load_reference()
+    torch.manual_seed(0)
+    ref = ns.CPFPN(in_channels=[128, 192], out_channels=256, num_outs=2).eval()
+    for p in ref.parameters():
+        torch.nn.init.normal_(p, std=0.05)
+    xs = [torch.randn(2, 128, 12, 20), torch.randn(2, 192, 6, 10)]
+    with torch.no_grad():
+        a = ref(xs)
+        b = po.cpfpn_forward({k: v.detach() for k, v in ref.state_dict().items()}, xs)
+    assert all(torch.equal(u, v) for u, v in zip(a, b))
+    import petr_b200 as pb
+    mine = pb.build_neck(dict(type='CPFPN', in_channels=[128, 192], out_channels=256, num_outs=2))
+    assert {k: tuple(v.shape) for k, v in mine.state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in ref.state_dict().items()}
