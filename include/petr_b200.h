@@ -325,6 +325,63 @@ int petr_im2col3x3_tokens(const float* x, void* out, int out_mode, int G, int H,
 int petr_norm_scale_f32(const float* x, float* out, int B, int Q, int E, int along_queries, float power,
                         float eps, float mult, void* stream);
 
+/* ---- Training path: backward of the fp32 forward kernels above, the loss of
+ * petr_head.py:578-728 and the matching cost of hungarian_assigner_3d.py:117-123.  Exact fp32 arithmetic. ---- */
+
+/* dW[N,K] += dY[M,N]^T (A[M,K] + A2[m % a2_rows]) -- weight gradient of petr_gemm_f32 (A layouts as there).  dW must
+ * hold zeros or a running gradient (partial sums over row chunks are added atomically). */
+int petr_gemm_f32_tn(const float* dY, int ldy, const float* A, int lda, int a_layout, int hw,
+                     const float* A2, int a2_rows, float* dW, int M, int N, int K, void* stream);
+/* out[N] += column sums of X[M,N] (bias gradient). */
+int petr_colsum_f32(const float* X, int ldx, int M, int N, float* out, void* stream);
+/* out[period_rows, E] += sum_j X[j*period_rows + r, :] (gradient of the row-periodic A2 / query_pos add). */
+int petr_rowsum_periodic_f32(const float* X, int rows, int E, int period_rows, float* out, void* stream);
+/* dX = dY where Y > 0 else 0 (ReLU epilogue). */
+int petr_relu_bwd_f32(const float* dY, const float* Y, float* dX, int64_t n, void* stream);
+/* out = gate * sigmoid(z) (PETR_ACT_SIGMOID_GATE): dZ = dOut * gate * s(1-s), dGate = dOut * s with s = sigmoid(Zpre). */
+int petr_sigmoid_gate_bwd_f32(const float* dOut, const float* Zpre, const float* gate, float* dZ, float* dGate,
+                              int64_t n, void* stream);
+/* nn.Dropout in training, forward and backward alike: Y[i] = (keep(seed, i) ? X[i] / (1 - p) : 0) + residual[i]
+ * (residual nullable: the `identity + dropout(out)` of petr_transformer.py:367 in one pass). */
+int petr_dropout_f32(const float* X, const float* residual, float* Y, int64_t n, float p, uint64_t seed,
+                     void* stream);
+/* nn.LayerNorm backward (E = 256): dX, and dgamma / dbeta (nullable) accumulated atomically.  relu / nan_to_num as in
+ * petr_layernorm_f32 (their masks are re-derived from the recomputed output). */
+int petr_layernorm_bwd_f32(const float* X, const float* gamma, const float* beta, const float* dY, float* dX,
+                           float* dgamma, float* dbeta, int rows, int E, float eps, int relu, int nan_to_num,
+                           void* stream);
+/* Backward of petr_attention_f32 (same operands, lse / drop_p / seed from the forward call): dQ, dK, dV in the
+ * layouts of Q, K, V.  Nothing of size Lq x Lk is stored; P is recomputed from lse. */
+int petr_attention_f32_bwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
+                           const float* O, int ldo, const float* dO, int lddo, const float* lse,
+                           const uint8_t* key_mask, const float* attn_bias, int bias_per_head,
+                           float* dQ, int lddq, float* dK, int lddk, float* dV, int lddv,
+                           float drop_p, uint64_t seed, int B, int Lq, int Lk, int heads, int head_dim,
+                           float scale, void* stream);
+/* d reference_points += backward of petr_pos2posemb3d. */
+int petr_pos2posemb3d_bwd(const float* ref, const float* dim_t, const float* dOut, int Q, int num_feats,
+                          float* dref, void* stream);
+/* Backward of petr_decode_boxes given its OUTPUT: dReg [L*B*Q, code_size]; dref (nullable) += gradient through
+ * inverse_sigmoid(reference_points). */
+int petr_decode_boxes_bwd(const float* out, const float* dOut, const float* ref, const float* h_pc_range,
+                          const float* time_div, float* dReg, float* dref, int L, int B, int Q, int code_size,
+                          void* stream);
+/* normalize_bbox (core/bbox/util.py:38-61): gt [n, code_in] (cx, cy, cz, w, l, h, rot[, vx, vy]) -> [n, code_in + 1]. */
+int petr_normalize_bbox(const float* gt, int n, int code_in, float* out, void* stream);
+/* HungarianAssigner3D cost matrix [Q, G] = w_cls * FocalLossCost + w_reg * BBox3DL1Cost over the first 8 box
+ * channels, nan_to_num'ed as hungarian_assigner_3d.py:131; the assignment itself is scipy's linear_sum_assignment on
+ * the host, as in the reference. */
+int petr_hungarian_cost(const float* cls, const float* pred, const int64_t* gt_labels, const float* ngt,
+                        int Q, int G, int C, int code, int gcode, float w_cls, float w_reg, float alpha,
+                        float gamma, float eps, float* cost, void* stream);
+/* Sigmoid focal loss (mmdet FocalLoss -> mmcv sigmoid_focal_loss) with per-row weights: *loss_sum += sum; dX
+ * (nullable) = grad_scale * d loss / dX.  labels == C means background. */
+int petr_focal_loss(const float* X, const int64_t* labels, const float* row_weight, int64_t rows, int C,
+                    float alpha, float gamma, float grad_scale, float* loss_sum, float* dX, void* stream);
+/* Weighted L1 over the rows whose target is finite (petr_head.py:634-640): *loss_sum += sum w |X - T|; dX (nullable). */
+int petr_l1_loss(const float* X, const float* T, const float* W, int64_t rows, int code, float grad_scale,
+                 float* loss_sum, float* dX, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

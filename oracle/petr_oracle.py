@@ -455,3 +455,88 @@ def nms_free_decode(cls_scores: Tensor, bbox_preds: Tensor, max_num: int, num_cl
             boxes[:, 2] = boxes[:, 2] - boxes[:, 5] * 0.5
         out.append(dict(bboxes=boxes, scores=scores[mask], labels=labels[mask], index=bbox_index[mask]))
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# training loss (petr_head.py:470-728) with HungarianAssigner3D
+# (core/bbox/assigners/hungarian_assigner_3d.py:60-143).  Differentiable torch restatement (autograd gives the
+# reference gradients).  mmdet's FocalLoss / FocalLossCost / L1Loss are un-vendored (mmdet 2.24.1) and restated
+# from their published formulas -- that boundary is unpinned; normalize_bbox, BBox3DL1Cost, the assignment and
+# loss_single bookkeeping follow the reference's own files.
+# ------------------------------------------------------------------------------------------
+def normalize_bbox(b: Tensor) -> Tensor:
+    """core/bbox/util.py:38-61."""
+    cx, cy, cz = b[..., 0:1], b[..., 1:2], b[..., 2:3]
+    w, l, h = b[..., 3:4].log(), b[..., 4:5].log(), b[..., 5:6].log()
+    rot = b[..., 6:7]
+    parts = [cx, cy, w, l, cz, h, rot.sin(), rot.cos()]
+    if b.size(-1) > 7:
+        parts += [b[..., 7:8], b[..., 8:9]]
+    return torch.cat(parts, dim=-1)
+
+
+def focal_loss_cost(cls_pred: Tensor, gt_labels: Tensor, weight=2.0, alpha=0.25, gamma=2.0, eps=1e-12) -> Tensor:
+    """mmdet FocalLossCost._focal_loss_cost."""
+    p = cls_pred.sigmoid()
+    neg = -(1 - p + eps).log() * (1 - alpha) * p.pow(gamma)
+    pos = -(p + eps).log() * alpha * (1 - p).pow(gamma)
+    return (pos[:, gt_labels] - neg[:, gt_labels]) * weight
+
+
+def hungarian_cost(cls_pred, bbox_pred, gt_bboxes, gt_labels, w_cls=2.0, w_reg=0.25) -> Tensor:
+    """hungarian_assigner_3d.py:117-131 (cost matrix as handed to scipy)."""
+    cost = focal_loss_cost(cls_pred, gt_labels, w_cls) + \
+        torch.cdist(bbox_pred[:, :8], normalize_bbox(gt_bboxes)[:, :8], p=1) * w_reg
+    return torch.nan_to_num(cost.detach().cpu(), nan=100.0, posinf=100.0, neginf=-100.0)
+
+
+def sigmoid_focal_loss(pred: Tensor, target_labels: Tensor, num_classes: int, gamma=2.0, alpha=0.25) -> Tensor:
+    """mmdet py_sigmoid_focal_loss (== mmcv's sigmoid_focal_loss op), element-wise; labels == num_classes: background."""
+    t = F.one_hot(target_labels, num_classes + 1)[:, :num_classes].type_as(pred)
+    p = pred.sigmoid()
+    pt = (1 - p) * t + p * (1 - t)
+    fw = (alpha * t + (1 - alpha) * (1 - t)) * pt.pow(gamma)
+    return F.binary_cross_entropy_with_logits(pred, t, reduction="none") * fw
+
+
+def head_loss(out: dict, gt_bboxes: List[Tensor], gt_labels: List[Tensor], num_classes=10, code_weights=None,
+              w_cls=2.0, w_bbox=0.25, cost_cls=2.0, cost_reg=0.25, bg_cls_weight=0.0, matches=None):
+    """PETRHead.loss petr_head.py:647-728 (loss_single :578-645, get_targets/_get_target_single :470-576).
+    gt_bboxes: (G, 9) gravity-centre boxes per image.  Returns (dict of losses, matches[l][b] = (rows, cols))."""
+    from scipy.optimize import linear_sum_assignment
+    cls_all, box_all = out["all_cls_scores"], out["all_bbox_preds"]
+    L, B, Q, C = cls_all.shape
+    cw = torch.tensor(code_weights if code_weights is not None else [1.0] * 8 + [0.2, 0.2])
+    losses, all_matches = {}, []
+    for l in range(L):
+        labels = torch.full((B * Q,), num_classes, dtype=torch.long)
+        tgt = torch.zeros((B * Q, gt_bboxes[0].shape[1]))
+        wts = torch.zeros((B * Q, box_all.shape[-1]))
+        npos, ml = 0, []
+        for b in range(B):
+            if gt_bboxes[b].shape[0] == 0:
+                ml.append((np.zeros(0, np.int64), np.zeros(0, np.int64)))
+                continue
+            if matches is None:
+                r, c = linear_sum_assignment(hungarian_cost(cls_all[l, b], box_all[l, b], gt_bboxes[b], gt_labels[b],
+                                                            cost_cls, cost_reg))
+            else:
+                r, c = matches[l][b]
+            ml.append((np.asarray(r), np.asarray(c)))
+            r, c = torch.as_tensor(r), torch.as_tensor(c)
+            labels[b * Q + r] = gt_labels[b][c]
+            tgt[b * Q + r] = gt_bboxes[b][c]
+            wts[b * Q + r] = 1.0
+            npos += len(r)
+        all_matches.append(ml)
+        cls_avg = max(npos * 1.0 + (B * Q - npos) * bg_cls_weight, 1)
+        lc = sigmoid_focal_loss(cls_all[l].reshape(-1, C), labels, num_classes).sum() / cls_avg * w_cls
+        ntgt = normalize_bbox(tgt)
+        ok = torch.isfinite(ntgt).all(dim=-1)
+        wts = wts * cw
+        lb = ((box_all[l].reshape(B * Q, -1)[ok, :10] - ntgt[ok, :10]).abs() * wts[ok, :10]).sum() / max(npos, 1) * w_bbox
+        pre = "" if l == L - 1 else f"d{l}."
+        losses[pre + "loss_cls"], losses[pre + "loss_bbox"] = torch.nan_to_num(lc), torch.nan_to_num(lb)
+    # petr_head.py:713-725: the last layer's losses come first in the dict
+    order = ["loss_cls", "loss_bbox"] + [f"d{l}.{n}" for l in range(L - 1) for n in ("loss_cls", "loss_bbox")]
+    return {k: losses[k] for k in order}, all_matches

@@ -59,6 +59,21 @@ SIGNATURES = {
     "petr_upsample_add_tokens": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "petr_im2col3x3_tokens": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "petr_norm_scale_f32": (c_int, [_P, _P, _I, _I, _I, _I, _F, _F, _F, _P]),
+    "petr_gemm_f32_tn": (c_int, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "petr_colsum_f32": (c_int, [_P, _I, _I, _I, _P, _P]),
+    "petr_rowsum_periodic_f32": (c_int, [_P, _I, _I, _I, _P, _P]),
+    "petr_relu_bwd_f32": (c_int, [_P, _P, _P, c_int64, _P]),
+    "petr_sigmoid_gate_bwd_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, _P]),
+    "petr_dropout_f32": (c_int, [_P, _P, _P, c_int64, _F, c_uint64, _P]),
+    "petr_layernorm_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _I, _P]),
+    "petr_attention_f32_bwd": (c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _I,
+                                       _P, _I, _P, _I, _P, _I, _F, c_uint64, _I, _I, _I, _I, _I, _F, _P]),
+    "petr_pos2posemb3d_bwd": (c_int, [_P, _P, _P, _I, _I, _P, _P]),
+    "petr_decode_boxes_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "petr_normalize_bbox": (c_int, [_P, _I, _I, _P, _P]),
+    "petr_hungarian_cost": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _F, _P, _P]),
+    "petr_focal_loss": (c_int, [_P, _P, _P, c_int64, _I, _F, _F, _F, _P, _P, _P]),
+    "petr_l1_loss": (c_int, [_P, _P, _P, c_int64, _I, _F, _P, _P, _P]),
 }
 
 _lib = None

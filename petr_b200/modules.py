@@ -737,6 +737,8 @@ class _PETRHeadBase(BaseModule):
         self.bbox_coder = build_bbox_coder(bbox_coder)
         self.pc_range = self.bbox_coder.pc_range
         self._engine = None
+        self._train_engine = None
+        self._loss_impl = None
         self.precision = 'bf16'
         # None: samples are simply data-parallel.  dict(world, rank, group): this process computes its
         # share of a key-split over camera views (every rank passes the full inputs, gets the full outputs)
@@ -846,16 +848,29 @@ class _PETRHeadBase(BaseModule):
         pos = pos.view(B, N, H, W, self.embed_dims).permute(0, 1, 4, 2, 3)
         return pos, cmask.to(torch.bool)
 
-    @torch.no_grad()
     def forward(self, mlvl_feats, img_metas):
-        """petr_head.py:366-468 / petrv2_head.py:429-540.  With `use_cuda_graph = True` the returned tensors are
-        the static outputs of the captured graph: valid until the next call on this head (clone to keep), and the
-        feature tensor must be the same device buffer every call (see HeadEngine._graph_forward).  Not thread-safe:
-        one head object per host thread."""
-        _require_eval(self)
+        """petr_head.py:366-468 / petrv2_head.py:429-540.
+
+        eval mode: the inference engine (no autograd).  With `use_cuda_graph = True` the returned tensors are the
+        static outputs of the captured graph: valid until the next call on this head (clone to keep), and the feature
+        tensor must be the same device buffer every call (see HeadEngine._graph_forward).  Not thread-safe: one head
+        object per host thread.
+        train mode (`.train()`): the differentiable forward of petr_b200/train.py (fp32 kernels, dropout active);
+        follow with `loss(...)` and `.backward()` as petr3d.py:126-128 does."""
         x = mlvl_feats[self.position_level]
-        return self.engine.forward(x, img_metas, precision=self.precision, keysplit=self.keysplit,
-                                   use_graph=self.use_cuda_graph)
+        if self.training:
+            return self.forward_autograd(mlvl_feats, img_metas, dropout=True)
+        with torch.no_grad():
+            return self.engine.forward(x, img_metas, precision=self.precision, keysplit=self.keysplit,
+                                       use_graph=self.use_cuda_graph)
+
+    def forward_autograd(self, mlvl_feats, img_metas, dropout: bool = True):
+        """Differentiable forward (what `.train()` + forward runs); `dropout=False` gives the eval-mode function with
+        gradients (parity tests against the reference's autograd)."""
+        from .train import TrainEngine
+        if self._train_engine is None:
+            self._train_engine = TrainEngine(self)
+        return self._train_engine.forward(mlvl_feats[self.position_level], img_metas, training=dropout)
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys,
                               unexpected_keys, error_msgs):
@@ -888,9 +903,13 @@ class _PETRHeadBase(BaseModule):
             ret_list.append([bboxes, pr['scores'], pr['labels']])
         return ret_list
 
-    def loss(self, *args, **kwargs):
-        raise NotImplementedError("training loss (petr_head.py:647-728) is outside the hot path; "
-                                  "see DESIGN.md 'what comes next'")
+    def loss(self, gt_bboxes_list, gt_labels_list, preds_dicts, gt_bboxes_ignore=None):
+        """petr_head.py:647-728: dict(loss_cls, loss_bbox, d0.loss_cls, ... d4.loss_bbox).  Focal / L1 loss kernels on
+        Hungarian-matched queries; the cost matrix is a kernel, the assignment scipy on the host as in the reference."""
+        from .train import HeadLoss
+        if self._loss_impl is None:
+            self._loss_impl = HeadLoss(self)
+        return self._loss_impl(gt_bboxes_list, gt_labels_list, preds_dicts, gt_bboxes_ignore)
 
 
 _HEAD_DEFAULTS = dict(

@@ -83,9 +83,12 @@ def test_no_cpu_fallback():
     x = synth.make_features(wl, 1)
     with pytest.raises(RuntimeError, match="CUDA"):
         head([x], synth.make_img_metas(wl, 1))
-    head.train()
-    with pytest.raises(RuntimeError, match="inference"):
+    head.train()                      # the training path is CUDA-only as well
+    with pytest.raises(RuntimeError, match="CUDA"):
         head([x], synth.make_img_metas(wl, 1))
+    att = head.transformer.decoder.layers[0].attentions[0]
+    with pytest.raises(RuntimeError, match="inference"):       # stand-alone bricks: the head drives training
+        att(x.new_zeros(4, 1, 256))
 
 
 def test_library_exports_every_declared_symbol(lib_built):
