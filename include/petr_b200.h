@@ -189,9 +189,9 @@ int petr_nms_free_decode(const float* cls_scores, const float* bbox_preds, int B
 
 /* ---- tcgen05 tier (sm_100a tensor cores, TMA-fed, TMEM accumulators) ----------------- */
 
-/* fp32 NCHW feature maps x[G][C][hw] -> bf16 token-major out[G*hw][C] (A operand of input_proj,
- * petr_head.py:390). */
-int petr_nchw_to_tokens_bf16(const float* x, void* out, int G, int C, int hw, void* stream);
+/* NCHW feature maps x[G][C][hw] (in_dtype PETR_DTYPE_F32, or PETR_DTYPE_BF16 for maps handed over in half
+ * precision) -> bf16 token-major out[G*hw][C] (A operand of input_proj, petr_head.py:390). */
+int petr_nchw_to_tokens_bf16(const void* x, int in_dtype, void* out, int G, int C, int hw, void* stream);
 
 /* bf16 x bf16 -> fp32 GEMM on tcgen05 (persistent, 128x256 tiles, TMA-fed, TMEM accumulators):
  *   C = alpha * act(A[M,K] * W[N,K]^T + bias) (+ residual)

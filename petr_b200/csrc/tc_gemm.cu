@@ -464,17 +464,25 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // One CTA moves a 32-pixel x 64-channel block: every global read is a 128-byte row segment (32 pixels of one
 // channel), every global write a 128-byte row segment (64 bf16 channels of one pixel); 8 independent loads per
 // thread are in flight before the first use (HBM-bound: 4 B in + 2 B out per element).
+__device__ __forceinline__ float ld_as_f32(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_as_f32(const __nv_bfloat16* p) {
+    return __uint_as_float(static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
+}
+
+// InT = float, or __nv_bfloat16 for feature maps handed over in half precision (an AMP backbone / the bf16 wire
+// format of bench.py's e2e_bf16_features: half the host -> device bytes, bit-identical tokens).
+template <typename InT>
 __global__ void __launch_bounds__(256)
-nchw_to_tokens_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int hw) {
+nchw_to_tokens_bf16_kernel(const InT* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int hw) {
     __shared__ float tile[64][33];
     const int g = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;          // 8 warps
-    const float* xg = x + (int64_t)g * C * hw;
+    const InT* xg = x + (int64_t)g * C * hw;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = c0 + w * 8 + i, pp = p0 + lane;
-        v[i] = (c < C && pp < hw) ? __ldg(xg + (int64_t)c * hw + pp) : 0.f;
+        v[i] = (c < C && pp < hw) ? ld_as_f32(xg + (int64_t)c * hw + pp) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) tile[w * 8 + i][lane] = v[i];
@@ -495,12 +503,18 @@ nchw_to_tokens_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restric
 
 using namespace petr;
 
-extern "C" int petr_nchw_to_tokens_bf16(const float* x, void* out, int G, int C, int hw, void* stream) {
+extern "C" int petr_nchw_to_tokens_bf16(const void* x, int in_dtype, void* out, int G, int C, int hw, void* stream) {
     PETR_REQUIRE(x && out, PETR_E_BADARG, "petr_nchw_to_tokens_bf16: null pointer");
     PETR_REQUIRE(G > 0 && C > 0 && hw > 0 && G <= 65535, PETR_E_BADARG, "petr_nchw_to_tokens_bf16: bad dimension");
     PETR_REQUIRE((C % 2) == 0, PETR_E_SHAPE, "petr_nchw_to_tokens_bf16: C must be even, got %d", C);
     dim3 grid((hw + 31) / 32, (C + 63) / 64, G);
-    nchw_to_tokens_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, C, hw);
+    if (in_dtype == PETR_DTYPE_F32)
+        nchw_to_tokens_bf16_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (__nv_bfloat16*)out, C, hw);
+    else if (in_dtype == PETR_DTYPE_BF16)
+        nchw_to_tokens_bf16_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x,
+                                                                                          (__nv_bfloat16*)out, C, hw);
+    else
+        return fail(PETR_E_BADARG, "petr_nchw_to_tokens_bf16: bad in_dtype %d", in_dtype);
     return after_launch("petr_nchw_to_tokens_bf16");
 }
 

@@ -113,7 +113,8 @@ def key_side_tc(eng, x, mi: MetaInputs, taps=None, views: slice = None):
     s = eng.spec
     if s.E != 256 or s.heads != 8:
         raise NotImplementedError("tcgen05 path is specialised for embed_dims 256, 8 heads of 32")
-    x = x.float()
+    if x.dtype != torch.bfloat16:            # bf16 feature maps are taken as they are (half the bytes on the way in)
+        x = x.float()
     B, N_all, Cin, H, W = x.shape
     if Cin % 64 != 0:
         raise NotImplementedError("tcgen05 path needs in_channels % 64 == 0")

@@ -177,12 +177,12 @@ def split_rows(X, add=None, relu=False, out=None) -> torch.Tensor:
 
 
 def nchw_to_tokens_bf16(x: torch.Tensor) -> torch.Tensor:
-    """fp32 (G,C,h,w) contiguous -> bf16 (G*h*w, C)."""
+    """fp32 | bf16 (G,C,h,w) contiguous -> bf16 (G*h*w, C)."""
     _cuda(x, "x")
     assert x.is_contiguous() and x.dim() == 4
     G, C, h, w = x.shape
     out = torch.empty((G * h * w, C), dtype=torch.bfloat16, device=x.device)
-    call("petr_nchw_to_tokens_bf16", ptr(x), ptr(out), G, C, h * w, stream_ptr(x.device))
+    call("petr_nchw_to_tokens_bf16", ptr(x), _dt(x.dtype), ptr(out), G, C, h * w, stream_ptr(x.device))
     return out
 
 

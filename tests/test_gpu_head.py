@@ -290,3 +290,19 @@ def test_cuda_graph_forward_matches_eager(name):
     for k in out2:
         assert torch.equal(out2[k], ref2[k]), k
     assert not torch.equal(out2["all_bbox_preds"], ref["all_bbox_preds"])
+
+
+def test_bf16_feature_maps_give_identical_results():
+    """Feature maps handed over as bf16 (half the bytes on the way in): the bf16 path rounds fp32 features to bf16 in its
+    first kernel, so bf16 input == fp32 input holding the same (bf16-representable) values, bit for bit."""
+    case, wl, feats, metas, head = _build("small_padded")
+    head.precision = "bf16"
+    xb = feats.to(DEV).to(torch.bfloat16)
+    a = head([xb], metas)
+    b = head([xb.float()], metas)
+    for k in ("all_cls_scores", "all_bbox_preds"):
+        assert torch.equal(a[k], b[k]), k
+    head.precision = "fp32"
+    c = head([xb], metas)
+    d = head([xb.float()], metas)
+    assert torch.equal(c["all_bbox_preds"], d["all_bbox_preds"])

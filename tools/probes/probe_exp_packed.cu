@@ -36,12 +36,14 @@ __global__ void __launch_bounds__(512, 1) probe(int iters, long long* cyc, uint3
             if (MODE == 3) acc ^= ex2_bf16x2(pk[pr]);
             if (MODE == 4) acc ^= __float_as_uint(ex2(v[2 * pr])) ^ __float_as_uint(ex2(v[2 * pr + 1]));
         }
+        // every input must change every iteration: ptxas hoists loop-invariant ex2 out of the loop (a first version
+        // of this probe changed one input in eight and "measured" 96 exp2/clk/SM)
         if (MODE == 3) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) pk[i] = (acc & 0x007F007Fu) | 0xBF80BF80u;
+            for (int i = 0; i < 32; ++i) pk[i] = ((acc + i * 0x00010001u) & 0x007F007Fu) | 0xBF80BF80u;
         } else {
 #pragma unroll
-            for (int i = 0; i < 64; i += 8) v[i] = __uint_as_float((acc & 0x007FFFFFu) | 0xBF800000u) - i;
+            for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(((acc + i) & 0x007FFFFFu) | 0xBF800000u);
         }
     }
     __syncthreads();
