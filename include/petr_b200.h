@@ -219,6 +219,20 @@ int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const void* W, int l
                       void* C, void* C2, int ldc, int out_mode, int M, int N, int K,
                       int kv_Lk, void* stream);
 
+/* 3xTF32 GEMM on tcgen05 (kind::tf32; same persistent kernel, fp32 operands): the fp32-PARITY path of the 1x1-conv
+ * MLPs (petr_head.py:332 position_encoder, :249-254 adapt_pos3d) and the fp32 K / V projections on the tensor cores.
+ *   C = act(A[M,K] * W[N,K]^T + bias) (+ residual),  K % 32 == 0, fp32 row-major operands with 16-byte aligned rows.
+ * With A = [hi | lo] (2K0 columns; petr_split_rows_tf32 or out_mode 6 of a previous call: hi = value rounded to
+ * tf32, lo = value - hi), W = [W_hi | W_hi | W_lo] (3K0 columns) and a_k_wrap = 2K0 the product is
+ * hi*hi + lo*hi + hi*lo: ~2^-21 relative, i.e. fp32-class (the 1e-5 position-embedding tolerance has 20x margin).
+ * out_mode 0: fp32 C[m*ldc + n];  6: fp32 split rows C[m*2N + n] = hi, C[m*2N + N + n] = lo (ldc = residual stride). */
+int petr_gemm_tf32x3_tc(const float* A, int lda, int a_k_wrap, const float* W, int ldw, const float* bias,
+                        const float* residual, int act, float* C, int ldc, int out_mode, int M, int N, int K,
+                        void* stream);
+/* fp32 rows X[rows, E] (row stride ldx) (+ add[r % add_rows], nullable) -> fp32 [hi | lo] rows out[rows, 2E]. */
+int petr_split_rows_tf32(const float* X, int ldx, const float* add, int add_rows, float* out, int rows, int E,
+                         void* stream);
+
 /* ---- a1, fused (K1): the whole position embedding of petr_head.py:286-334 in one kernel per
  * 128-token tile: frustum -> img2lidar -> normalise -> inverse_sigmoid -> bf16 A operand written
  * straight into 128B-swizzled shared memory -> tcgen05 GEMM (192 -> hidden, TMEM) -> bias + ReLU ->

@@ -41,6 +41,8 @@ SIGNATURES = {
     "petr_nms_free_decode": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P]),
     "petr_decode_boxes": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "petr_gemm_bf16_tc": (c_int, [_P, _I, _I, _P, _I, _P, _P, _P, _I, _F, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "petr_gemm_tf32x3_tc": (c_int, [_P, _I, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "petr_split_rows_tf32": (c_int, [_P, _I, _P, _I, _P, _I, _I, _P]),
     "petr_position_mlp_fused": (c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P,
                                         _I, _I, _P, _P, _I, _P, _P, _P]),
     "petr_stage_small": (c_int, [_P, _P, _I, _P]),

@@ -58,6 +58,12 @@ constexpr int STAGE_OUT_BYTES = 8 * 2048;      // one 32-row x 64-byte staging s
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias tiles*/ + STAGE_OUT_BYTES;
 constexpr int GEMM_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 struct EpiParams {
     const float* bias; const float* residual; const float* gate; int act; float alpha;
     void* C; void* C2; int ldc; int out_mode;
@@ -110,10 +116,15 @@ struct TileMap {
 
 // One instantiation per output mode: with all five store paths in one kernel the epilogue alone was ~70 KB of
 // SASS, far beyond the 32 KB instruction cache (measured: 3 300 clk per 32-column chunk in single-tile GEMMs).
-template <int OM>
+// TF32 = true: fp32 operands through kind::tf32 (32 elements = 128 bytes per K block: the same byte geometry, the same
+// four MMAs per stage).  With A = [hi | lo] and W = [W_hi | W_hi | W_lo] (hi = value rounded to tf32, lo = remainder)
+// this is the 3xTF32 product hi*hi + lo*hi + hi*lo, accurate to ~2^-21: the fp32-parity path on the tensor cores.
+// out_mode 6 (TF32 only): fp32 [hi | lo] split rows of the result (the A operand of the next 3xTF32 GEMM).
+template <int OM, bool TF32 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     EpiParams p) {
+    constexpr int BKE = TF32 ? 32 : BK;                    // K elements per 128-byte block
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -127,7 +138,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // warp index through a shuffle: ptxas then treats it as warp-uniform and keeps the producer / MMA issuer
     // loops (descriptors, barrier addresses) in uniform registers instead of R2UR / ELECT loops per instruction
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-    const int num_k = p.K / BK;
+    const int num_k = p.K / BKE;
     const int num_tiles = p.tiles_m * p.tiles_n;
     const TileMap tmap_{p.tiles_m, p.tiles_n, p.band};
 
@@ -166,17 +177,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (kb < 4) GEMM_TR(0, ttile, kb);
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                     uint8_t* a = smem + s * STAGE_BYTES;
-                    int ka = kb * BK;
+                    int ka = kb * BKE;
                     if (ka >= p.a_k_wrap) ka -= p.a_k_wrap;      // A = [hi | lo | hi] without a third copy
                     tma_load_2d(a, &tmA, &full_bar[s], ka, m0);
-                    tma_load_2d(a + TILE_A_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+                    tma_load_2d(a + TILE_A_BYTES, &tmB, &full_bar[s], kb * BKE, n0);
                 }
                 __syncwarp();
             }
         }
     } else if (warp == 1) {
         const bool leader = elect_one();
-        constexpr uint32_t idesc = make_idesc(BM, BN, 1, 0, 0);
+        constexpr uint32_t idesc = make_idesc(BM, BN, TF32 ? 2 : 1, 0, 0);
         const uint64_t desc0 = make_smem_desc(smem_u32(smem), 16, 1024, LAYOUT_SW128);
         uint32_t it = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
@@ -194,8 +205,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint64_t ad = desc0 + (uint64_t)((s * STAGE_BYTES) >> 4);
                     const uint64_t bd = ad + (uint64_t)(TILE_A_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_f16_ss(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) {          // 32 bytes of K per MMA: 16 bf16 or 8 tf32
+                        if constexpr (TF32) umma_tf32_ss(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                        else umma_f16_ss(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    }
                     umma_commit(&empty_bar[s]);                  // smem stage free when these retire
                 }
                 __syncwarp();
@@ -347,6 +360,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             }
                             if (OM == 0) {
                                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (int64_t)mr * p.ldc + col) = x;
+                            } else if (OM == 6) {                             // fp32 [hi | lo] tf32 split rows
+                                float4 hi4, lo4;
+                                hi4.x = tf32_rna(x.x); hi4.y = tf32_rna(x.y); hi4.z = tf32_rna(x.z); hi4.w = tf32_rna(x.w);
+                                lo4.x = x.x - hi4.x; lo4.y = x.y - hi4.y; lo4.z = x.z - hi4.z; lo4.w = x.w - hi4.w;
+                                float* cp = reinterpret_cast<float*>(p.C) + (int64_t)mr * (2 * p.N) + col;
+                                *reinterpret_cast<float4*>(cp) = hi4;
+                                *reinterpret_cast<float4*>(cp + p.N) = lo4;
                             } else if (OM == 1) {
                                 *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)mr * p.ldc + col) =
                                     make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
@@ -388,6 +408,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (nb + j < p.N) v[j] += rp[j];
                     }
+                }
+                if (OM == 6) {
+                    float* cp = reinterpret_cast<float*>(p.C) + (int64_t)m * (2 * p.N) + nb;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < p.N) { const float h = tf32_rna(v[j]); cp[j] = h; cp[p.N + j] = v[j] - h; }
                 }
                 if (OM == 0 || (OM == 3 && p.C2)) {
                     float* cp = reinterpret_cast<float*>(OM == 0 ? p.C : p.C2) + (int64_t)m * p.ldc + nb;
@@ -498,10 +524,77 @@ nchw_to_tokens_bf16_kernel(const InT* __restrict__ x, __nv_bfloat16* __restrict_
     }
 }
 
+// fp32 rows (R, E) (+ add[r % add_rows]) -> fp32 [hi | lo] rows (R, 2E): hi = tf32(x), lo = x - hi (3xTF32 operand)
+__global__ void split_rows_tf32_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ add, int add_rows,
+                                       float* __restrict__ out, int64_t total, int E) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t r = i / E;
+    const int c = (int)(i - r * E);
+    float v = X[r * ldx + c];
+    if (add) v += add[(r % add_rows) * (int64_t)E + c];
+    const float h = tf32_rna(v);
+    out[r * 2 * E + c] = h;
+    out[r * 2 * E + E + c] = v - h;
+}
+
 }  // namespace
 }  // namespace petr
 
 using namespace petr;
+
+extern "C" int petr_split_rows_tf32(const float* X, int ldx, const float* add, int add_rows, float* out, int rows, int E,
+                                    void* stream) {
+    PETR_REQUIRE(X && out && rows > 0 && E > 0 && ldx >= E, PETR_E_BADARG, "petr_split_rows_tf32: bad argument");
+    PETR_REQUIRE(!add || add_rows > 0, PETR_E_BADARG, "petr_split_rows_tf32: add needs add_rows > 0");
+    const int64_t total = (int64_t)rows * E;
+    split_rows_tf32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, add, add_rows, out, total, E);
+    return after_launch("petr_split_rows_tf32");
+}
+
+extern "C" int petr_gemm_tf32x3_tc(const float* A, int lda, int a_k_wrap, const float* W, int ldw, const float* bias,
+                                   const float* residual, int act, float* C, int ldc, int out_mode, int M, int N, int K,
+                                   void* stream) {
+    PETR_REQUIRE(A && W && C, PETR_E_BADARG, "petr_gemm_tf32x3_tc: null pointer");
+    PETR_REQUIRE(M > 0 && N > 0 && K > 0, PETR_E_BADARG, "petr_gemm_tf32x3_tc: bad dimension");
+    PETR_REQUIRE(K % 32 == 0, PETR_E_SHAPE, "petr_gemm_tf32x3_tc: K must be a multiple of 32, got %d", K);
+    if (a_k_wrap <= 0) a_k_wrap = K;
+    PETR_REQUIRE(a_k_wrap % 32 == 0 && a_k_wrap <= K && K - a_k_wrap <= a_k_wrap, PETR_E_SHAPE,
+                 "petr_gemm_tf32x3_tc: a_k_wrap must be a multiple of 32 with K/2 <= a_k_wrap <= K");
+    PETR_REQUIRE(lda >= a_k_wrap && ldw >= K && (lda % 4) == 0 && (ldw % 4) == 0 && aligned16(A) && aligned16(W),
+                 PETR_E_ALIGN, "petr_gemm_tf32x3_tc: A/W rows must be 16-byte aligned");
+    PETR_REQUIRE(act == PETR_ACT_NONE || act == PETR_ACT_RELU, PETR_E_BADARG, "petr_gemm_tf32x3_tc: bad act");
+    PETR_REQUIRE(out_mode == 0 || out_mode == 6, PETR_E_BADARG, "petr_gemm_tf32x3_tc: out_mode must be 0 (fp32) or 6 (split)");
+    PETR_REQUIRE((N % 4) == 0 && aligned16(C) && (!residual || aligned16(residual)), PETR_E_ALIGN,
+                 "petr_gemm_tf32x3_tc: N %% 4 == 0 and 16-byte aligned C / residual required");
+    if (out_mode == 0 || residual) PETR_REQUIRE(ldc >= N && (ldc % 4) == 0, PETR_E_BADARG, "petr_gemm_tf32x3_tc: bad ldc");
+    EpiParams p{};
+    p.bias = bias; p.residual = residual; p.gate = nullptr; p.act = act; p.alpha = 1.f;
+    p.C = C; p.C2 = nullptr; p.ldc = ldc; p.out_mode = out_mode;
+    p.M = M; p.N = N; p.K = K; p.a_k_wrap = a_k_wrap; p.kv_E = 256;
+    p.trace = nullptr;
+    p.coalesce = 1;
+    CUtensorMap tmA, tmB;
+    uint64_t dA[2] = {(uint64_t)a_k_wrap, (uint64_t)M}, sA[1] = {(uint64_t)lda * 4};
+    uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)ldw * 4};
+    uint32_t boxA[2] = {32, BM}, boxB[2] = {32, BN};
+    int rc = tmap::encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, A, dA, sA, boxA, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = tmap::encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, W, dB, sB, boxB, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, EpiParams);
+    const gemm_fn fn = out_mode == 0 ? (gemm_fn)gemm_bf16_tc_kernel<0, true> : (gemm_fn)gemm_bf16_tc_kernel<6, true>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    if (e != cudaSuccess) return fail((int)e, "petr_gemm_tf32x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    p.tiles_m = (M + BM - 1) / BM;
+    p.tiles_n = (N + BN - 1) / BN;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int tiles = p.tiles_m * p.tiles_n;
+    fn<<<tiles < sms ? tiles : sms, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, p);
+    return after_launch("petr_gemm_tf32x3_tc");
+}
 
 extern "C" int petr_nchw_to_tokens_bf16(const void* x, int in_dtype, void* out, int G, int C, int hw, void* stream) {
     PETR_REQUIRE(x && out, PETR_E_BADARG, "petr_nchw_to_tokens_bf16: null pointer");

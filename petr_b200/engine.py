@@ -196,6 +196,16 @@ def sine_dim_t(num_feats: int, temperature: float) -> torch.Tensor:
     return temperature ** (2 * (dim_t // 2) / num_feats)
 
 
+# 3xTF32 tcgen05 GEMMs (ops.gemm_tf32x3) for the Lk-side GEMMs of the fp32 path (position / adapt MLPs; K / V
+# projections).  OFF: measured on the B200 the tensor core's fp32 accumulator truncates, so the error of a 3xTF32 product
+# grows with the number of accumulation steps -- 2.0e-6 of the output scale at K = 192, 8.9e-6 at K = 1024
+# (tests/test_gpu_kernels.py::test_gemm_tf32x3_fp32_class) against 1e-7 for FFMA -- which breaks the 1e-5 position-
+# embedding tolerance on 7 of the 10 golden cases and is amplified by peaked attention logits.  The parity path
+# therefore stays on exact FFMA; the switches remain for A/B measurements.
+TF32X3_FP32_PATH = False
+TF32X3_KV_PROJ = False
+
+
 class HeadSpec:
     """Static description of a head, read from the module's ctor arguments."""
 
@@ -326,12 +336,26 @@ class HeadEngine:
         return ops.frustum_features(mi.i2l, masks, H, W, s.D, mi.pad_h, mi.pad_w, s.lid, s.depth_start,
                                     s.bin_size, s.position_range, dtype, want_mask, want_coords)
 
+    def _t3(self, P, key: str) -> torch.Tensor:
+        """[W_hi | W_hi | W_lo] tf32 pack of a weight of the packed dict (cached with it)."""
+        c = P.setdefault("t3", {})
+        if key not in c:
+            c[key] = ops.x3_weight_tf32(P[key])
+        return c[key]
+
+    def mlp_f32(self, P, x: torch.Tensor, w1: str, b1: str, w2: str, b2: str, residual=None) -> torch.Tensor:
+        """Linear - ReLU - Linear (+ residual) of the fp32 parity path.  On tcgen05 as two 3xTF32 GEMMs (fp32-class:
+        ~2^-21) when the shapes allow, the hidden activation handed over as [hi | lo] split rows; else exact FFMA."""
+        if TF32X3_FP32_PATH and x.shape[1] % 32 == 0 and P[w1].shape[0] % 32 == 0 and P[w2].shape[0] % 4 == 0:
+            h = ops.gemm_tf32x3(ops.split_rows_tf32(x), self._t3(P, w1), P[b1], act=ACT_RELU, split_out=True)
+            return ops.gemm_tf32x3(h, self._t3(P, w2), P[b2], residual=residual)
+        h = ops.gemm_f32(x, P[w1], P[b1], act=ACT_RELU)
+        return ops.gemm_f32(h, P[w2], P[b2], residual=residual)
+
     def position_embedding_tokens(self, P, mi: MetaInputs, B, N, H, W, masks):
         """fp32 path of position_embeding (petr_head.py:286-334): (T,256) tokens + coords_mask."""
         feat, cmask, _ = self.frustum(mi, B, N, H, W, masks)
-        h = ops.gemm_f32(feat, P["pe_w1"], P["pe_b1"], act=ACT_RELU)
-        pos = ops.gemm_f32(h, P["pe_w2"], P["pe_b2"])
-        return pos, cmask
+        return self.mlp_f32(P, feat, "pe_w1", "pe_b1", "pe_w2", "pe_b2"), cmask
 
     def pos_features(self, P, masks: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
         """The positional-encoding features of petr_head.py:399-420 as tokens: SinePositionalEncoding3D over all
@@ -361,12 +385,24 @@ class HeadEngine:
         y = ops.gemm_f32(o, lw["sa_out_w"], lw["sa_out_b"], residual=X)
         return ops.layernorm(y, *lw["ln"][0], out=y)
 
-    def _cross_attn_f32(self, X, qpos, mem, pos, kmask, lw, B, Lk):
+    def _cross_attn_f32(self, X, qpos, mem, pos, kmask, lw, B, Lk, ks):
         s = self.spec
         E = s.E
         q = ops.gemm_f32(X, lw["ca_in_w"][:E], lw["ca_in_b"][:E], A2=qpos)
-        k = ops.gemm_f32(mem, lw["ca_in_w"][E:2 * E], lw["ca_in_b"][E:2 * E], A2=pos)
-        v = ops.gemm_f32(mem, lw["ca_in_w"][2 * E:], lw["ca_in_b"][2 * E:])
+        if TF32X3_KV_PROJ and E % 32 == 0:
+            # K / V projections of the Lk side (petr_transformer.py:341-344) as 3xTF32 tcgen05 GEMMs
+            t3 = lw.setdefault("t3", {})
+            if not t3:
+                t3["k"] = ops.x3_weight_tf32(lw["ca_in_w"][E:2 * E])
+                t3["v"] = ops.x3_weight_tf32(lw["ca_in_w"][2 * E:])
+            if "kin_t3" not in ks:              # layer-invariant operands: split once per forward
+                ks["kin_t3"] = ops.split_rows_tf32(mem, add=pos)
+                ks["vin_t3"] = ops.split_rows_tf32(mem)
+            k = ops.gemm_tf32x3(ks["kin_t3"], t3["k"], lw["ca_in_b"][E:2 * E])
+            v = ops.gemm_tf32x3(ks["vin_t3"], t3["v"], lw["ca_in_b"][2 * E:])
+        else:
+            k = ops.gemm_f32(mem, lw["ca_in_w"][E:2 * E], lw["ca_in_b"][E:2 * E], A2=pos)
+            v = ops.gemm_f32(mem, lw["ca_in_w"][2 * E:], lw["ca_in_b"][2 * E:])
         o = ops.attention_f32(q, k, v, kmask, B, s.Lq, Lk, s.heads)
         y = ops.gemm_f32(o, lw["ca_out_w"], lw["ca_out_b"], residual=X)
         return ops.layernorm(y, *lw["ln"][1], out=y)
@@ -469,7 +505,6 @@ class HeadEngine:
             if taps is not None:
                 taps.update(masks=masks, memory=mem, pos_embed=pos)
             return dict(precision="fp32", B=B, Lk=Lk, mem=mem, pos=pos, kmask=masks.view(B, Lk))
-        h2 = ops.gemm_f32(sf, P["ad_w1"], P["ad_b1"], act=ACT_RELU)
         if s.with_position:
             pos, _ = self.position_embedding_tokens(P, mi, B, N, H, W, masks)
             if taps is not None:
@@ -477,9 +512,9 @@ class HeadEngine:
             if s.with_fpe:
                 se = ops.gemm_f32(mem, P["fpe_wr"], P["fpe_br"], act=ACT_RELU)
                 pos = ops.gemm_f32(se, P["fpe_we"], P["fpe_be"], act=ACT_SIGMOID_GATE, gate=pos)
-            pos = ops.gemm_f32(h2, P["ad_w2"], P["ad_b2"], residual=pos)
+            pos = self.mlp_f32(P, sf, "ad_w1", "ad_b1", "ad_w2", "ad_b2", residual=pos)
         else:
-            pos = ops.gemm_f32(h2, P["ad_w2"], P["ad_b2"])
+            pos = self.mlp_f32(P, sf, "ad_w1", "ad_b1", "ad_w2", "ad_b2")
         if taps is not None:
             taps.update(masks=masks, memory=mem, pos_embed=pos)
         return dict(precision="fp32", B=B, Lk=Lk, mem=mem, pos=pos, kmask=masks.view(B, Lk))
@@ -491,7 +526,7 @@ class HeadEngine:
         B = ks["B"]
         X = self._self_attn(X, qpos, lw, B)
         assert ks["precision"] == "fp32", "the bf16 path runs engine_tc.decoder_layer_tc"
-        X = self._cross_attn_f32(X, qpos, ks["mem"], ks["pos"], ks["kmask"], lw, B, ks["Lk"])
+        X = self._cross_attn_f32(X, qpos, ks["mem"], ks["pos"], ks["kmask"], lw, B, ks["Lk"], ks)
         return self._ffn(X, lw)
 
     @torch.no_grad()

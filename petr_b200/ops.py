@@ -494,3 +494,47 @@ def norm_scale(x: torch.Tensor, B: int, Q: int, along_queries: bool, power: floa
     call("petr_norm_scale_f32", ptr(x), ptr(out), B, Q, x.shape[-1], int(bool(along_queries)), float(power),
          float(eps), float(mult), stream_ptr(x.device))
     return out
+
+
+# ---- 3xTF32 tier: fp32-class GEMMs on tcgen05 (the fp32 parity path) --------------------------------------------
+def split_rows_tf32(X: torch.Tensor, add=None) -> torch.Tensor:
+    """fp32 (R,E) (+ add[r % add_rows]) -> fp32 (R,2E) [hi | lo], hi = tf32-rounded value, lo = remainder."""
+    _cuda(X, "X")
+    assert X.dim() == 2 and X.stride(1) == 1 and X.dtype == torch.float32
+    R, E = X.shape
+    out = torch.empty((R, 2 * E), dtype=torch.float32, device=X.device)
+    if add is not None:
+        assert add.is_contiguous() and add.shape[1] == E
+    call("petr_split_rows_tf32", ptr(X), X.stride(0), ptr(add), add.shape[0] if add is not None else 0, ptr(out), R, E,
+         stream_ptr(X.device))
+    return out
+
+
+def x3_weight_tf32(W: torch.Tensor) -> torch.Tensor:
+    """fp32 (N,K) -> fp32 (N,3K) = [W_hi | W_hi | W_lo], the W operand of a 3xTF32 GEMM."""
+    s = split_rows_tf32(W.contiguous())
+    K = W.shape[1]
+    return torch.cat([s[:, :K], s[:, :K], s[:, K:]], 1).contiguous()
+
+
+def gemm_tf32x3(A_split: torch.Tensor, W3: torch.Tensor, bias=None, *, residual=None, act=ACT_NONE,
+                split_out: bool = False, out=None, name: str = "gemm_tf32x3") -> torch.Tensor:
+    """C = act(A @ W.T + bias) (+ residual) with A = [hi | lo] (M, 2K0) and W3 = x3_weight_tf32 (N, 3K0).
+    split_out: fp32 (M, 2N) [hi | lo] rows instead of (M, N)."""
+    _cuda(A_split, "A")
+    assert A_split.dtype == torch.float32 and W3.dtype == torch.float32
+    assert A_split.dim() == 2 and A_split.stride(1) == 1 and W3.is_contiguous()
+    M = A_split.shape[0]
+    N, K = W3.shape
+    assert 3 * A_split.shape[1] == 2 * K, (A_split.shape, W3.shape)
+    if out is None:
+        out = torch.empty((M, 2 * N if split_out else N), dtype=torch.float32, device=A_split.device)
+    ldc = residual.stride(0) if residual is not None else (N if split_out else out.stride(0))
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(1) == 1
+        if not split_out:
+            assert residual.stride(0) == out.stride(0)
+    with _Timed(name):
+        call("petr_gemm_tf32x3_tc", ptr(A_split), A_split.stride(0), A_split.shape[1], ptr(W3), W3.stride(0), ptr(bias),
+             ptr(residual), act, ptr(out), ldc, 6 if split_out else 0, M, N, K, stream_ptr(A_split.device))
+    return out

@@ -537,3 +537,38 @@ def test_nms_free_decode_kernel(B, Q, C, code, max_num, thr):
         eager = coder.decode_padded(xs, bs, bottom_center=True)
         for a, b_ in zip(out, eager):
             assert torch.equal(a, b_)
+
+
+@pytest.mark.parametrize("M,K,N", [(333, 192, 1024), (4096 + 77, 1024, 256), (128, 384, 100), (1000, 256, 260)])
+def test_gemm_tf32x3_fp32_class(M, K, N):
+    """3xTF32 tcgen05 GEMM (fp32 operands split hi/lo, kind::tf32): fp32-class accuracy against float64 (measured
+    2e-6 of the output scale: the operands carry 22 mantissa bits, the remainder is the tensor core's fp32 accumulation),
+    bias / ReLU / residual epilogues, and the [hi | lo] split output feeding the next GEMM (the fp32-parity position MLP)."""
+    g = torch.Generator().manual_seed(M + K + N)
+    A = torch.randn(M, K, generator=g) * 3
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    R = torch.randn(M, N, generator=g)
+    ref = A.double() @ W.double().T + b.double()
+    As = ops.split_rows_tf32(A.to(DEV))
+    assert torch.equal(As[:, :K] + As[:, K:], A.to(DEV))                       # hi + lo == value exactly
+    W3 = ops.x3_weight_tf32(W.to(DEV))
+    out = ops.gemm_tf32x3(As, W3, b.to(DEV))
+    scale = ref.abs().max().item()
+    err = (out.cpu().double() - ref).abs().max().item()
+    print(f"3xTF32 {M}x{K}x{N}: err / scale = {err / scale:.2e}")
+    tol = 2e-6 + 1e-8 * K          # the tensor core's truncating fp32 accumulator: error grows with the K steps
+    assert err <= tol * scale, (err, scale)
+    out = ops.gemm_tf32x3(As, W3, b.to(DEV), residual=R.to(DEV), act=ops.ACT_RELU)
+    assert (out.cpu().double() - (torch.relu(ref) + R.double())).abs().max().item() <= tol * (scale + R.abs().max().item())
+    sp = ops.gemm_tf32x3(As, W3, b.to(DEV), act=ops.ACT_RELU, split_out=True)
+    assert sp.shape == (M, 2 * N)
+    assert (sp[:, :N] + sp[:, N:]).cpu().double().sub(torch.relu(ref)).abs().max().item() <= tol * scale
+    assert (sp[:, N:].abs() <= sp[:, :N].abs() * 2.0 ** -10 + 1e-30).all()      # lo is the tf32 remainder of hi
+    # add[r % rows] prologue of the split
+    add = torch.randn(37, K, generator=g)
+    if M % 37 == 0 or True:
+        m2 = (M // 37) * 37
+        s2 = ops.split_rows_tf32(A[:m2].to(DEV).contiguous(), add=add.to(DEV))
+        want = A[:m2] + add.repeat(m2 // 37, 1)
+        assert torch.equal(s2[:, :K] + s2[:, K:], want.to(DEV))
