@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     EpiParams p) {
     constexpr int BKE = TF32 ? 32 : BK;                    // K elements per 128-byte block
+    // (measured and rejected: a 3-stage operand ring for out_mode 2 with the freed 48 KB as a ring of three store slabs
+    // per epilogue warp -- 0.498 vs 0.492 ms: the K / V projection is not paced by slab reuse)
+    constexpr int NST = STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -170,8 +173,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tmap_(tile, mt, nt);
             const int m0 = mt * BM, n0 = nt * BN;
             for (int kb = 0; kb < num_k; ++kb, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
+                const int s = it % NST;
+                const uint32_t ph = (it / NST) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (leader) {
                     if (kb < 4) GEMM_TR(0, ttile, kb);
@@ -197,8 +200,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (leader) GEMM_TR(1, tcount, 0);
             const uint32_t d = tmem_base + buf * BN;
             for (int kb = 0; kb < num_k; ++kb, ++it) {
-                const int s = it % STAGES;
-                mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                const int s = it % NST;
+                mbar_wait(&full_bar[s], (it / NST) & 1);
                 tcgen05_fence_after();
                 if (leader) {
                     if (kb < 4) GEMM_TR(1, tcount, 1 + kb);
