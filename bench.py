@@ -217,12 +217,15 @@ def main():
     ap.add_argument("--keysplit", action="store_true",
                     help="BASELINE config 4: every rank works on the SAME samples, keys split over camera "
                          "views, one NCCL all-gather of (O, m, l) partials per decoder layer (strong scaling)")
+    ap.add_argument("--p2p", action="store_true",
+                    help="with --keysplit: exchange the partials by pushing them over NVLink peer memory (own kernels, "
+                         "graph-capturable) instead of NCCL all-gathers")
     args = ap.parse_args()
 
     if args.graph is None:
         # default: whole-head CUDA-graph replay, also in data-parallel multi-process runs (the graph captures no
         # collective there; NCCL is only used for the timing barrier).  Key-split captures NCCL all-gathers: eager.
-        args.graph = not args.keysplit
+        args.graph = (not args.keysplit) or args.p2p
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -253,10 +256,10 @@ def main():
     head.precision = args.precision
     head.use_cuda_graph = bool(args.graph)
     if args.keysplit and world > 1:
-        if args.graph:
-            raise SystemExit("--graph with --keysplit is not supported (NCCL collectives captured in a CUDA "
-                             "graph hung process-group teardown; see profiles/README.md)")
-        head.keysplit = dict(world=world, rank=rank, group=None)
+        if args.graph and not args.p2p:
+            raise SystemExit("--graph with --keysplit needs --p2p (NCCL collectives captured in a CUDA graph hung "
+                             "process-group teardown; see profiles/README.md)")
+        head.keysplit = dict(world=world, rank=rank, group=None, p2p=bool(args.p2p))
     # data parallel: each rank gets its own shard of the global batch (different seeds per rank);
     # key-split: every rank gets the same samples
     data_seed = 0 if args.keysplit else rank
@@ -466,7 +469,7 @@ def main():
                     data="synthetic",
                     config=dict(workload=wl.name, batch_per_gpu=B, global_batch=B * nrep,
                                 num_keys=wl.num_keys, num_query=900, decoder_layers=6,
-                                parallelism=(f"keysplit{world}" if args.keysplit else f"dp{world}"),
+                                parallelism=((f"keysplit{world}" + ("-p2p" if args.p2p else "-nccl")) if args.keysplit else f"dp{world}"),
                                 precision=args.precision, cuda_graph=bool(args.graph),
                                 l2="inputs larger than L2 (%.0f MB features per step)" % (x_host.numel() * 4 / 1e6)),
                     e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=int(h2d),

@@ -396,6 +396,27 @@ int petr_focal_loss(const float* X, const int64_t* labels, const float* row_weig
 int petr_l1_loss(const float* X, const float* T, const float* W, int64_t rows, int code, float grad_scale,
                  float* loss_sum, float* dX, void* stream);
 
+/* ---- Key-split exchange over NVLink peer memory (second row) without a library collective ----
+ * Every rank owns one peer-mapped ("symmetric") allocation: gathered[2 parities][world][slot_floats] fp32 followed by
+ * flags[2][world] uint32.  d_peer_bufs / d_peer_flags are DEVICE arrays of `world` pointers to the ranks' gathered /
+ * flags bases.  Per decoder layer (seq = layer index, parity = seq & 1, seqs_per_epoch = layers per forward):
+ *   petr_cross_attention_bf16(write_partial) into the rank's OWN slot gathered[parity][rank]  ->
+ *   petr_p2p_push_partial: stores that slot into gathered[parity][rank] of every peer and, from the last CTA, releases
+ *     flags[parity][rank] = epoch * seqs_per_epoch + seq + 1 at system scope (also on the own rank)  ->
+ *   petr_attention_merge_p2p: acquires flags[parity][0..world) >= that value, then merges the nparts = world * nsplit
+ *     parts like petr_attention_merge (a slot may hold the nsplit split-KV parts of its rank: slot_floats = nsplit *
+ *     petr_attention_partial_floats).
+ * petr_p2p_epoch_inc bumps the device-side forward counter once per forward, so a captured CUDA graph replays with
+ * fresh flag values.  d_counters: uint32[world] zero-initialised scratch; d_err: set non-zero if a flag did not arrive
+ * within ~2 s (the kernel then proceeds instead of hanging).  All ranks must issue the same sequence of layers. */
+int petr_p2p_push_partial(const float* src, void* const* d_peer_bufs, void* const* d_peer_flags, int world, int rank,
+                          int64_t slot_floats, int parity, const uint32_t* d_epoch, int seq, int seqs_per_epoch,
+                          uint32_t* d_counters, void* stream);
+int petr_p2p_epoch_inc(uint32_t* d_epoch, void* stream);
+int petr_attention_merge_p2p(const float* gathered, int nparts, int world, const uint32_t* d_flags, const uint32_t* d_epoch,
+                             int seq, int seqs_per_epoch, uint32_t* d_err, float* O, int ldo, void* O_split,
+                             int B, int Lq, int heads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,9 @@ SIGNATURES = {
     "petr_upsample_add_tokens": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "petr_im2col3x3_tokens": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "petr_norm_scale_f32": (c_int, [_P, _P, _I, _I, _I, _I, _F, _F, _F, _P]),
+    "petr_p2p_push_partial": (c_int, [_P, _P, _P, _I, _I, c_int64, _I, _P, _I, _I, _P, _P]),
+    "petr_p2p_epoch_inc": (c_int, [_P, _P]),
+    "petr_attention_merge_p2p": (c_int, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _I, _P]),
     "petr_gemm_f32_tn": (c_int, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P]),
     "petr_colsum_f32": (c_int, [_P, _I, _I, _I, _P, _P]),
     "petr_rowsum_periodic_f32": (c_int, [_P, _I, _I, _I, _P, _P]),

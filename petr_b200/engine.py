@@ -262,7 +262,7 @@ class HeadEngine:
     # -------------------------------------------------------------------------------------
     def invalidate(self):
         self._packed.clear()
-        self._graphs.clear()
+        self._graphs.clear()          # (the peer-memory exchange state in self._p2p survives: it holds no parameters)
 
     def packed(self, device) -> dict:
         device = torch.device(device)
@@ -486,6 +486,9 @@ class HeadEngine:
             if keysplit:
                 if keysplit.get("emulate"):
                     return tc.key_side_keysplit_emulated(self, x, mi, keysplit["world"], taps)
+                if keysplit.get("p2p"):
+                    return tc.key_side_keysplit_p2p(self, x, mi, keysplit["world"], keysplit["rank"],
+                                                    keysplit.get("group"), taps)
                 return tc.key_side_keysplit(self, x, mi, keysplit["world"], keysplit["rank"],
                                             keysplit.get("group"), taps)
             return tc.key_side_tc(self, x, mi, taps)
@@ -541,7 +544,7 @@ class HeadEngine:
         B, N, Cin, H, W = x.shape
         host = host_prep(img_metas, N, H, W, s.with_time)
         if use_graph and taps is None:
-            if keysplit and not keysplit.get("emulate"):
+            if keysplit and not keysplit.get("emulate") and not keysplit.get("p2p"):
                 # measured once (profiles/README.md): works, but tearing down a process group with live
                 # graphs that captured NCCL collectives hung the ranks at exit -- not supported
                 raise NotImplementedError("use_cuda_graph together with a multi-process key-split is not supported")
@@ -556,7 +559,8 @@ class HeadEngine:
         meta buffers that are refreshed per call; the returned tensors are the graph's static outputs:
         they are OVERWRITTEN by the next call on this head, clone them to keep them."""
         dev = x.device
-        ksk = None if not keysplit else (keysplit["world"], keysplit.get("rank"), bool(keysplit.get("emulate")))
+        ksk = None if not keysplit else (keysplit["world"], keysplit.get("rank"), bool(keysplit.get("emulate")),
+                                         bool(keysplit.get("p2p")))
         key = (x.data_ptr(), tuple(x.shape), x.dtype, precision, host["has_mask"], host["uniform_masks"],
                host["pad_h"], host["pad_w"], ksk)
         ent = self._graphs.get(key)

@@ -345,6 +345,15 @@ def state_from_rows(eng, X, qpos, st_like: dict) -> dict:
 # [O | m, l] partials are exchanged with ONE all-gather and merged by petr_attention_merge (the same
 # kernel and layout as on-GPU split-KV).  Queries / self-attention / FFN / branches are replicated.
 # ----------------------------------------------------------------------------------------------
+def keysplit_nsplit(s, B: int, x, world: int) -> int:
+    """Split-KV factor INSIDE every rank of a key-split (each rank still has to fill its 148 SMs: at B = 1 one
+    (head, query-tile pair) grid is 32 CTAs).  The same on all ranks -- derived from the smallest shard -- because the
+    gathered buffer is laid out [rank][split]."""
+    N, H, W = x.shape[1], x.shape[3], x.shape[4]
+    views = min(shard_views(N, world, r).stop - shard_views(N, world, r).start for r in range(world))
+    return choose_nsplit(B, s.heads, s.Lq, views * H * W)
+
+
 def key_side_keysplit(eng, x, mi: MetaInputs, world: int, rank: int, group=None, taps=None) -> dict:
     """Key-side state of one rank of a `world`-way key-split (torch.distributed NCCL group)."""
     import torch.distributed as dist
@@ -352,17 +361,97 @@ def key_side_keysplit(eng, x, mi: MetaInputs, world: int, rank: int, group=None,
     N = x.shape[1]
     ks = key_side_tc(eng, x, mi, taps, views=shard_views(N, world, rank))
     B = ks["B"]
-    floats = ops.attention_partial_floats(B, s.Lq, s.heads)
+    ns = keysplit_nsplit(s, B, x, world)
+    ws = ops.cross_attention_workspace(B, s.Lq, ks["Lk"], s.heads, ns, x.device)
+    floats = ns * ops.attention_partial_floats(B, s.Lq, s.heads)
     local = torch.empty((floats,), dtype=torch.float32, device=x.device)
     gathered = torch.empty((world * floats,), dtype=torch.float32, device=x.device)
 
     def xattn(qs, l, o_s):
-        ops.cross_attention_bf16(qs, ks["Kh"][l], ks["Vh"][l], ks["kmask"], B, s.Lq, ks["Lk"], s.heads, 1,
-                                 partial=local, write_partial=True, workspace=ks["att_ws"])
+        ops.cross_attention_bf16(qs, ks["Kh"][l], ks["Vh"][l], ks["kmask"], B, s.Lq, ks["Lk"], s.heads, ns,
+                                 partial=local, write_partial=True, workspace=ws)
         dist.all_gather_into_tensor(gathered, local, group=group)
-        ops.attention_merge(gathered, world, B, s.Lq, s.heads, out_split=o_s, want_f32=False)
+        ops.attention_merge(gathered, world * ns, B, s.Lq, s.heads, out_split=o_s, want_f32=False)
 
     ks["xattn"] = xattn
+    return ks
+
+
+class P2PExchange:
+    """Peer-memory exchange state of one rank of a key-split (include/petr_b200.h, "Key-split exchange over NVLink peer
+    memory"): one symmetric allocation (torch.distributed._symmetric_memory: cuMem + IPC handles, no NVSHMEM) holding
+    gathered[2][world][floats] fp32 and flags[2][world] uint32, plus the device arrays of peer pointers the push
+    kernel dereferences.  Creation is collective (rendezvous + barrier) and must happen outside graph capture."""
+
+    def __init__(self, world: int, rank: int, floats: int, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank, self.floats = world, rank, floats
+        n = 2 * world * floats
+        self.buf = symm_mem.empty(n + 64, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        pg = group if group is not None else dist.group.WORLD
+        try:                                      # needed by some torch versions, deprecated no-op in others
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                symm_mem.enable_symm_mem_for_group(pg.group_name)
+        except Exception:
+            pass
+        hdl = symm_mem.rendezvous(self.buf, pg)
+        self.hdl = hdl
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self.peer_bufs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.peer_flags = torch.tensor([p + n * 4 for p in ptrs], dtype=torch.int64, device=device)
+        self.flags = self.buf[n:n + 2 * world].view(torch.int32)
+        self.epoch = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.counters = torch.zeros((world,), dtype=torch.int32, device=device)
+        self.err = torch.zeros((1,), dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                       # nobody pushes before every rank has zeroed its flags
+
+    def slot(self, parity: int, r: int) -> torch.Tensor:
+        o = (parity * self.world + r) * self.floats
+        return self.buf[o:o + self.floats]
+
+    def gathered(self, parity: int) -> torch.Tensor:
+        o = parity * self.world * self.floats
+        return self.buf[o:o + self.world * self.floats]
+
+
+def key_side_keysplit_p2p(eng, x, mi: MetaInputs, world: int, rank: int, group=None, taps=None) -> dict:
+    """Key-side state of one rank of a `world`-way key-split whose per-layer exchange is a push over NVLink peer memory
+    (petr_p2p_push_partial / petr_attention_merge_p2p) instead of an NCCL all-gather: graph-capturable."""
+    from ._lib import call, ptr, stream_ptr
+    s = eng.spec
+    N = x.shape[1]
+    ks = key_side_tc(eng, x, mi, taps, views=shard_views(N, world, rank))
+    B = ks["B"]
+    ns = keysplit_nsplit(s, B, x, world)
+    ws = ops.cross_attention_workspace(B, s.Lq, ks["Lk"], s.heads, ns, x.device)
+    floats = ns * ops.attention_partial_floats(B, s.Lq, s.heads)
+    key = ("p2p", world, rank, floats, str(x.device))
+    st = eng._p2p.get(key) if hasattr(eng, "_p2p") else None
+    if st is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("petr_b200: the peer-memory exchange must be set up by an un-captured forward first")
+        if not hasattr(eng, "_p2p"):
+            eng._p2p = {}
+        st = eng._p2p[key] = P2PExchange(world, rank, floats, x.device, group)
+    dev = x.device
+    call("petr_p2p_epoch_inc", ptr(st.epoch), stream_ptr(dev))
+
+    def xattn(qs, l, o_s):
+        par = l & 1
+        ops.cross_attention_bf16(qs, ks["Kh"][l], ks["Vh"][l], ks["kmask"], B, s.Lq, ks["Lk"], s.heads, ns,
+                                 partial=st.slot(par, rank), write_partial=True, workspace=ws)
+        call("petr_p2p_push_partial", ptr(st.slot(par, rank)), ptr(st.peer_bufs), ptr(st.peer_flags), world, rank, floats,
+             par, ptr(st.epoch), l, s.L, ptr(st.counters), stream_ptr(dev))
+        call("petr_attention_merge_p2p", ptr(st.gathered(par)), world * ns, world, ptr(st.flags[par * world:]), ptr(st.epoch), l, s.L,
+             ptr(st.err), None, 0, ptr(o_s), B, s.Lq, s.heads, stream_ptr(dev))
+
+    ks["xattn"] = xattn
+    ks["p2p"] = st
     return ks
 
 
@@ -375,15 +464,17 @@ def key_side_keysplit_emulated(eng, x, mi: MetaInputs, world: int, taps=None) ->
     shards = [key_side_tc(eng, x, mi, taps if r == 0 else None, views=shard_views(N, world, r))
               for r in range(world)]
     B = shards[0]["B"]
-    floats = ops.attention_partial_floats(B, s.Lq, s.heads)
+    ns = keysplit_nsplit(s, B, x, world)
+    wss = [ops.cross_attention_workspace(B, s.Lq, k["Lk"], s.heads, ns, x.device) for k in shards]
+    floats = ns * ops.attention_partial_floats(B, s.Lq, s.heads)
     gathered = torch.empty((world * floats,), dtype=torch.float32, device=x.device)
 
     def xattn(qs, l, o_s):
         for r, k in enumerate(shards):
-            ops.cross_attention_bf16(qs, k["Kh"][l], k["Vh"][l], k["kmask"], B, s.Lq, k["Lk"], s.heads, 1,
+            ops.cross_attention_bf16(qs, k["Kh"][l], k["Vh"][l], k["kmask"], B, s.Lq, k["Lk"], s.heads, ns,
                                      partial=gathered[r * floats:(r + 1) * floats], write_partial=True,
-                                     workspace=k["att_ws"])
-        ops.attention_merge(gathered, world, B, s.Lq, s.heads, out_split=o_s, want_f32=False)
+                                     workspace=wss[r])
+        ops.attention_merge(gathered, world * ns, B, s.Lq, s.heads, out_split=o_s, want_f32=False)
 
     out = dict(shards[0])
     out["xattn"] = xattn

@@ -572,3 +572,45 @@ def test_gemm_tf32x3_fp32_class(M, K, N):
         s2 = ops.split_rows_tf32(A[:m2].to(DEV).contiguous(), add=add.to(DEV))
         want = A[:m2] + add.repeat(m2 // 37, 1)
         assert torch.equal(s2[:, :K] + s2[:, K:], want.to(DEV))
+
+
+def test_p2p_exchange_kernels_two_ranks_on_one_device():
+    """Push / flag / acquire-merge kernels of the peer-memory key-split exchange with both 'ranks' on one GPU (their
+    symmetric buffers are two local allocations; the peer-pointer tables are what a rendezvous would hand out): three
+    forwards x two layers, results bit-equal to petr_attention_merge of the same partials, flags monotonic, no timeout."""
+    from petr_b200._lib import call, ptr, stream_ptr
+    B, Lq, Lk, world, L = 2, 100, 512, 2, 2
+    qs, Kh, Vh, s = _flash_inputs(B, Lq, Lk, 2.0, 11)
+    floats = ops.attention_partial_floats(B, Lq, 8)
+    n = 2 * world * floats
+    bufs = [torch.zeros(n + 64, dtype=torch.float32, device=DEV) for _ in range(world)]
+    peer_bufs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+    peer_flags = torch.tensor([b.data_ptr() + n * 4 for b in bufs], dtype=torch.int64, device=DEV)
+    epochs = [torch.zeros(1, dtype=torch.int32, device=DEV) for _ in range(world)]
+    counters = [torch.zeros(world, dtype=torch.int32, device=DEV) for _ in range(world)]
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    halves = ((0, 256), (256, Lk))
+    sp = stream_ptr(DEV)
+    for fwd in range(3):
+        for r in range(world):
+            call("petr_p2p_epoch_inc", ptr(epochs[r]), sp)
+        for l in range(L):
+            par = l & 1
+            parts = []
+            for r, (lo, hi) in enumerate(halves):
+                slot = bufs[r][(par * world + r) * floats:(par * world + r + 1) * floats]
+                ops.cross_attention_bf16(qs * (1.0 + 0.1 * l), Kh[:, :, lo:hi].contiguous(), Vh[:, :, lo:hi].contiguous(), None,
+                                         B, Lq, hi - lo, 8, 1, partial=slot, write_partial=True)
+                parts.append(slot.clone())
+                call("petr_p2p_push_partial", ptr(slot), ptr(peer_bufs), ptr(peer_flags), world, r, floats, par,
+                     ptr(epochs[r]), l, L, ptr(counters[r]), sp)
+            want = ops.attention_merge(torch.cat(parts), world, B, Lq, 8)
+            for r in range(world):
+                got = torch.empty_like(want)
+                flags = bufs[r][n:n + 2 * world].view(torch.int32)
+                call("petr_attention_merge_p2p", ptr(bufs[r][par * world * floats:]), world, world, ptr(flags[par * world:]),
+                     ptr(epochs[r]), l, L, ptr(err), ptr(got), got.stride(0), None, B, Lq, 8, sp)
+                assert torch.equal(got, want), (fwd, l, r)
+                assert flags[par * world:(par + 1) * world].tolist() == [(fwd + 1) * L + l + 1] * world
+    assert int(err.item()) == 0
+    assert all(int(c.sum()) == 0 for c in counters)            # the per-peer CTA counters wrapped back to zero
