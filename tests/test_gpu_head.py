@@ -306,3 +306,20 @@ def test_bf16_feature_maps_give_identical_results():
     c = head([xb], metas)
     d = head([xb.float()], metas)
     assert torch.equal(c["all_bbox_preds"], d["all_bbox_preds"])
+
+
+def test_layer0_self_attention_dedup_is_bit_identical():
+    """The first decoder layer's self-attention block (input = zeros for every sample) evaluated once and broadcast must
+    give the bits of evaluating it per sample."""
+    from petr_b200 import engine_tc
+    case, wl, feats, metas, head = _build("small_padded")
+    head.precision = "bf16"
+    x = feats.to(DEV)
+    a = {k: v.clone() for k, v in head([x], metas).items() if v is not None}
+    engine_tc.DEDUP_LAYER0 = False
+    try:
+        b = head([x], metas)
+    finally:
+        engine_tc.DEDUP_LAYER0 = True
+    for k in a:
+        assert torch.equal(torch.nan_to_num(a[k]), torch.nan_to_num(b[k])), k
