@@ -209,7 +209,7 @@ int petr_nchw_to_tokens_bf16(const void* x, int in_dtype, void* out, int G, int 
  *   5: two results from one accumulator: C = bf16 [m*N + n] of alpha*act(acc + bias) WITHOUT the residual and
  *      C2 = fp32 [m*ldc + n] WITH residual[(m %% kv_Lk)*ldc + n] added -- input_proj emitting the V-projection
  *      operand and "memory + batch-invariant sine embedding" (the K-side residual of the position MLP) at once.
- * residual (nullable, fp32, ldc) is added after alpha.  act PETR_ACT_SIGMOID_GATE (out_mode 0/1/3) multiplies
+ * residual (nullable, fp32, ldc) is added after alpha.  act PETR_ACT_SIGMOID_GATE (out_mode 0) multiplies
  * sigmoid(acc + bias) by gate[m*ldc + n] (fp32) before the residual: the PETRv2 SELayer
  * (petrv2_head.py:48-60) as a GEMM epilogue.  Used for the K/V projection of all
  * decoder layers in one launch (petr_transformer.py:341-344,:357-360), the position_encoder /

@@ -37,6 +37,7 @@ bool gemm_staged();
 bool gemm_coalesce();
 bool gemm_skinny();
 bool gemm_band();
+int gemm_debug();
 void* debug_trace();
 }  // namespace tuning
 

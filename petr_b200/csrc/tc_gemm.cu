@@ -71,6 +71,7 @@ struct EpiParams {
     int tiles_m, tiles_n, band;
     long long* trace;  // diagnostic clock64 stamps of CTA 0 (petr_debug_set_trace), normally null
     int coalesce;      // transposing (coalesced) epilogue allowed: 16-byte aligned bases, ldc % 4 == 0, N % 4 == 0
+    int dbg;           // diagnostic (petr_set_tuning gemm_debug): 1 = out_mode 2 skips its global stores
     int staged;        // out_mode 2: stage each warp's 32 x 32 bf16 chunk in smem and write it with one bulk copy
 };
 
@@ -123,11 +124,14 @@ struct TileMap {
 template <int OM, bool TF32 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    EpiParams p) {
+                    const __grid_constant__ CUtensorMap tmC, EpiParams p) {
     constexpr int BKE = TF32 ? 32 : BK;                    // K elements per 128-byte block
-    // (measured and rejected: a 3-stage operand ring for out_mode 2 with the freed 48 KB as a ring of three store slabs
-    // per epilogue warp -- 0.498 vs 0.492 ms: the K / V projection is not paced by slab reuse)
-    constexpr int NST = STAGES;
+    // out_mode 2 (head-split K / V projection, K = 256: four k-blocks per tile, epilogue-bound -- measured: TMEM loads
+    // only 0.20 ms, + bias / pack 0.31, + staging through shared memory 0.45, + the global stores 0.48): a 3-stage
+    // operand ring, the fourth stage's 48 KB + the old 16 KB = four 2 KB store slabs per epilogue warp (one per
+    // 32-column chunk of the tile), written in the 64-byte TMA swizzle (conflict-free: the linear layout had a 4-way
+    // bank conflict on every st.shared.v4) and sent with cp.async.bulk.tensor; ONE proxy fence per two chunks.
+    constexpr int NST = (OM == 2) ? 3 : STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -270,8 +274,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + chalf * 128;
             uint32_t rbuf[2][32];
             tmem_ld_x32(t_addr, rbuf[0]);
+            if (OM == 2 && p.staged) {           // this warp's four store slabs: the previous tile's TMA stores have read them
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
 #pragma unroll 1
             for (int cpair = 0; cpair < 2; ++cpair) {
+            int slab_row[2] = {-1, -1};
+            uint32_t slab_src[2] = {0u, 0u};
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci) {
                 const int cc = cpair * 2 + ci;
@@ -296,6 +306,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (cc + 1 < 4) tmem_ld_x32(t_addr + (cc + 1) * 32, rbuf[ci ^ 1]);
                 const int nb = n0 + c * 32;
                 if (nb >= p.N) continue;
+                if (OM == 2 && p.dbg == 2) continue;                 // diagnostic: TMEM loads only
                 const bool full = (nb + 32 <= p.N);
                 float v[32];
 #pragma unroll
@@ -311,9 +322,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
-                if (p.act == PETR_ACT_SIGMOID_GATE) {                  // PETRv2 SELayer: gate[m,n] * sigmoid(acc + bias)
+                if constexpr (OM == 7) {                               // PETRv2 SELayer: gate[m,n] * sigmoid(acc + bias)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+                    for (int j = 0; j < 32; ++j) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
                 }
                 if (p.alpha != 1.f) {
 #pragma unroll
@@ -353,7 +364,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C2) + (int64_t)mr * p.ldc + col) = x;
                                 continue;
                             }
-                            if (p.gate) {
+                            if constexpr (OM == 7) {
                                 const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gate + (int64_t)mr * p.ldc + col));
                                 x.x *= g4.x; x.y *= g4.y; x.z *= g4.z; x.w *= g4.w;
                             }
@@ -361,7 +372,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 const float4 q4 = res4[hh * 4 + i];
                                 x.x += q4.x; x.y += q4.y; x.z += q4.z; x.w += q4.w;
                             }
-                            if (OM == 0) {
+                            if (OM == 0 || OM == 7) {
                                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (int64_t)mr * p.ldc + col) = x;
                             } else if (OM == 6) {                             // fp32 [hi | lo] tf32 split rows
                                 float4 hi4, lo4;
@@ -394,7 +405,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     continue;
                 }
                 if (m >= p.M) continue;
-                if (p.gate) {
+                if constexpr (OM == 7) {
                     const float* gp = p.gate + (int64_t)m * p.ldc + nb;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) if (nb + j < p.N) v[j] *= gp[j];
@@ -418,8 +429,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int j = 0; j < 32; ++j)
                         if (nb + j < p.N) { const float h = tf32_rna(v[j]); cp[j] = h; cp[p.N + j] = v[j] - h; }
                 }
-                if (OM == 0 || (OM == 3 && p.C2)) {
-                    float* cp = reinterpret_cast<float*>(OM == 0 ? p.C : p.C2) + (int64_t)m * p.ldc + nb;
+                if (OM == 0 || OM == 7 || (OM == 3 && p.C2)) {
+                    float* cp = reinterpret_cast<float*>(OM == 3 ? p.C2 : p.C) + (int64_t)m * p.ldc + nb;
                     if (full && ((p.ldc & 3) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -447,18 +458,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     // of 32 sectors per instruction (ncu: 73.7 M sector writes for 1.18 GB); staged,
                     // one elected lane issues a single 2 KB cp.async.bulk.
                     if (slab) {
-                        uint8_t* sw = stage_out + (warp - 2) * 2048;
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // slab free again
-                        __syncwarp();
-                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(sw + lane * 64), v);
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 2048;"
-                                         :: "l"(cp), "r"(smem_u32(sw)) : "memory");
-                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        }
-                    } else {
+                        // slab cc of this warp (three in the freed operand stage, the fourth in stage_out)
+                        uint8_t* sw = (cc < 3) ? smem + 3 * STAGE_BYTES + ((warp - 2) * 3 + cc) * 2048
+                                               : stage_out + (warp - 2) * 2048;
+                        const uint32_t sa = smem_u32(sw) + lane * 64;
+                        const int x = (sa >> 7) & 3;                              // SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8]
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            st_shared_v4(sa + ((j ^ x) << 4), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                         pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                        slab_row[ci] = (int)((((int64_t)l * p.kv_B + kv_b) * (p.kv_E >> 5) + h) * p.kv_Lk + key0w);
+                        slab_src[ci] = smem_u32(sw);
+                    } else if (p.dbg != 1) {
+                        slab_row[ci] = -1;
                         store_bf16x32(cp, v);
                     }
                 } else if (OM == 4) {
@@ -471,6 +483,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     // bf16 split [hi | lo] for the bf16x3 GEMMs: row m, hi at [nb], lo at [N + nb]
                     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)m * (2 * p.N) + nb;
                     store_split_bf16x32(cp, cp + p.N, v);
+                }
+            }
+            if (OM == 2 && (slab_row[0] >= 0 || slab_row[1] >= 0)) {      // warp-uniform: one proxy fence per two chunks
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && p.dbg != 1) {
+#pragma unroll
+                    for (int ci = 0; ci < 2; ++ci)
+                        if (slab_row[ci] >= 0) tma_store_2d(&tmC, slab_src[ci], 0, slab_row[ci]);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
             }
@@ -585,7 +607,7 @@ extern "C" int petr_gemm_tf32x3_tc(const float* A, int lda, int a_k_wrap, const 
     if (rc) return rc;
     rc = tmap::encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, W, dB, sB, boxB, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, EpiParams);
+    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, EpiParams);
     const gemm_fn fn = out_mode == 0 ? (gemm_fn)gemm_bf16_tc_kernel<0, true> : (gemm_fn)gemm_bf16_tc_kernel<6, true>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     if (e != cudaSuccess) return fail((int)e, "petr_gemm_tf32x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -595,7 +617,7 @@ extern "C" int petr_gemm_tf32x3_tc(const float* A, int lda, int a_k_wrap, const 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = p.tiles_m * p.tiles_n;
-    fn<<<tiles < sms ? tiles : sms, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, p);
+    fn<<<tiles < sms ? tiles : sms, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, tmA, p);
     return after_launch("petr_gemm_tf32x3_tc");
 }
 
@@ -630,14 +652,15 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
                  "petr_gemm_bf16_tc: bad act");
     PETR_REQUIRE((act == PETR_ACT_SIGMOID_GATE) == (gate != nullptr), PETR_E_BADARG,
                  "petr_gemm_bf16_tc: PETR_ACT_SIGMOID_GATE needs a gate array (and only it)");
-    if (gate) PETR_REQUIRE((out_mode == 0 || out_mode == 1 || out_mode == 3) && aligned16(gate) && ldc >= N, PETR_E_SHAPE,
-                           "petr_gemm_bf16_tc: a gate needs out_mode 0, 1 or 3 and a 16-byte aligned [M, ldc] array");
+    if (gate) PETR_REQUIRE(out_mode == 0 && aligned16(gate) && ldc >= N, PETR_E_SHAPE,
+                           "petr_gemm_bf16_tc: a gate needs out_mode 0 and a 16-byte aligned [M, ldc] array");
     PETR_REQUIRE(out_mode >= 0 && out_mode <= 5, PETR_E_BADARG, "petr_gemm_bf16_tc: bad out_mode");
     EpiParams p{};
     p.bias = bias; p.residual = residual; p.gate = gate; p.act = act; p.alpha = alpha;
     p.C = C; p.C2 = C2; p.ldc = ldc; p.out_mode = out_mode;
     p.M = M; p.N = N; p.K = K; p.a_k_wrap = a_k_wrap;
     p.staged = (out_mode == 2 && tuning::gemm_staged()) ? 1 : 0;
+    p.dbg = tuning::gemm_debug();
     p.trace = (long long*)tuning::debug_trace();
     p.coalesce = (tuning::gemm_coalesce() && aligned16(C) && (!C2 || aligned16(C2)) && (!residual || aligned16(residual)) &&
                   (N % 4) == 0 && ((out_mode == 4) || (ldc % 4) == 0)) ? 1 : 0;
@@ -662,14 +685,25 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     if (rc) return rc;
     rc = tmap::encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, dB, sB, boxB, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, EpiParams);
-    static const gemm_fn fns[6] = {gemm_bf16_tc_kernel<0>, gemm_bf16_tc_kernel<1>, gemm_bf16_tc_kernel<2>,
-                                   gemm_bf16_tc_kernel<3>, gemm_bf16_tc_kernel<4>, gemm_bf16_tc_kernel<5>};
+    CUtensorMap tmC = tmA;                         // only out_mode 2 (staged) uses it
+    if (p.staged) {
+        uint64_t dC[2] = {32, (uint64_t)(N / 256) * p.kv_B * 8 * (uint64_t)p.kv_Lk}, sC[1] = {64};
+        uint32_t boxC[2] = {32, 32};
+        rc = tmap::encode(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, dC, sC, boxC, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+    }
+    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, EpiParams);
+    // index 6: out_mode 0 with the sigmoid-gate epilogue -- its own instantiation (kernel-internal mode 7), so that the 32
+    // exponentials + divisions per chunk do not bloat the other kernels (they doubled every instantiation's SASS, 34 ->
+    // 63 KB against a 32 KB instruction cache, when the gate was a run-time branch)
+    static const gemm_fn fns[7] = {gemm_bf16_tc_kernel<0>, gemm_bf16_tc_kernel<1>, gemm_bf16_tc_kernel<2>,
+                                   gemm_bf16_tc_kernel<3>, gemm_bf16_tc_kernel<4>, gemm_bf16_tc_kernel<5>,
+                                   gemm_bf16_tc_kernel<7>};
     if (out_mode == 5)
         PETR_REQUIRE(p.coalesce && C2 && residual && kv_Lk > 0 && N % 32 == 0 && ldc >= N && aligned16(C), PETR_E_SHAPE,
                      "petr_gemm_bf16_tc: out_mode 5 needs C2, a residual with period kv_Lk, N %% 32 == 0 and 16-byte aligned bases");
     if (out_mode == 5) p.kv_Lk = kv_Lk;
-    const gemm_fn fn = fns[out_mode];
+    const gemm_fn fn = fns[gate ? 6 : out_mode];
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     if (e != cudaSuccess) return fail((int)e, "petr_gemm_bf16_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     p.tiles_m = (M + BM - 1) / BM;
@@ -680,6 +714,6 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     int tiles = p.tiles_m * p.tiles_n;
     int grid = tiles < sms ? tiles : sms;
     p.band = (out_mode == 2 && p.tiles_n > 1 && tuning::gemm_band()) ? grid : 0;      // measured slower (0.509 vs 0.466 ms): off by default
-    fn<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, p);
+    fn<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, tmC, p);
     return after_launch("petr_gemm_bf16_tc");
 }
