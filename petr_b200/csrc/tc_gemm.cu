@@ -71,6 +71,7 @@ struct EpiParams {
     int tiles_m, tiles_n, band;
     long long* trace;  // diagnostic clock64 stamps of CTA 0 (petr_debug_set_trace), normally null
     int coalesce;      // transposing (coalesced) epilogue allowed: 16-byte aligned bases, ldc % 4 == 0, N % 4 == 0
+    int tma_out;       // out_modes 3 / 4: split halves leave through swizzled slabs + TMA tensor stores (tmC / tmD)
     int dbg;           // diagnostic (petr_set_tuning gemm_debug): 1 = out_mode 2 skips its global stores
     int staged;        // out_mode 2: stage each warp's 32 x 32 bf16 chunk in smem and write it with one bulk copy
 };
@@ -124,14 +125,17 @@ struct TileMap {
 template <int OM, bool TF32 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, EpiParams p) {
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, EpiParams p) {
     constexpr int BKE = TF32 ? 32 : BK;                    // K elements per 128-byte block
     // out_mode 2 (head-split K / V projection, K = 256: four k-blocks per tile, epilogue-bound -- measured: TMEM loads
     // only 0.20 ms, + bias / pack 0.31, + staging through shared memory 0.45, + the global stores 0.48): a 3-stage
     // operand ring, the fourth stage's 48 KB + the old 16 KB = four 2 KB store slabs per epilogue warp (one per
     // 32-column chunk of the tile), written in the 64-byte TMA swizzle (conflict-free: the linear layout had a 4-way
     // bank conflict on every st.shared.v4) and sent with cp.async.bulk.tensor; ONE proxy fence per two chunks.
-    constexpr int NST = (OM == 2) ? 3 : STAGES;
+    // out_modes 3 (bf16 [hi | lo] split rows: FFN1, 68 us against a 34 us MMA floor at B = 16) and 4 (head-split hi / lo
+    // pair: the self-attention projections) take the same route when the host set p.tma_out: two slabs (hi, lo) per
+    // chunk, four per pair of chunks, reused every pair after a wait on the previous pair's stores.
+    constexpr int NST = (OM == 2 || OM == 3 || OM == 4) ? 3 : STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -270,7 +274,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if ((OM == 2 || OM == 4) && m < p.M) { kv_b = m / p.kv_Lk; kv_key = m - kv_b * p.kv_Lk; }
             // staged output (out_mode 2): decided per warp here, where all 32 lanes are still together
             const int key0w = __shfl_sync(0xffffffffu, kv_key, 0);
-            const bool slab = p.staged && (m0 + quarter * 32 + 32 <= p.M) && (key0w + 32 <= p.kv_Lk);
+            const bool slab = (OM == 4 ? p.tma_out : p.staged) && (m0 + quarter * 32 + 32 <= p.M) && (key0w + 32 <= p.kv_Lk);
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + chalf * 128;
             uint32_t rbuf[2][32];
             tmem_ld_x32(t_addr, rbuf[0]);
@@ -282,6 +286,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int cpair = 0; cpair < 2; ++cpair) {
             int slab_row[2] = {-1, -1};
             uint32_t slab_src[2] = {0u, 0u};
+            int slab_col[2] = {0, 0};                      // out_mode 3: column of the hi half (lo = + N)
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci) {
                 const int cc = cpair * 2 + ci;
@@ -306,7 +311,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (cc + 1 < 4) tmem_ld_x32(t_addr + (cc + 1) * 32, rbuf[ci ^ 1]);
                 const int nb = n0 + c * 32;
                 if (nb >= p.N) continue;
-                if (OM == 2 && p.dbg == 2) continue;                 // diagnostic: TMEM loads only
+                if (p.dbg == 2) continue;                            // diagnostic: TMEM loads only (the MMA-bound floor)
                 const bool full = (nb + 32 <= p.N);
                 float v[32];
 #pragma unroll
@@ -329,6 +334,39 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (p.alpha != 1.f) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+                }
+                if constexpr (OM == 3 || OM == 4) {
+                    const bool fast = (OM == 3) ? (p.tma_out != 0) : slab;              // warp-uniform
+                    if (fast) {
+                        // hi / lo halves of this 32 x 32 chunk -> slabs 2 ci and 2 ci + 1 of the warp (64-byte TMA swizzle)
+                        if (ci == 0) {                          // the pair's four slabs: previous pair's stores have read them
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            __syncwarp();
+                        }
+                        const int s0 = ci * 2;
+                        uint8_t* swh = smem + 3 * STAGE_BYTES + ((warp - 2) * 3 + s0) * 2048;
+                        uint8_t* swl = (s0 + 1 < 3) ? smem + 3 * STAGE_BYTES + ((warp - 2) * 3 + s0 + 1) * 2048
+                                                    : stage_out + (warp - 2) * 2048;
+                        const uint32_t ah = smem_u32(swh) + lane * 64, al = smem_u32(swl) + lane * 64;
+                        const int xh = (ah >> 7) & 3, xl = (al >> 7) & 3;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 hq, lq;
+                            split_bf16x2(v[8 * j], v[8 * j + 1], hq.x, lq.x); split_bf16x2(v[8 * j + 2], v[8 * j + 3], hq.y, lq.y);
+                            split_bf16x2(v[8 * j + 4], v[8 * j + 5], hq.z, lq.z); split_bf16x2(v[8 * j + 6], v[8 * j + 7], hq.w, lq.w);
+                            st_shared_v4(ah + ((j ^ xh) << 4), hq.x, hq.y, hq.z, hq.w);
+                            st_shared_v4(al + ((j ^ xl) << 4), lq.x, lq.y, lq.z, lq.w);
+                        }
+                        slab_src[ci] = smem_u32(swh);
+                        slab_col[ci] = (int)smem_u32(swl);       // (re-used as the lo slab's address)
+                        if constexpr (OM == 3) {
+                            slab_row[ci] = nb;                   // column of the hi half; row = m0 + 32 quarter
+                        } else {
+                            const int l = nb / p.kv_E, h = (nb % p.kv_E) >> 5;
+                            slab_row[ci] = (int)((((int64_t)l * p.kv_B + kv_b) * (p.kv_E >> 5) + h) * p.kv_Lk + key0w);
+                        }
+                        continue;
+                    }
                 }
                 if (coal) {
                     // Coalesced stores: a thread owns one ROW of the accumulator (TMEM lane), so direct stores put
@@ -485,13 +523,23 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     store_split_bf16x32(cp, cp + p.N, v);
                 }
             }
-            if (OM == 2 && (slab_row[0] >= 0 || slab_row[1] >= 0)) {      // warp-uniform: one proxy fence per two chunks
+            if ((OM == 2 || OM == 3 || OM == 4) && (slab_row[0] >= 0 || slab_row[1] >= 0)) {   // warp-uniform: one proxy fence per two chunks
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0 && p.dbg != 1) {
 #pragma unroll
-                    for (int ci = 0; ci < 2; ++ci)
-                        if (slab_row[ci] >= 0) tma_store_2d(&tmC, slab_src[ci], 0, slab_row[ci]);
+                    for (int ci = 0; ci < 2; ++ci) {
+                        if (slab_row[ci] < 0) continue;
+                        if constexpr (OM == 2) {
+                            tma_store_2d(&tmC, slab_src[ci], 0, slab_row[ci]);
+                        } else if constexpr (OM == 3) {
+                            tma_store_2d(&tmC, slab_src[ci], slab_row[ci], m0 + quarter * 32);
+                            tma_store_2d(&tmC, (uint32_t)slab_col[ci], p.N + slab_row[ci], m0 + quarter * 32);
+                        } else {
+                            tma_store_2d(&tmC, slab_src[ci], 0, slab_row[ci]);
+                            tma_store_2d(&tmD, (uint32_t)slab_col[ci], 0, slab_row[ci]);
+                        }
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -501,7 +549,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (tr) GEMM_TR(trole, tcount, 6);
             if (p.bias) sbias[(buf ^ 1) * BN + et] = next_bias;     // read after the next tile's barrier
         }
-        if (p.staged && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if ((p.staged || p.tma_out) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     if (warp == 1) {
@@ -607,7 +655,7 @@ extern "C" int petr_gemm_tf32x3_tc(const float* A, int lda, int a_k_wrap, const 
     if (rc) return rc;
     rc = tmap::encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, W, dB, sB, boxB, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, EpiParams);
+    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, EpiParams);
     const gemm_fn fn = out_mode == 0 ? (gemm_fn)gemm_bf16_tc_kernel<0, true> : (gemm_fn)gemm_bf16_tc_kernel<6, true>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
     if (e != cudaSuccess) return fail((int)e, "petr_gemm_tf32x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -617,7 +665,7 @@ extern "C" int petr_gemm_tf32x3_tc(const float* A, int lda, int a_k_wrap, const 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = p.tiles_m * p.tiles_n;
-    fn<<<tiles < sms ? tiles : sms, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, tmA, p);
+    fn<<<tiles < sms ? tiles : sms, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, tmA, tmA, p);
     return after_launch("petr_gemm_tf32x3_tc");
 }
 
@@ -685,14 +733,25 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     if (rc) return rc;
     rc = tmap::encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, dB, sB, boxB, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    CUtensorMap tmC = tmA;                         // only out_mode 2 (staged) uses it
-    if (p.staged) {
+    CUtensorMap tmC = tmA, tmD = tmA;              // output maps of the TMA-store epilogues (out_modes 2, 3, 4)
+    if (p.staged || (out_mode == 4 && tuning::gemm_staged())) {
         uint64_t dC[2] = {32, (uint64_t)(N / 256) * p.kv_B * 8 * (uint64_t)p.kv_Lk}, sC[1] = {64};
         uint32_t boxC[2] = {32, 32};
         rc = tmap::encode(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, dC, sC, boxC, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
+        if (out_mode == 4) {
+            rc = tmap::encode(&tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C2, dC, sC, boxC, CU_TENSOR_MAP_SWIZZLE_64B);
+            if (rc) return rc;
+            p.tma_out = 1;
+        }
+    } else if (out_mode == 3 && !C2 && !residual && tuning::gemm_staged() && p.coalesce) {
+        uint64_t dC[2] = {(uint64_t)2 * N, (uint64_t)M}, sC[1] = {(uint64_t)2 * N * 2};
+        uint32_t boxC[2] = {32, 32};
+        rc = tmap::encode(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, dC, sC, boxC, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+        p.tma_out = 1;
     }
-    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, EpiParams);
+    typedef void (*gemm_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, EpiParams);
     // index 6: out_mode 0 with the sigmoid-gate epilogue -- its own instantiation (kernel-internal mode 7), so that the 32
     // exponentials + divisions per chunk do not bloat the other kernels (they doubled every instantiation's SASS, 34 ->
     // 63 KB against a 32 KB instruction cache, when the gate was a run-time branch)
@@ -714,6 +773,6 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     int tiles = p.tiles_m * p.tiles_n;
     int grid = tiles < sms ? tiles : sms;
     p.band = (out_mode == 2 && p.tiles_n > 1 && tuning::gemm_band()) ? grid : 0;      // measured slower (0.509 vs 0.466 ms): off by default
-    fn<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, tmC, p);
+    fn<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, tmC, tmD, p);
     return after_launch("petr_gemm_bf16_tc");
 }
