@@ -59,7 +59,10 @@ void petr_launch_count_reset(void);
 /* Explicit, process-wide tuning switches (A/B measurements and tests; the library reads no
  * environment variables).  Keys: "flash_exact_only" (0/1: skip the max-free fast pass of
  * petr_cross_attention_bf16), "flash_poly" (0..4: exponential pairs per 4 evaluated on the FMA pipe in
- * the fast pass).  Returns 0, or PETR_E_BADARG for an unknown key / out-of-range value;
+ * the fast pass), "gemm_staged" / "gemm_coalesce" / "gemm_skinny" / "gemm_band" (0/1: epilogue and tile-order variants of
+ * petr_gemm_bf16_tc), "gemm_debug" (diagnostic, 0 = off: 1 = out_mode 2 skips its global stores, 2 = every epilogue
+ * reduced to its TMEM loads -- the MMA-bound floor that tools/kproj_store_bound.py and tools/qside_epilogue_floor.py
+ * measure; results are then garbage by design).  Returns 0, or PETR_E_BADARG for an unknown key / out-of-range value;
  * petr_get_tuning returns the current value or -1. */
 int petr_set_tuning(const char* key, int value);
 int petr_get_tuning(const char* key);
