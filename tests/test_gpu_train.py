@@ -368,3 +368,27 @@ def test_train_mode_step_reduces_loss():
     head.eval()
     o = head([x], metas)
     assert not o["all_cls_scores"].requires_grad and torch.isfinite(o["all_cls_scores"]).all()
+
+
+def test_loss_with_a_sample_without_ground_truth():
+    """hungarian_assigner_3d.py:100-106: a sample with no boxes assigns every query to background; only the focal loss
+    sees it.  Losses and the feature gradient must still match the oracle."""
+    case = TRAIN_CASES["tiny"]
+    wl, feats, metas = cases.inputs(case)
+    head = pb.build_head(cases.head_cfg(case))
+    sd = cases.weights(case, head)
+    head.load_state_dict(sd, strict=True)
+    head = head.to(DEV)
+    gts, lab = _gts(feats.shape[0], 2, 23)            # sample 1: 2 - 2 = 0 boxes
+    assert gts[1].shape[0] == 0 and gts[0].shape[0] == 2
+    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    xr = feats.clone().requires_grad_(True)
+    lossr, _ = po.head_loss(po.head_forward(sdr, xr, metas, cases.oracle_cfg(case)), gts, lab,
+                            code_weights=sd["code_weights"].tolist())
+    sum(lossr.values()).backward()
+    xm = feats.clone().to(DEV).requires_grad_(True)
+    lossm = head.loss([t.to(DEV) for t in gts], [t.to(DEV) for t in lab], head.forward_autograd([xm], metas, dropout=False))
+    for k in lossr:
+        _close(lossm[k], lossr[k], 1e-4, k)
+    sum(lossm.values()).backward()
+    _close_l2(xm.grad, xr.grad, "d features", 1e-7 * float(xr.grad.abs().max()))
