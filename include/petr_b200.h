@@ -129,10 +129,14 @@ int petr_gemm_f32(const float* A, int lda, int a_layout, int hw,
  * fp32 array [Lq, Lk] (bias_per_head 0) or [B*heads, Lq, Lk] (bias_per_head 1); -inf entries mask.
  * Training (section 8f row 3): lse (nullable) fp32 [B, heads, Lq] receives log2-sum-exp2 of the scaled scores for
  * petr_attention_f32_bwd; drop_p > 0 applies attention-probability dropout (nn.MultiheadAttention's `dropout`) decided
- * by a counter-based hash of (seed, row, key) that the backward kernel re-evaluates. */
+ * by a counter-based hash of (seed, row, key) that the backward kernel re-evaluates.
+ * ksplit > 1: the key axis is split over ksplit blocks per (row block, head, sample) -- one thread owns a query row, and
+ * 900 rows x 8 heads do not fill the chip at small batch -- through `partial` (ksplit * petr_attention_partial_floats
+ * floats, caller-allocated) and an internal petr_attention_merge; ksplit <= 1: single pass, partial may be null. */
 int petr_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                        const uint8_t* key_mask, const float* attn_bias, int bias_per_head,
                        float* O, int ldo, void* O_split, float* lse, float drop_p, uint64_t seed,
+                       float* partial, int ksplit,
                        int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream);
 
 /* ---- nn.LayerNorm over the last dim (eps 1e-5 on this path), optional fused ReLU
@@ -303,8 +307,8 @@ int64_t petr_attention_x3_workspace_bytes(int B, int Lq, int Lk, int heads, int 
 /* Merge `nparts` partial attention results (on-GPU split-KV or key-split across GPUs after an
  * all-gather):  m = max m_r;  O = sum e^{m_r-m} O_r / sum e^{m_r-m} l_r.
  * partial: fp32 [nparts][ rows*32 (O) | rows*2 (m, l) ], rows = B*heads*Lq ordered (b, head, q);
- * m is in the log2 domain. */
-int petr_attention_merge(const float* partial, int nparts, float* O, int ldo, void* O_split,
+ * m is in the log2 domain.  lse (nullable): fp32 [B, heads, Lq] log2-sum-exp2 of the merged rows. */
+int petr_attention_merge(const float* partial, int nparts, float* O, int ldo, void* O_split, float* lse,
                          int B, int Lq, int heads, void* stream);
 
 int64_t petr_attention_partial_floats(int B, int Lq, int heads);

@@ -32,7 +32,7 @@ SIGNATURES = {
     "petr_sine3d_features": (c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _I, _P]),
     "petr_pos2posemb3d": (c_int, [_P, _P, _I, _I, _P, _P]),
     "petr_gemm_f32": (c_int, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
-    "petr_attention_f32": (c_int, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _P, _I, _P, _P, _F, c_uint64,
+    "petr_attention_f32": (c_int, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _P, _I, _P, _P, _F, c_uint64, _P, _I,
                                    _I, _I, _I, _I, _I, _F, _P]),
     "petr_layernorm_multi_f32": (c_int, [_P, _P, _P, _F, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "petr_split_rows_bf16": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
@@ -53,7 +53,7 @@ SIGNATURES = {
     "petr_cross_attention_trace": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "petr_attention_x3_tc": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P]),
     "petr_attention_x3_workspace_bytes": (c_int64, [_I, _I, _I, _I, _I]),
-    "petr_attention_merge": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "petr_attention_merge": (c_int, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P]),
     "petr_attention_partial_floats": (c_int64, [_I, _I, _I]),
     "petr_sine2d_features": (c_int, [_P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _I, _P]),
     "petr_learned_pos_features": (c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),

@@ -41,6 +41,29 @@ int gemm_debug();
 void* debug_trace();
 }  // namespace tuning
 
+// packed fp32x2 arithmetic (sm_100: two fp32 FMAs per issued instruction)
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(uint64_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+
 #define PETR_REQUIRE(cond, code, ...) \
     do { if (!(cond)) return ::petr::fail((code), __VA_ARGS__); } while (0)
 

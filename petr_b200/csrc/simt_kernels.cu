@@ -369,143 +369,151 @@ gemm_f32_kernel(GemmParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// fp32 flash-style attention, head_dim 32.  A quad of 4 lanes owns one query row: lane `sub`
-// streams keys k = sub (mod 4) of every smem tile with its own online-softmax state (m, l, o[32]);
-// the four states are merged with warp shuffles at the end.  128 threads = 32 queries per block.
+// fp32 flash-style attention, head_dim 32 (the exact-arithmetic parity path and the training forward).
+// One thread owns one query row (q, the online-softmax state m / l and o[32] in registers); a block of 64 rows streams
+// 32-key tiles of K and V from shared memory -- every lane reads the SAME key row, so the loads are broadcasts -- in
+// groups of 8 keys (one running-maximum update and one rescale of o per group).  All dot products / axpys are packed
+// fma.rn.f32x2 (two fp32 FMAs per issued instruction on sm_100: the FMA pipe stays at 128 lanes/clk/SM but the issue
+// slots the shared-memory loads need are freed; tools/probes/probe_ffma2.cu).  1.6x the quad-per-row version it
+// replaces (shuffle merges, scalar FMAs): 13.5 -> 8.4 ms for the six cross-attentions of a 1600x640 sample.
 // ------------------------------------------------------------------------------------------
-constexpr int ATT_THREADS = 128, ATT_QPB = 32, ATT_KT = 64;
+constexpr int ATT_ROWS = 64, ATT_KT = 32;
 
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_ROWS)
 attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk,
                      const float* __restrict__ V, int ldv, const uint8_t* __restrict__ key_mask,
                      float* __restrict__ O, int ldo, __nv_bfloat16* __restrict__ O_split, int E,
                      int Lq, int Lk, float scale_log2, const float* __restrict__ attn_bias,
-                     int64_t bias_bh_stride, float* __restrict__ lse, float drop_p, uint64_t seed) {
-    // rows padded to 36 floats: the four lanes of a quad read four different rows per LDS.128 and
-    // a 32-float pitch would put them on the same banks
-    __shared__ __align__(16) float sK[ATT_KT][36];
-    __shared__ __align__(16) float sV[ATT_KT][36];
+                     int64_t bias_bh_stride, float* __restrict__ lse, float drop_p, uint64_t seed,
+                     float* __restrict__ partial, int ksplit) {
+    __shared__ __align__(16) float sK[ATT_KT][32];
+    __shared__ __align__(16) float sV[ATT_KT][32];
     __shared__ float sBias[ATT_KT];
-    const int head = blockIdx.y, b = blockIdx.z;
-    const int sub = threadIdx.x & 3;
-    const int q = blockIdx.x * ATT_QPB + (threadIdx.x >> 2);
+    // ksplit > 1: the key axis is split over `ksplit` blocks per (row block, head, sample) -- 900 query rows x 8 heads
+    // are 113 warps per sample, too few for 148 SMs -- and every part writes its un-normalised (o, m, l) to `partial`
+    // in the layout petr_attention_merge reads
+    const int head = blockIdx.y, b = blockIdx.z / ksplit, part = blockIdx.z - b * ksplit;
+    const int q = blockIdx.x * ATT_ROWS + threadIdx.x;
     const bool live = q < Lq;
-    float qv[32], o[32];
+    const int bh = b * gridDim.y + head;
+    uint64_t q2[16], o2[16];
     {
         const float* qp = Q + ((int64_t)b * Lq + (live ? q : 0)) * ldq + head * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-            float4 t = *reinterpret_cast<const float4*>(qp + i);
-            qv[i] = t.x * scale_log2; qv[i + 1] = t.y * scale_log2;
-            qv[i + 2] = t.z * scale_log2; qv[i + 3] = t.w * scale_log2;
-            o[i] = o[i + 1] = o[i + 2] = o[i + 3] = 0.f;
+            const float4 t = *reinterpret_cast<const float4*>(qp + i);
+            q2[i >> 1] = pack2(t.x * scale_log2, t.y * scale_log2);
+            q2[(i >> 1) + 1] = pack2(t.z * scale_log2, t.w * scale_log2);
+            o2[i >> 1] = o2[(i >> 1) + 1] = 0ull;
         }
     }
     float m = -INFINITY, l = 0.f;
     // attn_mask of torch.nn.MultiheadAttention as an additive fp32 bias [Lq, Lk] (bias_bh_stride 0) or
     // [B*heads, Lq, Lk]; attention-probability dropout (training) is a counter-based hash of (row, key)
-    const int bh = b * gridDim.y + head;
     const float* brow = attn_bias ? attn_bias + (int64_t)bh * bias_bh_stride + (int64_t)(live ? q : 0) * Lk : nullptr;
     const uint64_t drop_row = ((uint64_t)bh * Lq + (live ? q : 0)) * (uint64_t)Lk;
     const float drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
     const float* Kb = K + (int64_t)b * Lk * ldk + head * 32;
     const float* Vb = V + (int64_t)b * Lk * ldv + head * 32;
-    for (int k0 = 0; k0 < Lk; k0 += ATT_KT) {
+    const int tiles = (Lk + ATT_KT - 1) / ATT_KT;
+    const int k_begin = (int)((int64_t)tiles * part / ksplit) * ATT_KT;
+    const int k_end = min(Lk, (int)((int64_t)tiles * (part + 1) / ksplit) * ATT_KT);
+    for (int k0 = k_begin; k0 < k_end; k0 += ATT_KT) {
         __syncthreads();
-        for (int i = threadIdx.x; i < ATT_KT * 8; i += ATT_THREADS) {
-            int r = i / 8, c4 = (i % 8) * 4;
+        for (int i = threadIdx.x; i < ATT_KT * 8; i += ATT_ROWS) {
+            const int r = i >> 3, c4 = (i & 7) * 4;
             float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-            if (k0 + r < Lk) {
+            if (k0 + r < k_end) {
                 kv = *reinterpret_cast<const float4*>(Kb + (int64_t)(k0 + r) * ldk + c4);
                 vv = *reinterpret_cast<const float4*>(Vb + (int64_t)(k0 + r) * ldv + c4);
             }
             *reinterpret_cast<float4*>(&sK[r][c4]) = kv;
             *reinterpret_cast<float4*>(&sV[r][c4]) = vv;
         }
-        for (int r = threadIdx.x; r < ATT_KT; r += ATT_THREADS) {
-            bool dead = (k0 + r >= Lk) || (key_mask && key_mask[(int64_t)b * Lk + k0 + r]);
+        if (threadIdx.x < ATT_KT) {
+            const int r = threadIdx.x;
+            const bool dead = (k0 + r >= k_end) || (key_mask && key_mask[(int64_t)b * Lk + k0 + r]);
             sBias[r] = dead ? -INFINITY : 0.f;
         }
         __syncthreads();
 #pragma unroll 1
-        for (int g = 0; g < ATT_KT / 32; ++g) {          // 8 keys per lane per group
-            float s[8];
+        for (int g = 0; g < ATT_KT / 8; ++g) {
+            float sc[8];
             float mx = m;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int r = g * 32 + j * 4 + sub;
-                float a0 = 0.f, a1 = 0.f;
+            for (int jj = 0; jj < 8; ++jj) {
+                const int r = g * 8 + jj;
+                uint64_t a0 = 0ull, a1 = 0ull;
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    float4 k0v = *reinterpret_cast<const float4*>(&sK[r][i]);
-                    float4 k1v = *reinterpret_cast<const float4*>(&sK[r][i + 4]);
-                    a0 = fmaf(qv[i], k0v.x, a0); a0 = fmaf(qv[i + 1], k0v.y, a0);
-                    a0 = fmaf(qv[i + 2], k0v.z, a0); a0 = fmaf(qv[i + 3], k0v.w, a0);
-                    a1 = fmaf(qv[i + 4], k1v.x, a1); a1 = fmaf(qv[i + 5], k1v.y, a1);
-                    a1 = fmaf(qv[i + 6], k1v.z, a1); a1 = fmaf(qv[i + 7], k1v.w, a1);
+                for (int i = 0; i < 16; i += 4) {
+                    const ulonglong2 ka = *reinterpret_cast<const ulonglong2*>(&sK[r][2 * i]);
+                    const ulonglong2 kb = *reinterpret_cast<const ulonglong2*>(&sK[r][2 * i + 4]);
+                    a0 = fma2(q2[i], ka.x, a0); a1 = fma2(q2[i + 1], ka.y, a1);
+                    a0 = fma2(q2[i + 2], kb.x, a0); a1 = fma2(q2[i + 3], kb.y, a1);
                 }
-                s[j] = (a0 + a1) + sBias[r];
-                if (brow && k0 + r < Lk) s[j] += brow[k0 + r] * 1.4426950408889634f;
-                mx = fmaxf(mx, s[j]);
+                const float2 u = unpack2(a0), w = unpack2(a1);
+                float sj = ((u.x + u.y) + (w.x + w.y)) + sBias[r];
+                if (brow && k0 + r < Lk) sj += brow[k0 + r] * 1.4426950408889634f;
+                sc[jj] = sj;
+                mx = fmaxf(mx, sj);
             }
             if (mx == -INFINITY) continue;             // everything so far masked
-            float alpha = exp2f(m - mx);               // m = -inf -> 0
-            m = mx;
-            l *= alpha;
+            if (mx > m) {                              // new running maximum: rescale the state once per group
+                const float alpha = exp2f(m - mx);     // m = -inf -> 0
+                const uint64_t al2 = pack2(alpha, alpha);
+                l *= alpha;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] *= alpha;
+                for (int i = 0; i < 16; ++i) o2[i] = mul2(o2[i], al2);
+                m = mx;
+            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int r = g * 32 + j * 4 + sub;
-                float pj = exp2f(s[j] - mx);
+            for (int jj = 0; jj < 8; ++jj) {
+                const int r = g * 8 + jj;
+                float pj = exp2f(sc[jj] - m);
                 l += pj;
                 if (drop_p > 0.f) pj = dropout_keep(seed, drop_row + (uint64_t)(k0 + r), drop_p) ? pj * drop_scale : 0.f;
+                const uint64_t p2 = pack2(pj, pj);
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    float4 vv = *reinterpret_cast<const float4*>(&sV[r][i]);
-                    o[i] = fmaf(pj, vv.x, o[i]); o[i + 1] = fmaf(pj, vv.y, o[i + 1]);
-                    o[i + 2] = fmaf(pj, vv.z, o[i + 2]); o[i + 3] = fmaf(pj, vv.w, o[i + 3]);
+                for (int i = 0; i < 16; i += 2) {
+                    const ulonglong2 vv = *reinterpret_cast<const ulonglong2*>(&sV[r][2 * i]);
+                    o2[i] = fma2(p2, vv.x, o2[i]);
+                    o2[i + 1] = fma2(p2, vv.y, o2[i + 1]);
                 }
             }
         }
     }
-    // merge the quad's four partial states (xor 1, xor 2 stay inside the quad)
+    if (!live) return;
+    if (ksplit > 1) {
+        const int64_t rows = (int64_t)gridDim.z / ksplit * gridDim.y * Lq;
+        const int64_t r = (int64_t)bh * Lq + q;
+        float* po = partial + (int64_t)part * rows * 34 + r * 32;
 #pragma unroll
-    for (int off = 1; off <= 2; off <<= 1) {
-        float m2 = __shfl_xor_sync(0xffffffffu, m, off);
-        float l2 = __shfl_xor_sync(0xffffffffu, l, off);
-        float mn = fmaxf(m, m2);
-        float w1 = (m == -INFINITY) ? 0.f : exp2f(m - mn);
-        float w2 = (m2 == -INFINITY) ? 0.f : exp2f(m2 - mn);
-        l = l * w1 + l2 * w2;
+        for (int i = 0; i < 16; i += 2) {
+            const float2 t0 = unpack2(o2[i]), t1 = unpack2(o2[i + 1]);
+            *reinterpret_cast<float4*>(po + 2 * i) = make_float4(t0.x, t0.y, t1.x, t1.y);
+        }
+        float* pml = partial + (int64_t)part * rows * 34 + rows * 32 + r * 2;
+        pml[0] = m;
+        pml[1] = l;
+        return;
+    }
+    if (lse) lse[(int64_t)bh * Lq + q] = m + log2f(l);         // log2-domain log-sum-exp of the scaled scores (backward)
+    const float inv = 1.f / l;                                 // l == 0 (all keys masked) -> NaN, as torch
+    float r32[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float2 t = unpack2(o2[i]); r32[2 * i] = t.x * inv; r32[2 * i + 1] = t.y * inv; }
+    if (O) {
+        float* op = O + ((int64_t)b * Lq + q) * ldo + head * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(r32[i], r32[i + 1], r32[i + 2], r32[i + 3]);
+    }
+    if (O_split) {                                             // bf16 [hi | lo] rows of width 2E (bf16x3 GEMM input)
+        __nv_bfloat16* sp = O_split + ((int64_t)b * Lq + q) * (2 * E) + head * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            float o2 = __shfl_xor_sync(0xffffffffu, o[i], off);
-            o[i] = o[i] * w1 + o2 * w2;
-        }
-        m = mn;
-    }
-    if (live && lse && sub == 0)                       // log2-domain log-sum-exp of the scaled scores (backward)
-        lse[((int64_t)bh) * Lq + q] = m + log2f(l);
-    if (live) {
-        const float inv = 1.f / l;                     // l == 0 (all keys masked) -> NaN, as torch
-        // lane `sub` writes dims [8*sub, 8*sub+8)
-        float r8[8];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) if ((i >> 3) == sub) r8[i & 7] = o[i] * inv;
-        if (O) {
-            float* op = O + ((int64_t)b * Lq + q) * ldo + head * 32 + sub * 8;
-            *reinterpret_cast<float4*>(op) = make_float4(r8[0], r8[1], r8[2], r8[3]);
-            *reinterpret_cast<float4*>(op + 4) = make_float4(r8[4], r8[5], r8[6], r8[7]);
-        }
-        if (O_split) {                                 // bf16 [hi | lo] rows of width 2E (bf16x3 GEMM input)
-            __nv_bfloat16* sp = O_split + ((int64_t)b * Lq + q) * (2 * E) + head * 32 + sub * 8;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                __nv_bfloat16 hi = __float2bfloat16_rn(r8[i]);
-                sp[i] = hi;
-                sp[E + i] = __float2bfloat16_rn(r8[i] - __bfloat162float(hi));
-            }
+            const __nv_bfloat16 hi = __float2bfloat16_rn(r32[i]);
+            sp[i] = hi;
+            sp[E + i] = __float2bfloat16_rn(r32[i] - __bfloat162float(hi));
         }
     }
 }
@@ -889,6 +897,7 @@ extern "C" int petr_gemm_f32(const float* A, int lda, int a_layout, int hw, cons
 extern "C" int petr_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V,
                                   int ldv, const uint8_t* key_mask, const float* attn_bias, int bias_per_head,
                                   float* O, int ldo, void* O_split, float* lse, float drop_p, uint64_t seed,
+                                  float* partial, int ksplit,
                                   int B, int Lq, int Lk, int heads, int head_dim, float scale, void* stream) {
     PETR_REQUIRE(Q && K && V && (O || O_split), PETR_E_BADARG, "petr_attention_f32: null pointer");
     PETR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0, PETR_E_BADARG, "petr_attention_f32: bad dimension");
@@ -897,11 +906,19 @@ extern "C" int petr_attention_f32(const float* Q, int ldq, const float* K, int l
     PETR_REQUIRE((ldk & 3) == 0 && (ldv & 3) == 0 && aligned16(K) && aligned16(V) && (ldq & 3) == 0 && aligned16(Q),
                  PETR_E_ALIGN, "petr_attention_f32: Q/K/V rows must be 16-byte aligned");
     if (O) PETR_REQUIRE((ldo & 3) == 0 && aligned16(O), PETR_E_ALIGN, "petr_attention_f32: O rows must be 16-byte aligned");
-    dim3 grid((Lq + ATT_QPB - 1) / ATT_QPB, heads, B);
-    attention_f32_kernel<<<grid, ATT_THREADS, 0, (cudaStream_t)stream>>>(
+    if (ksplit < 1) ksplit = 1;
+    const int tiles = (Lk + ATT_KT - 1) / ATT_KT;
+    if (ksplit > tiles) ksplit = tiles;
+    PETR_REQUIRE(ksplit == 1 || (partial && aligned16(partial)), PETR_E_BADARG,
+                 "petr_attention_f32: ksplit > 1 needs a 16-byte aligned partial buffer (ksplit * petr_attention_partial_floats)");
+    PETR_REQUIRE((int64_t)B * ksplit <= 65535, PETR_E_SHAPE, "petr_attention_f32: B * ksplit too large");
+    dim3 grid((Lq + ATT_ROWS - 1) / ATT_ROWS, heads, B * ksplit);
+    attention_f32_kernel<<<grid, ATT_ROWS, 0, (cudaStream_t)stream>>>(
         Q, ldq, K, ldk, V, ldv, key_mask, O, ldo, (__nv_bfloat16*)O_split, heads * 32, Lq, Lk,
-        scale * 1.4426950408889634f, attn_bias, bias_per_head ? (int64_t)Lq * Lk : 0, lse, drop_p, seed);
-    return after_launch("petr_attention_f32");
+        scale * 1.4426950408889634f, attn_bias, bias_per_head ? (int64_t)Lq * Lk : 0, lse, drop_p, seed, partial, ksplit);
+    int rc = after_launch("petr_attention_f32");
+    if (rc || ksplit == 1) return rc;
+    return petr_attention_merge(partial, ksplit, O, ldo, O_split, lse, B, Lq, heads, stream);
 }
 
 extern "C" int petr_layernorm_f32(const float* X, const float* gamma, const float* beta, float* Y,

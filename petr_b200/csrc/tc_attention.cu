@@ -864,7 +864,8 @@ cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 
 // merge partial (O, m, l) over parts; thread per (row, 4 dims)
 __global__ void attention_merge_kernel(const float* __restrict__ part, int nparts, float* __restrict__ O,
-                                       int ldo, __nv_bfloat16* __restrict__ O_split, int B, int Lq, int heads) {
+                                       int ldo, __nv_bfloat16* __restrict__ O_split, int B, int Lq, int heads,
+                                       float* __restrict__ lse = nullptr) {
     const int64_t rows = (int64_t)B * heads * Lq;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * 8) return;
@@ -884,6 +885,7 @@ __global__ void attention_merge_kernel(const float* __restrict__ part, int npart
         acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
     }
     const float inv = 1.f / den;                     // den == 0 -> NaN (all keys masked)
+    if (lse && d4 == 0) lse[r] = m + log2f(den);     // rows are ordered (b, head, q): the layout petr_attention_f32_bwd reads
     const int q = (int)(r % Lq);
     const int bh = (int)(r / Lq);
     const int b = bh / heads, h = bh % heads;
@@ -1056,14 +1058,14 @@ extern "C" int petr_cross_attention_trace(const void* Qs, const void* Kh, const 
     return after_launch("petr_cross_attention_trace");
 }
 
-extern "C" int petr_attention_merge(const float* partial, int nparts, float* O, int ldo, void* O_split,
+extern "C" int petr_attention_merge(const float* partial, int nparts, float* O, int ldo, void* O_split, float* lse,
                                     int B, int Lq, int heads, void* stream) {
     PETR_REQUIRE(partial && (O || O_split), PETR_E_BADARG, "petr_attention_merge: null pointer");
     PETR_REQUIRE(nparts > 0 && B > 0 && Lq > 0 && heads > 0, PETR_E_BADARG, "petr_attention_merge: bad dimension");
     if (O) PETR_REQUIRE(ldo >= heads * 32 && (ldo % 4) == 0, PETR_E_BADARG, "petr_attention_merge: bad ldo");
     int64_t total = (int64_t)B * heads * Lq * 8;
     attention_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        partial, nparts, O, ldo, (__nv_bfloat16*)O_split, B, Lq, heads);
+        partial, nparts, O, ldo, (__nv_bfloat16*)O_split, B, Lq, heads, lse);
     return after_launch("petr_attention_merge");
 }
 

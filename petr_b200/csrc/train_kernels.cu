@@ -235,7 +235,7 @@ attention_bwd_dq_kernel(AttBwdParams p) {
     const bool live = q < p.Lq;
     const int bh = b * p.heads + head;
     const float scale_log2 = p.scale * LOG2E;
-    float qv[32], dov[32], dq[32];
+    uint64_t q2[16], do2[16], dq2[16];            // packed fp32 pairs (fma.rn.f32x2: two FMAs per issued instruction)
     float D = 0.f, lse = 0.f;
     {
         const int64_t row = (int64_t)b * p.Lq + (live ? q : 0);
@@ -243,11 +243,12 @@ attention_bwd_dq_kernel(AttBwdParams p) {
         const float* dop = p.dO + row * p.lddo + head * 32;
         const float* op = p.O + row * p.ldo + head * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            qv[i] = qp[i] * scale_log2;
-            dov[i] = dop[i];
-            D = fmaf(dov[i], op[i], D);
-            dq[i] = 0.f;
+        for (int i = 0; i < 32; i += 2) {
+            q2[i >> 1] = pack2(qp[i] * scale_log2, qp[i + 1] * scale_log2);
+            do2[i >> 1] = pack2(dop[i], dop[i + 1]);
+            D = fmaf(dop[i], op[i], D);
+            D = fmaf(dop[i + 1], op[i + 1], D);
+            dq2[i >> 1] = 0ull;
         }
         lse = p.lse[(int64_t)bh * p.Lq + (live ? q : 0)];
     }
@@ -281,30 +282,36 @@ attention_bwd_dq_kernel(AttBwdParams p) {
         if (dead_row) continue;
 #pragma unroll 2
         for (int r = 0; r < AB_TILE; ++r) {
-            float s0 = 0.f, s1 = 0.f, d0 = 0.f, d1 = 0.f;
+            uint64_t s0 = 0ull, s1 = 0ull, s2 = 0ull, s3 = 0ull, d0 = 0ull, d1 = 0ull, d2 = 0ull, d3 = 0ull;   // short chains
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                const float4 ka = *reinterpret_cast<const float4*>(&sK[r][i]), kb = *reinterpret_cast<const float4*>(&sK[r][i + 4]);
-                const float4 va = *reinterpret_cast<const float4*>(&sV[r][i]), vb = *reinterpret_cast<const float4*>(&sV[r][i + 4]);
-                s0 = fmaf(qv[i], ka.x, s0); s0 = fmaf(qv[i + 1], ka.y, s0); s0 = fmaf(qv[i + 2], ka.z, s0); s0 = fmaf(qv[i + 3], ka.w, s0);
-                s1 = fmaf(qv[i + 4], kb.x, s1); s1 = fmaf(qv[i + 5], kb.y, s1); s1 = fmaf(qv[i + 6], kb.z, s1); s1 = fmaf(qv[i + 7], kb.w, s1);
-                d0 = fmaf(dov[i], va.x, d0); d0 = fmaf(dov[i + 1], va.y, d0); d0 = fmaf(dov[i + 2], va.z, d0); d0 = fmaf(dov[i + 3], va.w, d0);
-                d1 = fmaf(dov[i + 4], vb.x, d1); d1 = fmaf(dov[i + 5], vb.y, d1); d1 = fmaf(dov[i + 6], vb.z, d1); d1 = fmaf(dov[i + 7], vb.w, d1);
+            for (int i = 0; i < 16; i += 4) {
+                const ulonglong2 ka = *reinterpret_cast<const ulonglong2*>(&sK[r][2 * i]);
+                const ulonglong2 kb = *reinterpret_cast<const ulonglong2*>(&sK[r][2 * i + 4]);
+                const ulonglong2 va = *reinterpret_cast<const ulonglong2*>(&sV[r][2 * i]);
+                const ulonglong2 vb = *reinterpret_cast<const ulonglong2*>(&sV[r][2 * i + 4]);
+                s0 = fma2(q2[i], ka.x, s0); s1 = fma2(q2[i + 1], ka.y, s1); s2 = fma2(q2[i + 2], kb.x, s2); s3 = fma2(q2[i + 3], kb.y, s3);
+                d0 = fma2(do2[i], va.x, d0); d1 = fma2(do2[i + 1], va.y, d1); d2 = fma2(do2[i + 2], vb.x, d2); d3 = fma2(do2[i + 3], vb.y, d3);
             }
-            float s = (s0 + s1) + sBias[r];
+            const float2 su = unpack2(s0), sw = unpack2(s1), sy = unpack2(s2), sz = unpack2(s3);
+            const float2 du = unpack2(d0), dw = unpack2(d1), dy = unpack2(d2), dz = unpack2(d3);
+            float s = (((su.x + su.y) + (sw.x + sw.y)) + ((sy.x + sy.y) + (sz.x + sz.y))) + sBias[r];
             if (brow && k0 + r < p.Lk) s += brow[k0 + r] * LOG2E;
             const float pr = exp2f(s - lse);                                  // -inf -> 0
-            float dp = d0 + d1;
+            float dp = ((du.x + du.y) + (dw.x + dw.y)) + ((dy.x + dy.y) + (dz.x + dz.y));
             if (p.drop_p > 0.f) dp = dropout_keep(p.seed, drop_row + (uint64_t)(k0 + r), p.drop_p) ? dp * drop_scale : 0.f;
             const float ds = pr * (dp - D);
+            const uint64_t ds2 = pack2(ds, ds);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 kk = *reinterpret_cast<const float4*>(&sK[r][i]);
-                dq[i] = fmaf(ds, kk.x, dq[i]); dq[i + 1] = fmaf(ds, kk.y, dq[i + 1]);
-                dq[i + 2] = fmaf(ds, kk.z, dq[i + 2]); dq[i + 3] = fmaf(ds, kk.w, dq[i + 3]);
+            for (int i = 0; i < 16; i += 2) {
+                const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(&sK[r][2 * i]);
+                dq2[i] = fma2(ds2, kk.x, dq2[i]);
+                dq2[i + 1] = fma2(ds2, kk.y, dq2[i + 1]);
             }
         }
     }
+    float dq[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float2 t = unpack2(dq2[i]); dq[2 * i] = t.x; dq[2 * i + 1] = t.y; }
     if (live) {
         float* out = p.dQ + ((int64_t)b * p.Lq + q) * p.lddq + head * 32;
         if (p.ksplit == 1) {
@@ -327,13 +334,18 @@ attention_bwd_dkv_kernel(AttBwdParams p) {
     const int bh = b * p.heads + head;
     const bool live = k < p.Lk && !(p.key_mask && p.key_mask[(int64_t)b * p.Lk + k]);
     const float scale_log2 = p.scale * LOG2E;
-    float kv[32], vv[32], dk[32], dv[32];
+    uint64_t k2[16], v2[16], dk2[16], dv2[16];    // packed fp32 pairs
     {
         const int64_t row = (int64_t)b * p.Lk + (k < p.Lk ? k : 0);
         const float* kp = p.K + row * p.ldk + head * 32;
         const float* vp = p.V + row * p.ldv + head * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { kv[i] = kp[i]; vv[i] = vp[i]; dk[i] = 0.f; dv[i] = 0.f; }
+        for (int i = 0; i < 32; i += 2) {
+            k2[i >> 1] = pack2(kp[i], kp[i + 1]);
+            v2[i >> 1] = pack2(vp[i], vp[i + 1]);
+            dk2[i >> 1] = 0ull;
+            dv2[i >> 1] = 0ull;
+        }
     }
     const float drop_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     const float* Qb = p.Q + (int64_t)b * p.Lq * p.ldq + head * 32;
@@ -369,17 +381,19 @@ attention_bwd_dkv_kernel(AttBwdParams p) {
         if (!live) continue;
 #pragma unroll 2
         for (int r = 0; r < AB_TILE; ++r) {
-            float s0 = 0.f, s1 = 0.f, d0 = 0.f, d1 = 0.f;
+            uint64_t s0 = 0ull, s1 = 0ull, s2 = 0ull, s3 = 0ull, d0 = 0ull, d1 = 0ull, d2 = 0ull, d3 = 0ull;   // short chains
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                const float4 qa = *reinterpret_cast<const float4*>(&sQ[r][i]), qb = *reinterpret_cast<const float4*>(&sQ[r][i + 4]);
-                const float4 da = *reinterpret_cast<const float4*>(&sdO[r][i]), db = *reinterpret_cast<const float4*>(&sdO[r][i + 4]);
-                s0 = fmaf(kv[i], qa.x, s0); s0 = fmaf(kv[i + 1], qa.y, s0); s0 = fmaf(kv[i + 2], qa.z, s0); s0 = fmaf(kv[i + 3], qa.w, s0);
-                s1 = fmaf(kv[i + 4], qb.x, s1); s1 = fmaf(kv[i + 5], qb.y, s1); s1 = fmaf(kv[i + 6], qb.z, s1); s1 = fmaf(kv[i + 7], qb.w, s1);
-                d0 = fmaf(vv[i], da.x, d0); d0 = fmaf(vv[i + 1], da.y, d0); d0 = fmaf(vv[i + 2], da.z, d0); d0 = fmaf(vv[i + 3], da.w, d0);
-                d1 = fmaf(vv[i + 4], db.x, d1); d1 = fmaf(vv[i + 5], db.y, d1); d1 = fmaf(vv[i + 6], db.z, d1); d1 = fmaf(vv[i + 7], db.w, d1);
+            for (int i = 0; i < 16; i += 4) {
+                const ulonglong2 qa = *reinterpret_cast<const ulonglong2*>(&sQ[r][2 * i]);
+                const ulonglong2 qb = *reinterpret_cast<const ulonglong2*>(&sQ[r][2 * i + 4]);
+                const ulonglong2 da = *reinterpret_cast<const ulonglong2*>(&sdO[r][2 * i]);
+                const ulonglong2 db = *reinterpret_cast<const ulonglong2*>(&sdO[r][2 * i + 4]);
+                s0 = fma2(k2[i], qa.x, s0); s1 = fma2(k2[i + 1], qa.y, s1); s2 = fma2(k2[i + 2], qb.x, s2); s3 = fma2(k2[i + 3], qb.y, s3);
+                d0 = fma2(v2[i], da.x, d0); d1 = fma2(v2[i + 1], da.y, d1); d2 = fma2(v2[i + 2], db.x, d2); d3 = fma2(v2[i + 3], db.y, d3);
             }
-            float s = s0 + s1;
+            const float2 su = unpack2(s0), sw = unpack2(s1), sy = unpack2(s2), sz = unpack2(s3);
+            const float2 du = unpack2(d0), dw = unpack2(d1), dy = unpack2(d2), dz = unpack2(d3);
+            float s = ((su.x + su.y) + (sw.x + sw.y)) + ((sy.x + sy.y) + (sz.x + sz.y));
             if (p.attn_bias && q0 + r < p.Lq)
                 s += p.attn_bias[(int64_t)bh * p.bias_bh_stride + (int64_t)(q0 + r) * p.Lk + k] * LOG2E;
             const float pr = exp2f(s - sLse[r]);
@@ -388,17 +402,22 @@ attention_bwd_dkv_kernel(AttBwdParams p) {
                 m = dropout_keep(p.seed, ((uint64_t)bh * p.Lq + (uint64_t)(q0 + r)) * (uint64_t)p.Lk + (uint64_t)k, p.drop_p)
                         ? drop_scale : 0.f;
             const float pd = pr * m;
-            const float ds = pr * ((d0 + d1) * m - sD[r]);
+            const float ds = pr * ((((du.x + du.y) + (dw.x + dw.y)) + ((dy.x + dy.y) + (dz.x + dz.y))) * m - sD[r]);
+            const uint64_t pd2 = pack2(pd, pd), ds2 = pack2(ds, ds);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 dd = *reinterpret_cast<const float4*>(&sdO[r][i]);
-                const float4 qq = *reinterpret_cast<const float4*>(&sQ[r][i]);
-                dv[i] = fmaf(pd, dd.x, dv[i]); dv[i + 1] = fmaf(pd, dd.y, dv[i + 1]);
-                dv[i + 2] = fmaf(pd, dd.z, dv[i + 2]); dv[i + 3] = fmaf(pd, dd.w, dv[i + 3]);
-                dk[i] = fmaf(ds, qq.x, dk[i]); dk[i + 1] = fmaf(ds, qq.y, dk[i + 1]);
-                dk[i + 2] = fmaf(ds, qq.z, dk[i + 2]); dk[i + 3] = fmaf(ds, qq.w, dk[i + 3]);
+            for (int i = 0; i < 16; i += 2) {
+                const ulonglong2 dd = *reinterpret_cast<const ulonglong2*>(&sdO[r][2 * i]);
+                const ulonglong2 qq = *reinterpret_cast<const ulonglong2*>(&sQ[r][2 * i]);
+                dv2[i] = fma2(pd2, dd.x, dv2[i]); dv2[i + 1] = fma2(pd2, dd.y, dv2[i + 1]);
+                dk2[i] = fma2(ds2, qq.x, dk2[i]); dk2[i + 1] = fma2(ds2, qq.y, dk2[i + 1]);
             }
         }
+    }
+    float dk[32], dv[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float2 a = unpack2(dk2[i]), c = unpack2(dv2[i]);
+        dk[2 * i] = a.x; dk[2 * i + 1] = a.y; dv[2 * i] = c.x; dv[2 * i + 1] = c.y;
     }
     if (k < p.Lk) {
         float* ok = p.dK + ((int64_t)b * p.Lk + k) * p.lddk + head * 32;

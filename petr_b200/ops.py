@@ -146,11 +146,17 @@ def attention_f32(Q, K, V, key_mask, B: int, Lq: int, Lk: int, heads: int, out=N
         assert attn_bias.dtype == torch.float32 and attn_bias.is_contiguous()
         assert tuple(attn_bias.shape) in ((Lq, Lk), (B * heads, Lq, Lk)), attn_bias.shape
         per_head = int(attn_bias.dim() == 3)
+    # one thread per query row: split the key axis until the grid has ~4 blocks per SM (each part >= 8 key tiles)
+    blocks = ((Lq + 63) // 64) * heads * B
+    ksplit = max(1, min((4 * 148 + blocks - 1) // blocks, ((Lk + 31) // 32) // 8, 65535 // max(B, 1)))
+    partial = None
+    if ksplit > 1:
+        partial = torch.empty((ksplit * attention_partial_floats(B, Lq, heads),), dtype=torch.float32, device=Q.device)
     with _Timed("attention_f32"):
         call("petr_attention_f32", ptr(Q), Q.stride(0), ptr(K), K.stride(0), ptr(V), V.stride(0),
              ptr(key_mask), ptr(attn_bias), per_head, ptr(out), out.stride(0) if out is not None else 0,
-             ptr(out_split), ptr(lse), float(drop_p), int(seed), B, Lq, Lk, heads, d, 1.0 / math.sqrt(d),
-             stream_ptr(Q.device))
+             ptr(out_split), ptr(lse), float(drop_p), int(seed), ptr(partial), ksplit, B, Lq, Lk, heads, d,
+             1.0 / math.sqrt(d), stream_ptr(Q.device))
     return out if out is not None else out_split
 
 
@@ -405,7 +411,7 @@ def attention_merge(partial: torch.Tensor, nparts: int, B: int, Lq: int, heads: 
     if out is None and want_f32:
         out = torch.empty((B * Lq, heads * 32), dtype=torch.float32, device=partial.device)
     call("petr_attention_merge", ptr(partial), nparts, ptr(out), out.stride(0) if out is not None else 0,
-         ptr(out_split), B, Lq, heads, stream_ptr(partial.device))
+         ptr(out_split), None, B, Lq, heads, stream_ptr(partial.device))
     return out if out is not None else out_split
 
 
