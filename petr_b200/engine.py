@@ -370,10 +370,18 @@ class HeadEngine:
         return out if dtype == torch.float32 else ops.add_rows_bf16(out, torch.zeros_like(out[:1]))
 
     def query_embeds(self, P) -> torch.Tensor:
+        """query_embedding(pos2posemb3d(reference_points)) (petr_head.py:422-423): a function of the parameters only, so
+        it is part of the packed state (evaluated once per weight version, like the [hi|hi|lo] weight packs; dropped with
+        them by `invalidate`).  Outside graph capture only: a tensor created while capturing belongs to that graph."""
+        if "qpos" in P:
+            return P["qpos"]
         sd = P["sd"]
         qe = ops.pos2posemb3d(P["ref"], P["dim_t_query"])
         h = ops.gemm_f32(qe, sd["query_embedding.0.weight"], sd["query_embedding.0.bias"], act=ACT_RELU)
-        return ops.gemm_f32(h, sd["query_embedding.2.weight"], sd["query_embedding.2.bias"])
+        qpos = ops.gemm_f32(h, sd["query_embedding.2.weight"], sd["query_embedding.2.bias"])
+        if not torch.cuda.is_current_stream_capturing():
+            P["qpos"] = qpos
+        return qpos
 
     # one decoder layer, fp32 path ---------------------------------------------------------
     def _self_attn(self, X, qpos, lw, B):
