@@ -614,3 +614,34 @@ def test_p2p_exchange_kernels_two_ranks_on_one_device():
                 assert flags[par * world:(par + 1) * world].tolist() == [(fwd + 1) * L + l + 1] * world
     assert int(err.item()) == 0
     assert all(int(c.sum()) == 0 for c in counters)            # the per-peer CTA counters wrapped back to zero
+
+
+@pytest.mark.parametrize("B,Lk,layers", [(3, 33, 2), (2, 160, 1), (1, 257, 6), (5, 64, 3)])
+def test_gemm_headsplit_tma_store_ragged(B, Lk, layers):
+    """Head-split outputs (out_mode 2 and the hi / lo pair of out_mode 4) leave through swizzled slabs + TMA tensor stores
+    where a warp's 32 rows are 32 consecutive keys of one sample, and through plain stores elsewhere (rows straddling a
+    sample boundary, the ragged end of M): every key count / batch combination must give the same values."""
+    g = torch.Generator().manual_seed(B * 1000 + Lk)
+    M, K, N = B * Lk, 256, 256 * layers
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) / 16).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    ref = (A.to(torch.bfloat16).double() @ W.to(torch.bfloat16).double().T + b.double()).float()
+    refh = ref.view(B, Lk, layers, 8, 32).permute(2, 0, 3, 1, 4)                  # [layer][b][head][key][32]
+    hs = ops.gemm_bf16_tc(A.to(torch.bfloat16), W.to(torch.bfloat16).contiguous(), b, headsplit_Lk=Lk)
+    assert hs.shape == (layers, B, 8, Lk, 32)
+    assert (hs.float() - refh).abs().max() <= 0.03 * max(1.0, ref.abs().max().item())
+    # fp32-class pair: hi + lo against the exact product
+    As, W3 = ops.split_rows(A), ops.x3_weight(W)
+    ref32 = (A.double() @ W.double().T + b.double()).float().view(B, Lk, layers, 8, 32).permute(2, 0, 3, 1, 4)
+    pair = ops.gemm_bf16_tc(As, W3, b, x3=True, headsplit_Lk=Lk, headsplit_pair=True)
+    assert pair.shape == (2, layers, B, 8, Lk, 32)
+    assert (pair[0].float() + pair[1].float() - ref32).abs().max() <= 6e-5 * max(1.0, ref32.abs().max().item())
+    # and with the staging switched off (plain stores everywhere): identical bits
+    _lib.set_tuning("gemm_staged", 0)
+    try:
+        hs0 = ops.gemm_bf16_tc(A.to(torch.bfloat16), W.to(torch.bfloat16).contiguous(), b, headsplit_Lk=Lk)
+        pair0 = ops.gemm_bf16_tc(As, W3, b, x3=True, headsplit_Lk=Lk, headsplit_pair=True)
+    finally:
+        _lib.set_tuning("gemm_staged", 1)
+    assert torch.equal(hs, hs0) and torch.equal(pair, pair0)
