@@ -15,6 +15,7 @@ from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID_GATE
 
 NUM_SMS = 148
 DEDUP_SINE = True                # evaluate the batch-invariant sine/adapt embedding once per forward
+CACHE_CONST_SINE = True          # no padded key anywhere: the sine / adapt embedding is a constant of (N, H, W) and the weights
 FOLD_KV_BIAS = True              # drop the K bias (softmax-invariant), fold the V bias into the out-projection bias
 DEDUP_LAYER0 = True              # layer 0's self-attention block sees X = 0 for every sample: evaluate it for one
 FUSED_POSITION_MLP = True        # False: unfused frustum kernel + two GEMMs (kept for A/B tests)
@@ -148,18 +149,29 @@ def key_side_tc(eng, x, mi: MetaInputs, taps=None, views: slice = None):
     # sample of the batch has the same img_shape list (all shipped configs: no padding at all) the
     # masks are identical per sample, so the (Lk, 256) result is evaluated once per forward for one
     # sample and broadcast over the batch instead of B times.
-    dedup = DEDUP_SINE and mi.uniform_masks and B > 1
+    dedup = DEDUP_SINE and mi.uniform_masks
     m_sine = masks_all[:1] if dedup else masks_all
     raw_pos = not s.with_position and not s.with_multiview      # petr_head.py:414-420: encoding used as is
-    sf = eng.pos_features(P, m_sine, torch.float32 if raw_pos else torch.bfloat16)
-    if views is not None:
-        sf = sf.view(m_sine.shape[0], N_all, H * W, -1)[:, views].reshape(m_sine.shape[0] * Lk, -1).contiguous()
-    if raw_pos:
-        h2, sin1 = None, sf                                                              # (Lk | B*Lk, E) fp32
-        dedup = True                                     # add_rows_bf16 below takes either period
+    # With no padded key at all (every shipped config: final_dim divisible by 32, img_shape == pad_shape; known on the
+    # host) the encoding is a constant of (N, H, W) and the adapt_pos3d weights: SURVEY 8a3 "cache per (N,H,W)".  It then
+    # lives in the packed state (dropped with the weights); tensors made during graph capture are not kept.
+    ckey = ("sine_const", N_all, H, W, None if views is None else (views.start, views.stop), raw_pos)
+    const = CACHE_CONST_SINE and dedup and not has_mask
+    if const and ckey in T:
+        h2, sin1 = None, T[ckey]
     else:
-        h2 = ops.gemm_bf16_tc(sf, T["ad_w1"], P["ad_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_adapt1")
-        sin1 = ops.gemm_bf16_tc(h2, T["ad_w2"], P["ad_b2"], name="gemm_adapt2") if dedup else None   # (Lk, E) fp32
+        sf = eng.pos_features(P, m_sine, torch.float32 if raw_pos else torch.bfloat16)
+        if views is not None:
+            sf = sf.view(m_sine.shape[0], N_all, H * W, -1)[:, views].reshape(m_sine.shape[0] * Lk, -1).contiguous()
+        if raw_pos:
+            h2, sin1 = None, sf                                                          # (Lk | B*Lk, E) fp32
+        else:
+            h2 = ops.gemm_bf16_tc(sf, T["ad_w1"], P["ad_b1"], act=ACT_RELU, out_dtype=torch.bfloat16, name="gemm_adapt1")
+            sin1 = ops.gemm_bf16_tc(h2, T["ad_w2"], P["ad_b2"], name="gemm_adapt2") if dedup else None   # (Lk, E) fp32
+        if const and sin1 is not None and not torch.cuda.is_current_stream_capturing():
+            T[ckey] = sin1
+    if raw_pos:
+        dedup = True                                     # add_rows_bf16 below takes either period
     fused = s.with_position and FUSED_POSITION_MLP and s.D == 64 and tuple(T["pe_w1"].shape) == (1024, 192) and \
         tuple(T["pe_w2"].shape) == (256, 1024)
     # input_proj (petr_head.py:390): fp32 NCHW -> bf16 tokens -> tcgen05 GEMM.  One accumulator, two results
