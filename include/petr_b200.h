@@ -149,11 +149,13 @@ int petr_layernorm_f32(const float* X, const float* gamma, const float* beta, fl
  * query+query_pos of petr_transformer.py:341); Z = LN2(Y) with nan_to_num (the decoder's
  * post_norm on a copy, petr_transformer.py:444 + petr_head.py:435) as fp32 and/or split bf16.
  * relu != 0 applies ReLU to Y (cls_branches, petr_head.py:226-231).  Every pointer must be 16-byte
- * aligned (one warp per row, 16-byte loads and stores). */
+ * aligned (one warp per row, 16-byte loads and stores).  nparts > 1: X is the sum of nparts arrays part_stride floats
+ * apart -- the split-K partial products of the preceding petr_gemm_bf16_tc (ksplit), added in a fixed order. */
 int petr_layernorm_multi_f32(const float* X, const float* gamma, const float* beta, float eps,
                              const float* qpos, int qpos_rows, float* Y, void* Y_split,
                              void* Ypos_split, const float* gamma2, const float* beta2,
-                             float* Z, void* Z_split, int rows, int E, int relu, void* stream);
+                             float* Z, void* Z_split, int rows, int E, int relu, int nparts,
+                             int64_t part_stride, void* stream);
 
 /* fp32 rows -> bf16 [hi | lo] rows of width 2*E: split(relu?(X + add[row % add_rows])). */
 int petr_split_rows_bf16(const float* X, int ldx, const float* add, int add_rows, void* out,
@@ -220,11 +222,14 @@ int petr_nchw_to_tokens_bf16(const void* x, int in_dtype, void* out, int G, int 
  * sigmoid(acc + bias) by gate[m*ldc + n] (fp32) before the residual: the PETRv2 SELayer
  * (petrv2_head.py:48-60) as a GEMM epilogue.  Used for the K/V projection of all
  * decoder layers in one launch (petr_transformer.py:341-344,:357-360), the position_encoder /
- * adapt_pos3d MLPs, input_proj and the query-side projections / FFN. */
+ * adapt_pos3d MLPs, input_proj and the query-side projections / FFN.
+ * ksplit > 1 (out_mode 0 only): split-K for GEMMs with few output tiles (M = B * 900 rows at small batch leave most SMs
+ * idle): part s of the K range writes its partial product to C + s * M * ldc (bias and residual go into part 0);
+ * the consumer (petr_layernorm_multi_f32 nparts) adds the parts in a fixed order, so results stay deterministic. */
 int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const void* W, int ldw,
                       const float* bias, const float* residual, const float* gate, int act, float alpha,
                       void* C, void* C2, int ldc, int out_mode, int M, int N, int K,
-                      int kv_Lk, void* stream);
+                      int kv_Lk, int ksplit, void* stream);
 
 /* 3xTF32 GEMM on tcgen05 (kind::tf32; same persistent kernel, fp32 operands): the fp32-PARITY path of the 1x1-conv
  * MLPs (petr_head.py:332 position_encoder, :249-254 adapt_pos3d) and the fp32 K / V projections on the tensor cores.

@@ -34,13 +34,13 @@ SIGNATURES = {
     "petr_gemm_f32": (c_int, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
     "petr_attention_f32": (c_int, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _P, _I, _P, _P, _F, c_uint64, _P, _I,
                                    _I, _I, _I, _I, _I, _F, _P]),
-    "petr_layernorm_multi_f32": (c_int, [_P, _P, _P, _F, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "petr_layernorm_multi_f32": (c_int, [_P, _P, _P, _F, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, c_int64, _P]),
     "petr_split_rows_bf16": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
     "petr_nchw_to_tokens_bf16": (c_int, [_P, _I, _P, _I, _I, _I, _P]),
     "petr_layernorm_f32": (c_int, [_P, _P, _P, _P, _I, _I, _F, _I, _I, _P]),
     "petr_nms_free_decode": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P]),
     "petr_decode_boxes": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "petr_gemm_bf16_tc": (c_int, [_P, _I, _I, _P, _I, _P, _P, _P, _I, _F, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "petr_gemm_bf16_tc": (c_int, [_P, _I, _I, _P, _I, _P, _P, _P, _I, _F, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "petr_gemm_tf32x3_tc": (c_int, [_P, _I, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "petr_split_rows_tf32": (c_int, [_P, _I, _P, _I, _P, _I, _I, _P]),
     "petr_position_mlp_fused": (c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P,

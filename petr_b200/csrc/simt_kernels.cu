@@ -567,6 +567,7 @@ struct LnMultiParams {
     float* Y; __nv_bfloat16* Y_split; __nv_bfloat16* Ypos_split;
     const float* gamma2; const float* beta2; float* Z; __nv_bfloat16* Z_split;
     int rows; int relu;
+    int nparts; int64_t part_stride;     // X = sum of nparts arrays (split-K partial products of the preceding GEMM)
 };
 
 __device__ __forceinline__ void store_split_elem(__nv_bfloat16* base, int E, int c, float v) {
@@ -609,6 +610,12 @@ layernorm_multi_kernel(LnMultiParams p) {
     const int c0 = lane * PER;
     float v[PER], y[PER], g[PER], bt[PER];
     load8(p.X + (int64_t)row * E + c0, v);
+    for (int pt = 1; pt < p.nparts; ++pt) {            // fixed order: deterministic
+        float w[PER];
+        load8(p.X + pt * p.part_stride + (int64_t)row * E + c0, w);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) v[i] += w[i];
+    }
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < PER; ++i) s += v[i];
@@ -954,8 +961,11 @@ extern "C" int petr_decode_boxes(float* reg, const float* ref, const float* h_pc
 extern "C" int petr_layernorm_multi_f32(const float* X, const float* gamma, const float* beta, float eps,
                                         const float* qpos, int qpos_rows, float* Y, void* Y_split,
                                         void* Ypos_split, const float* gamma2, const float* beta2,
-                                        float* Z, void* Z_split, int rows, int E, int relu, void* stream) {
+                                        float* Z, void* Z_split, int rows, int E, int relu, int nparts,
+                                        int64_t part_stride, void* stream) {
     PETR_REQUIRE(X && gamma && beta, PETR_E_BADARG, "petr_layernorm_multi_f32: null pointer");
+    PETR_REQUIRE(nparts <= 1 || (part_stride > 0 && (part_stride % 4) == 0), PETR_E_BADARG,
+                 "petr_layernorm_multi_f32: nparts > 1 needs a part_stride that is a multiple of 4 floats");
     PETR_REQUIRE(rows > 0, PETR_E_BADARG, "petr_layernorm_multi_f32: bad dimension");
     PETR_REQUIRE(E == 256, PETR_E_SHAPE, "petr_layernorm_multi_f32: E must be 256, got %d", E);
     if (Ypos_split) PETR_REQUIRE(qpos && qpos_rows > 0, PETR_E_BADARG, "petr_layernorm_multi_f32: qpos required");
@@ -966,7 +976,7 @@ extern "C" int petr_layernorm_multi_f32(const float* X, const float* gamma, cons
                  "petr_layernorm_multi_f32: every pointer must be 16-byte aligned");
     LnMultiParams p{X, gamma, beta, eps, qpos, qpos_rows, Y, (__nv_bfloat16*)Y_split,
                     (__nv_bfloat16*)Ypos_split, (Z || Z_split) ? gamma2 : nullptr, beta2, Z,
-                    (__nv_bfloat16*)Z_split, rows, relu};
+                    (__nv_bfloat16*)Z_split, rows, relu, nparts < 1 ? 1 : nparts, part_stride};
     layernorm_multi_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p);
     return after_launch("petr_layernorm_multi_f32");
 }

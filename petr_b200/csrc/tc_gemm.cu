@@ -71,6 +71,7 @@ struct EpiParams {
     int tiles_m, tiles_n, band;
     long long* trace;  // diagnostic clock64 stamps of CTA 0 (petr_debug_set_trace), normally null
     int coalesce;      // transposing (coalesced) epilogue allowed: 16-byte aligned bases, ldc % 4 == 0, N % 4 == 0
+    int ksplit;        // out_mode 0: split-K parts (part s writes C + s * M * ldc; bias / residual in part 0)
     int tma_out;       // out_modes 3 / 4: split halves leave through swizzled slabs + TMA tensor stores (tmC / tmD)
     int dbg;           // diagnostic (petr_set_tuning gemm_debug): 1 = out_mode 2 skips its global stores
     int staged;        // out_mode 2: stage each warp's 32 x 32 bf16 chunk in smem and write it with one bulk copy
@@ -150,7 +151,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // loops (descriptors, barrier addresses) in uniform registers instead of R2UR / ELECT loops per instruction
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int num_k = p.K / BKE;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int ksplit = (OM == 0) ? p.ksplit : 1;
+    const int num_tiles = p.tiles_m * p.tiles_n * ksplit;        // tile index = (output tile) * ksplit + K part
     const TileMap tmap_{p.tiles_m, p.tiles_n, p.band};
 
     if (warp == 0 && lane == 0) {
@@ -178,14 +180,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t ttile = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ttile) {
             int mt, nt;
-            tmap_(tile, mt, nt);
+            const int ks = tile % ksplit;
+            tmap_(tile / ksplit, mt, nt);
             const int m0 = mt * BM, n0 = nt * BN;
-            for (int kb = 0; kb < num_k; ++kb, ++it) {
+            const int kb_begin = (int)((int64_t)num_k * ks / ksplit), kb_end = (int)((int64_t)num_k * (ks + 1) / ksplit);
+            for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
                 const int s = it % NST;
                 const uint32_t ph = (it / NST) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 if (leader) {
-                    if (kb < 4) GEMM_TR(0, ttile, kb);
+                    if (kb - kb_begin < 4) GEMM_TR(0, ttile, kb - kb_begin);
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                     uint8_t* a = smem + s * STAGE_BYTES;
                     int ka = kb * BKE;
@@ -207,18 +211,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tcgen05_fence_after();
             if (leader) GEMM_TR(1, tcount, 0);
             const uint32_t d = tmem_base + buf * BN;
-            for (int kb = 0; kb < num_k; ++kb, ++it) {
+            const int ks = tile % ksplit;
+            const int kb_begin = (int)((int64_t)num_k * ks / ksplit), kb_end = (int)((int64_t)num_k * (ks + 1) / ksplit);
+            for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
                 const int s = it % NST;
                 mbar_wait(&full_bar[s], (it / NST) & 1);
                 tcgen05_fence_after();
                 if (leader) {
-                    if (kb < 4) GEMM_TR(1, tcount, 1 + kb);
+                    if (kb - kb_begin < 4) GEMM_TR(1, tcount, 1 + kb - kb_begin);
                     const uint64_t ad = desc0 + (uint64_t)((s * STAGE_BYTES) >> 4);
                     const uint64_t bd = ad + (uint64_t)(TILE_A_BYTES >> 4);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {          // 32 bytes of K per MMA: 16 bf16 or 8 tf32
-                        if constexpr (TF32) umma_tf32_ss(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-                        else umma_f16_ss(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                        if constexpr (TF32) umma_tf32_ss(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
+                        else umma_f16_ss(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[s]);                  // smem stage free when these retire
                 }
@@ -242,13 +248,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t sbias_u32 = smem_u32(sbias);
         if (p.bias && (int)blockIdx.x < num_tiles) {
             int mt, nt;
-            tmap_((int)blockIdx.x, mt, nt);
+            tmap_((int)blockIdx.x / ksplit, mt, nt);
             const int n0 = nt * BN;
             sbias[et] = (n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
         }
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             int mt, nt;
-            tmap_(tile, mt, nt);
+            const int ks = tile % ksplit;                            // split-K part (out_mode 0): bias / residual in part 0
+            tmap_(tile / ksplit, mt, nt);
             const int m0 = mt * BM, n0 = nt * BN;
             const uint32_t buf = tcount & 1;
             const int m = m0 + row;
@@ -259,7 +266,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int ntile = tile + gridDim.x;
                 if (ntile < num_tiles) {
                     int mt2, nt2;
-                    tmap_(ntile, mt2, nt2);
+                    tmap_(ntile / ksplit, mt2, nt2);
                     const int nn = nt2 * BN + et;
                     if (nn < p.N) next_bias = __ldg(p.bias + nn);
                 }
@@ -296,7 +303,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // that its L2 latency overlaps the accumulator load and the bias / activation math
                 float4 res4[8];
                 const bool coal = p.coalesce && (n0 + c * 32 + 32 <= p.N) && OM != 2;
-                if (coal && p.residual) {
+                const bool use_res = p.residual && ks == 0;
+                if (coal && use_res) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int mr = m0 + quarter * 32 + (q & 3) * 8 + (lane >> 2);
@@ -316,7 +324,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (p.bias) {
+                if (p.bias && ks == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 t = ld_shared_f32x4(sb + (c * 32 + j) * 4);
@@ -406,12 +414,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gate + (int64_t)mr * p.ldc + col));
                                 x.x *= g4.x; x.y *= g4.y; x.z *= g4.z; x.w *= g4.w;
                             }
-                            if (p.residual) {
+                            if (use_res) {
                                 const float4 q4 = res4[hh * 4 + i];
                                 x.x += q4.x; x.y += q4.y; x.z += q4.z; x.w += q4.w;
                             }
                             if (OM == 0 || OM == 7) {
-                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (int64_t)mr * p.ldc + col) = x;
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (int64_t)ks * p.M * p.ldc +
+                                                           (int64_t)mr * p.ldc + col) = x;
                             } else if (OM == 6) {                             // fp32 [hi | lo] tf32 split rows
                                 float4 hi4, lo4;
                                 hi4.x = tf32_rna(x.x); hi4.y = tf32_rna(x.y); hi4.z = tf32_rna(x.z); hi4.w = tf32_rna(x.w);
@@ -448,7 +457,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 32; ++j) if (nb + j < p.N) v[j] *= gp[j];
                 }
-                if (p.residual) {
+                if (use_res) {
                     const float* rp = p.residual + (int64_t)m * p.ldc + nb;
                     if (full && ((p.ldc & 3) == 0)) {
 #pragma unroll
@@ -468,7 +477,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (nb + j < p.N) { const float h = tf32_rna(v[j]); cp[j] = h; cp[p.N + j] = v[j] - h; }
                 }
                 if (OM == 0 || OM == 7 || (OM == 3 && p.C2)) {
-                    float* cp = reinterpret_cast<float*>(OM == 3 ? p.C2 : p.C) + (int64_t)m * p.ldc + nb;
+                    float* cp = reinterpret_cast<float*>(OM == 3 ? p.C2 : p.C) + (OM == 0 ? (int64_t)ks * p.M * p.ldc : 0) +
+                                (int64_t)m * p.ldc + nb;
                     if (full && ((p.ldc & 3) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -647,6 +657,7 @@ extern "C" int petr_gemm_tf32x3_tc(const float* A, int lda, int a_k_wrap, const 
     p.M = M; p.N = N; p.K = K; p.a_k_wrap = a_k_wrap; p.kv_E = 256;
     p.trace = nullptr;
     p.coalesce = 1;
+    p.ksplit = 1;
     CUtensorMap tmA, tmB;
     uint64_t dA[2] = {(uint64_t)a_k_wrap, (uint64_t)M}, sA[1] = {(uint64_t)lda * 4};
     uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)ldw * 4};
@@ -687,7 +698,7 @@ extern "C" int petr_nchw_to_tokens_bf16(const void* x, int in_dtype, void* out, 
 extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const void* W, int ldw,
                                  const float* bias, const float* residual, const float* gate, int act, float alpha,
                                  void* C, void* C2, int ldc, int out_mode, int M, int N, int K,
-                                 int kv_Lk, void* stream) {
+                                 int kv_Lk, int ksplit, void* stream) {
     PETR_REQUIRE(A && W && C, PETR_E_BADARG, "petr_gemm_bf16_tc: null pointer");
     PETR_REQUIRE(M > 0 && N > 0 && K > 0, PETR_E_BADARG, "petr_gemm_bf16_tc: bad dimension");
     PETR_REQUIRE(K % BK == 0, PETR_E_SHAPE, "petr_gemm_bf16_tc: K must be a multiple of 64, got %d", K);
@@ -709,6 +720,10 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     p.M = M; p.N = N; p.K = K; p.a_k_wrap = a_k_wrap;
     p.staged = (out_mode == 2 && tuning::gemm_staged()) ? 1 : 0;
     p.dbg = tuning::gemm_debug();
+    if (ksplit < 1) ksplit = 1;
+    PETR_REQUIRE(ksplit == 1 || (out_mode == 0 && !gate && ksplit <= K / BK), PETR_E_BADARG,
+                 "petr_gemm_bf16_tc: ksplit > 1 needs out_mode 0 without a gate and at most K / 64 parts");
+    p.ksplit = ksplit;
     p.trace = (long long*)tuning::debug_trace();
     p.coalesce = (tuning::gemm_coalesce() && aligned16(C) && (!C2 || aligned16(C2)) && (!residual || aligned16(residual)) &&
                   (N % 4) == 0 && ((out_mode == 4) || (ldc % 4) == 0)) ? 1 : 0;
@@ -770,7 +785,7 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int tiles = p.tiles_m * p.tiles_n;
+    int tiles = p.tiles_m * p.tiles_n * ksplit;
     int grid = tiles < sms ? tiles : sms;
     p.band = (out_mode == 2 && p.tiles_n > 1 && tuning::gemm_band()) ? grid : 0;      // measured slower (0.509 vs 0.466 ms): off by default
     fn<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, tmC, tmD, p);

@@ -16,6 +16,7 @@ from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID_GATE
 NUM_SMS = 148
 DEDUP_SINE = True                # evaluate the batch-invariant sine/adapt embedding once per forward
 CACHE_CONST_SINE = True          # no padded key anywhere: the sine / adapt embedding is a constant of (N, H, W) and the weights
+SPLIT_K_SMALL_M = False          # split-K for the query-side residual GEMMs when B * 900 rows leave most SMs idle
 FOLD_KV_BIAS = True              # drop the K bias (softmax-invariant), fold the V bias into the out-projection bias
 DEDUP_LAYER0 = True              # layer 0's self-attention block sees X = 0 for every sample: evaluate it for one
 FUSED_POSITION_MLP = True        # False: unfused frustum kernel + two GEMMs (kept for A/B tests)
@@ -38,6 +39,16 @@ def choose_nsplit(B: int, heads: int, Lq: int, Lk: int) -> int:
         if eff > best_eff + 0.03:
             best, best_eff = ns, eff
     return best
+
+
+def choose_ksplit(rows: int, k_blocks: int) -> int:
+    """Split-K parts for a query-side GEMM with a 256-wide output (one column of 128-row tiles): at small batch the
+    B * 900 rows are a handful of tiles (8 at B = 1) and most SMs idle while each tile walks its whole K range.  The
+    parts are summed by the LayerNorm that follows (fixed order: deterministic)."""
+    tiles = (rows + 127) // 128
+    if not SPLIT_K_SMALL_M or tiles * 2 > NUM_SMS:
+        return 1
+    return max(1, min(NUM_SMS // tiles, k_blocks // 4, 8))
 
 
 def packed_tc(eng, device) -> dict:
@@ -267,10 +278,11 @@ def decoder_layer_tc(eng, P, l: int, st: dict, qpos, ks: dict, last: bool) -> di
           name="gemm_q_side")
     ops.attention_x3_tc(qk[:, 0], qk[:, 1], v[:, 0], None, n1, s.Lq, s.Lq, s.heads, out_split=o_s[:r1],
                         want_f32=False)
-    y = g(o_s[:r1], tw["sa_out"], lw["sa_out_b"], residual=st["X"][:r1], x3=True, name="gemm_q_side")
-    X1 = torch.empty_like(y)
+    kp = choose_ksplit(r1, 3 * E // 64)
+    y = g(o_s[:r1], tw["sa_out"], lw["sa_out_b"], residual=st["X"][:r1], x3=True, ksplit=kp, name="gemm_q_side")
+    X1 = torch.empty((r1, E), dtype=torch.float32, device=dev)
     X1ps = torch.empty((r1, 2 * E), dtype=torch.bfloat16, device=dev)
-    ops.layernorm_multi(y, *lw["ln"][0], qpos=qpos, Y=X1, Ypos_split=X1ps)
+    ops.layernorm_multi(y, *lw["ln"][0], qpos=qpos, Y=X1, Ypos_split=X1ps, nparts=kp)
     # ---- cross-attention (PETRMultiheadAttention) ----
     qs = g(X1ps, tw["ca_q"], tw["ca_q_b"], x3=True, alpha=Q_SCALE, headsplit_Lk=s.Lq, name="gemm_q_side")
     if n1 != B:
@@ -282,19 +294,21 @@ def decoder_layer_tc(eng, P, l: int, st: dict, qpos, ks: dict, last: bool) -> di
         ops.cross_attention_bf16(qs[0], ks["Kh"][l], ks["Vh"][l], ks["kmask"], B, s.Lq, ks["Lk"], s.heads,
                                  ks["nsplit"], partial=ks["partial"], out_split=o_s, want_f32=False,
                                  workspace=ks["att_ws"])
-    y = g(o_s, tw["ca_out"], tw["ca_out_b"], residual=X1, x3=True, name="gemm_q_side")
-    X2 = torch.empty_like(y)
+    kp = choose_ksplit(R, 3 * E // 64)
+    y = g(o_s, tw["ca_out"], tw["ca_out_b"], residual=X1, x3=True, ksplit=kp, name="gemm_q_side")
+    X2 = torch.empty((R, E), dtype=torch.float32, device=dev)
     X2s = torch.empty((R, 2 * E), dtype=torch.bfloat16, device=dev)
-    ops.layernorm_multi(y, *lw["ln"][1], Y=X2, Y_split=X2s)
+    ops.layernorm_multi(y, *lw["ln"][1], Y=X2, Y_split=X2s, nparts=kp)
     # ---- FFN ----
     hs = g(X2s, tw["f1"], lw["f1_b"], act=ACT_RELU, x3=True, split_out=True, name="gemm_q_side")
-    y = g(hs, tw["f2"], lw["f2_b"], residual=X2, x3=True, name="gemm_q_side")
-    X3 = torch.empty_like(y)
+    kp = choose_ksplit(R, 3 * hs.shape[1] // 2 // 64)
+    y = g(hs, tw["f2"], lw["f2_b"], residual=X2, x3=True, ksplit=kp, name="gemm_q_side")
+    X3 = torch.empty((R, E), dtype=torch.float32, device=dev)
     X3s = torch.empty((R, 2 * E), dtype=torch.bfloat16, device=dev)
     X3ps = None if last else torch.empty((R, 2 * E), dtype=torch.bfloat16, device=dev)
     ops.layernorm_multi(y, *lw["ln"][2], qpos=None if last else qpos, Y=X3, Y_split=X3s, Ypos_split=X3ps,
                         gamma2=P["post_norm"][0], beta2=P["post_norm"][1], Z=st["outs"][l],
-                        Z_split=st["outs_split"][l])
+                        Z_split=st["outs_split"][l], nparts=kp)
     return dict(X=X3, Xs=X3s, Xps=X3ps, outs=st["outs"], outs_split=st["outs_split"])
 
 

@@ -161,14 +161,16 @@ def attention_f32(Q, K, V, key_mask, B: int, Lq: int, Lk: int, heads: int, out=N
 
 
 def layernorm_multi(X, gamma, beta, *, eps=1e-5, qpos=None, Y=None, Y_split=None, Ypos_split=None,
-                    gamma2=None, beta2=None, Z=None, Z_split=None, relu=False):
-    """Fused LayerNorm with optional fp32 / split-bf16 / (+qpos) / second-LN outputs (E = 256)."""
+                    gamma2=None, beta2=None, Z=None, Z_split=None, relu=False, nparts: int = 1):
+    """Fused LayerNorm with optional fp32 / split-bf16 / (+qpos) / second-LN outputs (E = 256).
+    nparts > 1: X is (nparts, rows, 256), the split-K parts of the preceding GEMM, summed on load."""
     _cuda(X, "X")
     assert X.is_contiguous() and X.shape[-1] == 256
-    rows = X.numel() // 256
+    rows = X.numel() // 256 // nparts
     call("petr_layernorm_multi_f32", ptr(X), ptr(gamma), ptr(beta), float(eps), ptr(qpos),
          qpos.shape[0] if qpos is not None else 0, ptr(Y), ptr(Y_split), ptr(Ypos_split),
-         ptr(gamma2), ptr(beta2), ptr(Z), ptr(Z_split), rows, 256, int(relu), stream_ptr(X.device))
+         ptr(gamma2), ptr(beta2), ptr(Z), ptr(Z_split), rows, 256, int(relu), int(nparts), rows * 256,
+         stream_ptr(X.device))
 
 
 def split_rows(X, add=None, relu=False, out=None) -> torch.Tensor:
@@ -238,7 +240,7 @@ OUT_SPLIT = 3
 def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, gate=None, act=ACT_NONE,
                  alpha: float = 1.0, out=None, out_dtype=torch.float32, headsplit_Lk: int = 0,
                  split_out: bool = False, out_f32=None, x3: bool = False, headsplit_pair: bool = False,
-                 residual_period: int = 0, name: str = "gemm_bf16_tc"):
+                 residual_period: int = 0, ksplit: int = 1, name: str = "gemm_bf16_tc"):
     """C = alpha * act(A @ W.T + bias) (+ residual) on tcgen05; A (M,Ka) bf16, W (N,K) bf16.
     x3: A is a split (M, 2*K0) [hi | lo] activation and W an x3_weight (N, 3*K0).
     headsplit_Lk > 0: bf16 output in the [N/256][B][8][Lk][32] Q/K/V layout.
@@ -262,7 +264,7 @@ def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, 
             out = torch.empty((M, N), dtype=torch.bfloat16, device=A.device)
         with _Timed(name):
             call("petr_gemm_bf16_tc", ptr(A), A.stride(0), wrap, ptr(W), W.stride(0), ptr(bias), ptr(residual), None,
-                 act, float(alpha), ptr(out), ptr(out_f32), out_f32.stride(0), 5, M, N, K, int(residual_period),
+                 act, float(alpha), ptr(out), ptr(out_f32), out_f32.stride(0), 5, M, N, K, int(residual_period), 1,
                  stream_ptr(A.device))
         return out
     if headsplit_Lk > 0 and headsplit_pair:
@@ -285,15 +287,17 @@ def gemm_bf16_tc(A: torch.Tensor, W: torch.Tensor, bias=None, *, residual=None, 
         ldc = C2.stride(0) if C2 is not None else (residual.stride(0) if residual is not None else N)
     else:
         if out is None:
-            out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+            shape = (M, N) if ksplit <= 1 else (ksplit, M, N)         # split-K: one partial product per part
+            out = torch.empty(shape, dtype=out_dtype, device=A.device)
         mode = OUT_F32 if out.dtype == torch.float32 else OUT_BF16
-        ldc = out.stride(0)
+        ldc = out.stride(-2)
+        assert ksplit <= 1 or (mode == OUT_F32 and gate is None and out.is_contiguous())
     for t in (residual, gate):
         if t is not None:
             assert t.dtype == torch.float32 and t.stride(0) == ldc and t.stride(1) == 1
     with _Timed(name):
         call("petr_gemm_bf16_tc", ptr(A), A.stride(0), wrap, ptr(W), W.stride(0), ptr(bias), ptr(residual), ptr(gate),
-             act, float(alpha), ptr(out), ptr(C2), ldc, mode, M, N, K, int(headsplit_Lk),
+             act, float(alpha), ptr(out), ptr(C2), ldc, mode, M, N, K, int(headsplit_Lk), int(max(1, ksplit)),
              stream_ptr(A.device))
     return out
 

@@ -645,3 +645,25 @@ def test_gemm_headsplit_tma_store_ragged(B, Lk, layers):
     finally:
         _lib.set_tuning("gemm_staged", 1)
     assert torch.equal(hs, hs0) and torch.equal(pair, pair0)
+
+
+@pytest.mark.parametrize("M,K0,ksplit", [(900, 256, 3), (900, 2048, 8), (1800, 2048, 5), (130, 256, 2)])
+def test_gemm_split_k_parts_sum_to_the_product(M, K0, ksplit):
+    """Split-K (small-M query-side GEMMs): the parts written by petr_gemm_bf16_tc(ksplit) summed by
+    petr_layernorm_multi_f32(nparts) give the LayerNorm of the unsplit product; deterministic."""
+    g = torch.Generator().manual_seed(M + K0 + ksplit)
+    A = torch.randn(M, K0, generator=g).to(DEV)
+    W = (torch.randn(256, K0, generator=g) / math.sqrt(K0)).to(DEV)
+    b, res = torch.randn(256, generator=g).to(DEV), torch.randn(M, 256, generator=g).to(DEV)
+    gam, bet = torch.randn(256, generator=g).to(DEV), torch.randn(256, generator=g).to(DEV)
+    As, W3 = ops.split_rows(A), ops.x3_weight(W)
+    full = ops.gemm_bf16_tc(As, W3, b, residual=res, x3=True)
+    parts = ops.gemm_bf16_tc(As, W3, b, residual=res, x3=True, ksplit=ksplit)
+    assert parts.shape == (ksplit, M, 256)
+    assert (parts.sum(0) - full).abs().max() <= 2e-5 * full.abs().max()
+    Y0, Y1, Y2 = (torch.empty(M, 256, device=DEV) for _ in range(3))
+    ops.layernorm_multi(full, gam, bet, Y=Y0)
+    ops.layernorm_multi(parts, gam, bet, Y=Y1, nparts=ksplit)
+    ops.layernorm_multi(ops.gemm_bf16_tc(As, W3, b, residual=res, x3=True, ksplit=ksplit), gam, bet, Y=Y2, nparts=ksplit)
+    assert (Y1 - Y0).abs().max() <= 2e-5 * max(1.0, Y0.abs().max().item())
+    assert torch.equal(Y1, Y2)
