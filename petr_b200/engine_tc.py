@@ -16,7 +16,7 @@ from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID_GATE
 NUM_SMS = 148
 DEDUP_SINE = True                # evaluate the batch-invariant sine/adapt embedding once per forward
 CACHE_CONST_SINE = True          # no padded key anywhere: the sine / adapt embedding is a constant of (N, H, W) and the weights
-SPLIT_K_SMALL_M = False          # split-K for the query-side residual GEMMs when B * 900 rows leave most SMs idle
+SPLIT_K_SMALL_M = True           # split-K for the query-side residual GEMMs when B * 900 rows leave most SMs idle
 FOLD_KV_BIAS = True              # drop the K bias (softmax-invariant), fold the V bias into the out-projection bias
 DEDUP_LAYER0 = True              # layer 0's self-attention block sees X = 0 for every sample: evaluate it for one
 FUSED_POSITION_MLP = True        # False: unfused frustum kernel + two GEMMs (kept for A/B tests)
