@@ -62,7 +62,10 @@ void petr_launch_count_reset(void);
  * the fast pass), "gemm_staged" / "gemm_coalesce" / "gemm_skinny" / "gemm_band" (0/1: epilogue and tile-order variants of
  * petr_gemm_bf16_tc), "gemm_debug" (diagnostic, 0 = off: 1 = out_mode 2 skips its global stores, 2 = every epilogue
  * reduced to its TMEM loads -- the MMA-bound floor that tools/kproj_store_bound.py and tools/qside_epilogue_floor.py
- * measure; results are then garbage by design).  Returns 0, or PETR_E_BADARG for an unknown key / out-of-range value;
+ * measure; results are then garbage by design), "pdl" (0/1, default 0: launch the GEMM, LayerNorm, attention and merge
+ * kernels with programmatic stream serialization -- griddepcontrol.wait inside the kernels orders the data -- so that a
+ * kernel's launch and prologue overlap its predecessor's tail; measured SLOWER inside the captured graph, 1.324 vs
+ * 1.287 ms at B = 1 and 15.22 vs 15.09 ms at B = 32, hence off).  Returns 0, or PETR_E_BADARG for an unknown key / out-of-range value;
  * petr_get_tuning returns the current value or -1. */
 int petr_set_tuning(const char* key, int value);
 int petr_get_tuning(const char* key);

@@ -20,12 +20,14 @@ static std::atomic<int> g_gemm_coalesce{1};
 static std::atomic<int> g_gemm_skinny{1};
 static std::atomic<int> g_gemm_band{0};
 static std::atomic<int> g_gemm_debug{0};
+static std::atomic<int> g_pdl{0};
 bool flash_exact_only() { return g_flash_exact_only.load(std::memory_order_relaxed) != 0; }
 int flash_poly() { return g_flash_poly.load(std::memory_order_relaxed); }
 static std::atomic<void*> g_debug_trace{nullptr};
 void* debug_trace() { return g_debug_trace.load(std::memory_order_relaxed); }
 bool gemm_band() { return g_gemm_band.load(std::memory_order_relaxed) != 0; }
 int gemm_debug() { return g_gemm_debug.load(std::memory_order_relaxed); }
+bool pdl() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 bool gemm_skinny() { return g_gemm_skinny.load(std::memory_order_relaxed) != 0; }
 bool gemm_coalesce() { return g_gemm_coalesce.load(std::memory_order_relaxed) != 0; }
 bool gemm_staged() { return g_gemm_staged.load(std::memory_order_relaxed) != 0; }
@@ -38,6 +40,7 @@ static const Entry kEntries[] = {
     {"gemm_skinny", &g_gemm_skinny, 0, 1},
     {"gemm_band", &g_gemm_band, 0, 1},
     {"gemm_debug", &g_gemm_debug, 0, 3},
+    {"pdl", &g_pdl, 0, 1},
 };
 }  // namespace tuning
 }  // namespace petr

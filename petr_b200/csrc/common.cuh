@@ -31,6 +31,7 @@ inline int after_launch(const char* what) {
 
 // process-wide tuning switches behind petr_set_tuning (capi.cu)
 namespace tuning {
+bool pdl();
 bool flash_exact_only();
 int flash_poly();
 bool gemm_staged();
@@ -63,6 +64,30 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
     return d;
 }
 
+
+// Programmatic dependent launch (the query side is ~100 short kernels in one stream: at B = 1 a GEMM is one wave of 8
+// tiles).  A kernel launched through launch_pdl may be scheduled while its predecessor drains; pdl_wait() -- placed before
+// the first access to anything a predecessor wrote or still reads -- blocks until the predecessor has completed and its
+// memory is visible; pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as resources free up.
+// Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = tuning::pdl() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #define PETR_REQUIRE(cond, code, ...) \
     do { if (!(cond)) return ::petr::fail((code), __VA_ARGS__); } while (0)

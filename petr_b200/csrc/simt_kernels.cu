@@ -606,6 +606,8 @@ __global__ void __launch_bounds__(256)
 layernorm_multi_kernel(LnMultiParams p) {
     constexpr int PER = 8, E = 256;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     if (row >= p.rows) return;
     const int c0 = lane * PER;
     float v[PER], y[PER], g[PER], bt[PER];
@@ -977,7 +979,8 @@ extern "C" int petr_layernorm_multi_f32(const float* X, const float* gamma, cons
     LnMultiParams p{X, gamma, beta, eps, qpos, qpos_rows, Y, (__nv_bfloat16*)Y_split,
                     (__nv_bfloat16*)Ypos_split, (Z || Z_split) ? gamma2 : nullptr, beta2, Z,
                     (__nv_bfloat16*)Z_split, rows, relu, nparts < 1 ? 1 : nparts, part_stride};
-    layernorm_multi_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p);
+    cudaError_t e = launch_pdl(layernorm_multi_kernel, dim3((rows + 7) / 8), dim3(256), 0, (cudaStream_t)stream, p);
+    if (e != cudaSuccess) return fail((int)e, "petr_layernorm_multi_f32: launch: %s", cudaGetErrorString(e));
     return after_launch("petr_layernorm_multi_f32");
 }
 

@@ -168,6 +168,8 @@ constexpr int TM_PH = 320, TM_PL = 384;       // FAST: P hi / lo (bf16 pairs, 64
 template <bool FAST>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_x3_tc_kernel(const __grid_constant__ Maps tm, AttParams p, float scale_log2) {
+    pdl_launch_dependents();
+    pdl_wait();                                      // the flags below were written by the fast pass just before
     const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     if (!FAST && p.flags && p.flags[cta] == 0) return;
     extern __shared__ uint8_t smem_raw[];
@@ -551,6 +553,8 @@ template <bool FAST, int POLY, bool TRACE = false>
 __global__ void __launch_bounds__(THREADS, 1)
 cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                            const __grid_constant__ CUtensorMap tmV, AttParams p) {
+    pdl_launch_dependents();
+    pdl_wait();                 // before the flag read / reset: the previous launch (fast pass, previous layer) owns them
     const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     if (!FAST && p.flags && p.flags[cta] == 0) return;      // exact pass: only CTAs the fast pass flagged
     extern __shared__ uint8_t smem_raw[];
@@ -866,6 +870,8 @@ cross_attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 __global__ void attention_merge_kernel(const float* __restrict__ part, int nparts, float* __restrict__ O,
                                        int ldo, __nv_bfloat16* __restrict__ O_split, int B, int Lq, int heads,
                                        float* __restrict__ lse = nullptr) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t rows = (int64_t)B * heads * Lq;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * 8) return;
@@ -1015,18 +1021,21 @@ extern "C" int petr_cross_attention_bf16(const void* Qs, const void* Kh, const v
     dim3 grid((Lq + 2 * QT - 1) / (2 * QT), B * heads, nsplit);
     int rc = 0;
     if (fast) {
-        fast_fn<<<grid, v4::THREADS, v4::SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+        e = launch_pdl(fast_fn, grid, dim3(v4::THREADS), v4::SMEM, (cudaStream_t)stream, tmQ, tmK, tmV, p);
+        if (e != cudaSuccess) return fail((int)e, "petr_cross_attention_bf16: launch: %s", cudaGetErrorString(e));
         rc = after_launch("petr_cross_attention_bf16 (fast pass)");
         if (rc) return rc;
     }
-    exact_fn<<<grid, v4::THREADS, v4::SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    e = launch_pdl(exact_fn, grid, dim3(v4::THREADS), v4::SMEM, (cudaStream_t)stream, tmQ, tmK, tmV, p);
+    if (e != cudaSuccess) return fail((int)e, "petr_cross_attention_bf16: launch: %s", cudaGetErrorString(e));
     rc = after_launch("petr_cross_attention_bf16");
     if (rc) return rc;
     if (part && !write_partial) {
         // on-GPU split-KV: merge right away
         int64_t total = rows * 8;
-        attention_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            partial, nsplit, O, ldo, (__nv_bfloat16*)O_split, B, Lq, heads);
+        e = launch_pdl(attention_merge_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+                       (const float*)partial, nsplit, O, ldo, (__nv_bfloat16*)O_split, B, Lq, heads, (float*)nullptr);
+        if (e != cudaSuccess) return fail((int)e, "petr_attention_merge: launch: %s", cudaGetErrorString(e));
         return after_launch("petr_attention_merge");
     }
     return 0;
@@ -1109,11 +1118,15 @@ extern "C" int petr_attention_x3_tc(const void* Qh, const void* Ql, const void* 
     dim3 grid((Lq + QT - 1) / QT, B * heads, nsplit);
     int rc = 0;
     if (fast) {
-        x3::attention_x3_tc_kernel<true><<<grid, x3::THREADS, x3::SMEM, (cudaStream_t)stream>>>(tm, p, scale * 1.4426950408889634f);
+        cudaError_t e2 = launch_pdl(x3::attention_x3_tc_kernel<true>, grid, dim3(x3::THREADS), x3::SMEM, (cudaStream_t)stream, tm, p,
+                                    scale * 1.4426950408889634f);
+        if (e2 != cudaSuccess) return fail((int)e2, "petr_attention_x3_tc: launch: %s", cudaGetErrorString(e2));
         rc = after_launch("petr_attention_x3_tc (fast pass)");
         if (rc) return rc;
     }
-    x3::attention_x3_tc_kernel<false><<<grid, x3::THREADS, x3::SMEM, (cudaStream_t)stream>>>(tm, p, scale * 1.4426950408889634f);
+    cudaError_t e3 = launch_pdl(x3::attention_x3_tc_kernel<false>, grid, dim3(x3::THREADS), x3::SMEM, (cudaStream_t)stream, tm, p,
+                                scale * 1.4426950408889634f);
+    if (e3 != cudaSuccess) return fail((int)e3, "petr_attention_x3_tc: launch: %s", cudaGetErrorString(e3));
     rc = after_launch("petr_attention_x3_tc");
     if (rc) return rc;
     if (part && !write_partial) {

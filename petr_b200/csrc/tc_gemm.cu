@@ -172,6 +172,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // TMA producer: the whole warp walks the loop (waits by all lanes), one elected lane issues
@@ -788,6 +791,7 @@ extern "C" int petr_gemm_bf16_tc(const void* A, int lda, int a_k_wrap, const voi
     int tiles = p.tiles_m * p.tiles_n * ksplit;
     int grid = tiles < sms ? tiles : sms;
     p.band = (out_mode == 2 && p.tiles_n > 1 && tuning::gemm_band()) ? grid : 0;      // measured slower (0.509 vs 0.466 ms): off by default
-    fn<<<grid, GEMM_THREADS, GEMM_SMEM, (cudaStream_t)stream>>>(tmA, tmB, tmC, tmD, p);
+    e = launch_pdl(fn, dim3(grid), dim3(GEMM_THREADS), GEMM_SMEM, (cudaStream_t)stream, tmA, tmB, tmC, tmD, p);
+    if (e != cudaSuccess) return fail((int)e, "petr_gemm_bf16_tc: launch: %s", cudaGetErrorString(e));
     return after_launch("petr_gemm_bf16_tc");
 }
