@@ -374,6 +374,14 @@ int petr_sigmoid_gate_bwd_f32(const float* dOut, const float* Zpre, const float*
  * (residual nullable: the `identity + dropout(out)` of petr_transformer.py:367 in one pass). */
 int petr_dropout_f32(const float* X, const float* residual, float* Y, int64_t n, float p, uint64_t seed,
                      void* stream);
+/* Backward of petr_norm_scale_f32 (NormedLinear operand scaling): dX from dOut and the forward input x; same group
+ * layout switch.  A zero-norm group passes dOut * mult / eps through (x is zero there). */
+int petr_norm_scale_bwd_f32(const float* x, const float* dOut, float* dX, int B, int Q, int E, int along_queries,
+                            float power, float eps, float mult, void* stream);
+/* Backward of petr_learned_pos_features: token gradients [G*H*W, 2*num_feats] summed into d_col_embed[W, num_feats]
+ * and d_row_embed[H, num_feats] (the first W / H rows of the embedding tables; overwritten, not accumulated). */
+int petr_learned_pos_bwd(const float* dOut, int G, int H, int W, int num_feats, float* d_row_embed,
+                         float* d_col_embed, void* stream);
 /* nn.LayerNorm backward (E = 256): dX, and dgamma / dbeta (nullable) accumulated atomically.  relu / nan_to_num as in
  * petr_layernorm_f32 (their masks are re-derived from the recomputed output). */
 int petr_layernorm_bwd_f32(const float* X, const float* gamma, const float* beta, const float* dY, float* dX,

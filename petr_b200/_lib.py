@@ -70,6 +70,8 @@ SIGNATURES = {
     "petr_relu_bwd_f32": (c_int, [_P, _P, _P, c_int64, _P]),
     "petr_sigmoid_gate_bwd_f32": (c_int, [_P, _P, _P, _P, _P, c_int64, _P]),
     "petr_dropout_f32": (c_int, [_P, _P, _P, c_int64, _F, c_uint64, _P]),
+    "petr_norm_scale_bwd_f32": (c_int, [_P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P]),
+    "petr_learned_pos_bwd": (c_int, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "petr_layernorm_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _I, _P]),
     "petr_attention_f32_bwd": (c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _I,
                                        _P, _I, _P, _I, _P, _I, _F, c_uint64, _I, _I, _I, _I, _I, _F, _P]),

@@ -14,6 +14,8 @@
 //   petr_pos2posemb3d                       petr_pos2posemb3d_bwd
 //   petr_decode_boxes                       petr_decode_boxes_bwd (d reg, d reference_points)
 //   nn.Dropout                              petr_dropout_f32 (same kernel both ways: counter-based mask)
+//   petr_norm_scale_f32 (NormedLinear)      petr_norm_scale_bwd_f32
+//   petr_learned_pos_features               petr_learned_pos_bwd (d row_embed, d col_embed)
 #include "common.cuh"
 
 namespace petr {
@@ -592,6 +594,85 @@ l1_loss_kernel(const float* __restrict__ X, const float* __restrict__ T, const f
     }
 }
 
+
+// ---- petr_norm_scale_f32 backward.  y = x * s(n), s = mult / (n^power + eps), n = ||x|| over the group:
+// dx = s * dy + x * (s'(n) / n) * sum(dy * x), s'(n) = -mult * power * n^(power-1) / (n^power + eps)^2;
+// n == 0 contributes nothing through the norm (x is zero there; torch's norm backward masks it the same way).
+__device__ __forceinline__ void norm_scale_coeffs(float sumsq, float dot, float power, float eps, float mult,
+                                                  float& s, float& c) {
+    const float n = sqrtf(sumsq);
+    const float np = powf(n, power);
+    const float den = np + eps;
+    s = mult / den;
+    c = n > 0.f ? -mult * power * powf(n, power - 2.f) / (den * den) * dot : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+col_norm_scale_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int Q,
+                          int E, float power, float eps, float mult) {
+    // block = one (b, 32-channel group), as the forward: 8 warps stride over the queries
+    __shared__ float p_sq[8][32], p_dot[8][32];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, c = blockIdx.x * 32 + lane, wrp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)b * Q * E;
+    float sq = 0.f, dot = 0.f;
+    if (c < E) for (int q = wrp; q < Q; q += 8) {
+        const float v = x[base + (int64_t)q * E + c];
+        sq = fmaf(v, v, sq);
+        dot = fmaf(dy[base + (int64_t)q * E + c], v, dot);
+    }
+    p_sq[wrp][lane] = sq; p_dot[wrp][lane] = dot;
+    __syncthreads();
+    float tsq = 0.f, tdot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { tsq += p_sq[i][lane]; tdot += p_dot[i][lane]; }
+    float s, cf;
+    norm_scale_coeffs(tsq, tdot, power, eps, mult, s, cf);
+    if (c < E) for (int q = wrp; q < Q; q += 8) {
+        const int64_t i = base + (int64_t)q * E + c;
+        dx[i] = fmaf(x[i], cf, s * dy[i]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+row_norm_scale_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int rows,
+                          int E, float power, float eps, float mult) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (int64_t)row * E;
+    const float* dr = dy + (int64_t)row * E;
+    float sq = 0.f, dot = 0.f;
+    for (int i = lane; i < E; i += 32) { sq = fmaf(xr[i], xr[i], sq); dot = fmaf(dr[i], xr[i], dot); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+    float s, cf;
+    norm_scale_coeffs(sq, dot, power, eps, mult, s, cf);
+    for (int i = lane; i < E; i += 32) dx[(int64_t)row * E + i] = fmaf(xr[i], cf, s * dr[i]);
+}
+
+// ---- petr_learned_pos_features backward: the token gradients [G*H*W, 2F] = [d col_embed[w] | d row_embed[h]] summed
+// into the tables.  Block = one table row (W column rows first, then H row rows), thread = one feature channel.
+__global__ void learned_pos_bwd_kernel(const float* __restrict__ d, int G, int H, int W, int F,
+                                       float* __restrict__ d_row, float* __restrict__ d_col) {
+    const int r = blockIdx.x;
+    const int64_t ld = 2 * F;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        float acc = 0.f;
+        if (r < W) {
+            for (int g = 0; g < G; ++g)
+                for (int h = 0; h < H; ++h) acc += d[(((int64_t)g * H + h) * W + r) * ld + f];
+            d_col[(int64_t)r * F + f] = acc;
+        } else {
+            const int h = r - W;
+            for (int g = 0; g < G; ++g)
+                for (int w = 0; w < W; ++w) acc += d[(((int64_t)g * H + h) * W + w) * ld + F + f];
+            d_row[(int64_t)h * F + f] = acc;
+        }
+    }
+}
+
 }  // namespace
 }  // namespace petr
 
@@ -698,6 +779,30 @@ extern "C" int petr_attention_f32_bwd(const float* Q, int ldq, const float* K, i
     dim3 gk((Lk + AB_ROWS - 1) / AB_ROWS, heads, B);
     attention_bwd_dkv_kernel<<<gk, AB_ROWS, 0, (cudaStream_t)stream>>>(p);
     return after_launch("petr_attention_f32_bwd(dkv)");
+}
+
+extern "C" int petr_norm_scale_bwd_f32(const float* x, const float* dOut, float* dX, int B, int Q, int E,
+                                       int along_queries, float power, float eps, float mult, void* stream) {
+    PETR_REQUIRE(x && dOut && dX, PETR_E_BADARG, "petr_norm_scale_bwd_f32: null pointer");
+    PETR_REQUIRE(B > 0 && Q > 0 && E > 0 && B <= 65535, PETR_E_BADARG, "petr_norm_scale_bwd_f32: bad dimension");
+    if (along_queries) {
+        dim3 grid((E + 31) / 32, B);
+        col_norm_scale_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, dOut, dX, Q, E, power, eps, mult);
+    } else {
+        const int rows = B * Q;
+        row_norm_scale_bwd_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, dOut, dX, rows, E, power, eps, mult);
+    }
+    return after_launch("petr_norm_scale_bwd_f32");
+}
+
+extern "C" int petr_learned_pos_bwd(const float* dOut, int G, int H, int W, int num_feats, float* d_row_embed,
+                                    float* d_col_embed, void* stream) {
+    PETR_REQUIRE(dOut && d_row_embed && d_col_embed, PETR_E_BADARG, "petr_learned_pos_bwd: null pointer");
+    PETR_REQUIRE(G > 0 && H > 0 && W > 0 && num_feats > 0, PETR_E_BADARG, "petr_learned_pos_bwd: bad dimension");
+    const int threads = num_feats >= 256 ? 256 : ((num_feats + 31) / 32) * 32;
+    learned_pos_bwd_kernel<<<(unsigned)(H + W), threads, 0, (cudaStream_t)stream>>>(dOut, G, H, W, num_feats,
+                                                                                   d_row_embed, d_col_embed);
+    return after_launch("petr_learned_pos_bwd");
 }
 
 extern "C" int petr_pos2posemb3d_bwd(const float* ref, const float* dim_t, const float* dOut, int Q, int num_feats,

@@ -227,6 +227,48 @@ def dropout(X, p: float, residual=None):
     return _Dropout.apply(X, residual, p, _next_seed())
 
 
+class _NormScale(Function):
+    """mmdet NormedLinear operand scaling (petr_head.py:231-232): x * mult / (||x||^power + eps), norm over the query
+    axis of (B, Q, E) rows (along_queries) or over each row (the weight)."""
+
+    @staticmethod
+    def forward(ctx, x, B, Q, along_queries, power, eps, mult):
+        x = _c(x.detach())
+        ctx.cfg = (B, Q, bool(along_queries), float(power), float(eps), float(mult))
+        ctx.save_for_backward(x)
+        return ops.norm_scale(x, B, Q, along_queries, power, eps, mult)
+
+    @staticmethod
+    def backward(ctx, dOut):
+        (x,) = ctx.saved_tensors
+        B, Q, along, power, eps, mult = ctx.cfg
+        dOut = _c(dOut)
+        dx = torch.empty_like(x)
+        call("petr_norm_scale_bwd_f32", ptr(x), ptr(dOut), ptr(dx), B, Q, x.shape[-1], int(along), power, eps, mult,
+             stream_ptr(x.device))
+        return dx, None, None, None, None, None, None
+
+
+class _LearnedPos(Function):
+    """LearnedPositionalEncoding3D.forward as tokens (positional_encoding.py:137-160): (G*H*W, 2F) =
+    [col_embed[w] | row_embed[h]]; the backward sums the token gradients into the two tables."""
+
+    @staticmethod
+    def forward(ctx, row_w, col_w, G, H, W):
+        row_w, col_w = _c(row_w.detach().float()), _c(col_w.detach().float())
+        ctx.cfg = (G, H, W, tuple(row_w.shape), tuple(col_w.shape))
+        return ops.learned_pos_features(row_w, col_w, G, H, W)
+
+    @staticmethod
+    def backward(ctx, dOut):
+        G, H, W, rs, cs = ctx.cfg
+        dOut = _c(dOut)
+        d_row = torch.zeros(rs, dtype=torch.float32, device=dOut.device)
+        d_col = torch.zeros(cs, dtype=torch.float32, device=dOut.device)
+        call("petr_learned_pos_bwd", ptr(dOut), G, H, W, rs[1], ptr(d_row), ptr(d_col), stream_ptr(dOut.device))
+        return d_row, d_col, None, None, None
+
+
 class _Pos2PosEmb(Function):
     @staticmethod
     def forward(ctx, ref, dim_t):
@@ -382,8 +424,6 @@ class TrainEngine:
         s = eng.spec
         if not x.is_cuda:
             raise RuntimeError("petr_b200: features must be CUDA tensors (no CPU fallback)")
-        if s.normedlinear:
-            raise NotImplementedError("training path: normedlinear=True is not built")
         x = x.float()
         B, N, Cin, H, W = x.shape
         dev = x.device
@@ -394,9 +434,11 @@ class TrainEngine:
         kmask = masks.view(B, Lk)
         # key side (petr_head.py:381-420)
         mem = linear(x.contiguous().view(B * N, Cin, H, W), head.input_proj.weight, head.input_proj.bias, nchw_hw=H * W)
-        sf = eng.pos_features(P, masks)                     # no gradient: depends on the masks only
         if s.pos_kind == "learned":
-            raise NotImplementedError("training path: LearnedPositionalEncoding3D gradients are not built")
+            pe = head.positional_encoding
+            sf = _LearnedPos.apply(pe.row_embed.weight, pe.col_embed.weight, B * N, H, W)
+        else:
+            sf = eng.pos_features(P, masks)                 # no gradient: depends on the masks only
         if not s.with_position and not s.with_multiview:
             pos = sf
         else:
@@ -429,7 +471,13 @@ class TrainEngine:
             h = outs[l]
             for i in range(s.num_reg_fcs):
                 h = self._ln(cb[3 * i + 1], linear(h, cb[3 * i].weight, cb[3 * i].bias), relu=True)
-            cls_all.append(linear(h, cb[3 * s.num_reg_fcs].weight, cb[3 * s.num_reg_fcs].bias))
+            last = cb[3 * s.num_reg_fcs]
+            if s.normedlinear:                              # mmdet NormedLinear (petr_head.py:231-234)
+                wn = _NormScale.apply(last.weight, 1, last.weight.shape[0], False, last.power, last.eps, 1.0)
+                h = _NormScale.apply(h, B, Lq, True, last.power, last.eps, last.tempearture)
+                cls_all.append(linear(h, wn, last.bias))
+            else:
+                cls_all.append(linear(h, last.weight, last.bias))
             h = outs[l]
             if s.with_multi:
                 for i in range(s.num_reg_fcs):
