@@ -164,6 +164,10 @@ int petr_layernorm_multi_f32(const float* X, const float* gamma, const float* be
 int petr_split_rows_bf16(const float* X, int ldx, const float* add, int add_rows, void* out,
                          int rows, int E, int relu, void* stream);
 
+/* fp32 weight W[N,K] -> bf16 W operand of a bf16x3 GEMM: out[N, 3K] = [hi | hi | lo] of W (transpose 0), or
+ * out[K, 3N] = the same of W^T (transpose 1; the operand of the input-gradient GEMM dA = dY W). */
+int petr_x3_weight_bf16(const float* W, int N, int K, int transpose, void* out, void* stream);
+
 /* Copies nbytes (multiple of 4) from PINNED host memory (UVA-mapped; the one host pointer this ABI
  * reads from the device) to device memory with a tiny kernel instead of the copy engine, so the
  * per-call meta data (img2lidar, img_shape, timestamps) never queues behind a concurrent bulk

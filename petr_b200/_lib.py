@@ -36,6 +36,7 @@ SIGNATURES = {
                                    _I, _I, _I, _I, _I, _F, _P]),
     "petr_layernorm_multi_f32": (c_int, [_P, _P, _P, _F, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, c_int64, _P]),
     "petr_split_rows_bf16": (c_int, [_P, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "petr_x3_weight_bf16": (c_int, [_P, _I, _I, _I, _P, _P]),
     "petr_nchw_to_tokens_bf16": (c_int, [_P, _I, _P, _I, _I, _I, _P]),
     "petr_layernorm_f32": (c_int, [_P, _P, _P, _P, _I, _I, _F, _I, _I, _P]),
     "petr_nms_free_decode": (c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P]),

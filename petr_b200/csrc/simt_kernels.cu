@@ -692,6 +692,46 @@ __global__ void split_rows_kernel(const float* __restrict__ X, int ldx, const fl
     store_split_elem(out + r * 2 * E, E, c, v);
 }
 
+// the same, eight columns per thread (E % 8 == 0, ldx % 4 == 0, 16-byte aligned pointers)
+__global__ void split_rows8_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ add,
+                                   int add_rows, __nv_bfloat16* __restrict__ out, int64_t rows, int E, int relu) {
+    const int E8 = E >> 3;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * E8) return;
+    int64_t r = i / E8;
+    int c = (int)(i - r * E8) * 8;
+    float v[8];
+    load8(X + r * ldx + c, v);
+    if (add) {
+        float a[8];
+        load8(add + (r % add_rows) * (int64_t)E + c, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += a[j];
+    }
+    if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    store_split8(out + r * 2 * E + c, out + r * 2 * E + E + c, v);
+}
+
+// fp32 weight (N,K) -> the W operand of a bf16x3 GEMM: rows [hi | hi | lo] of W (transpose 0: (N, 3K)) or of its
+// transpose (transpose 1: (K, 3N), the operand of the input-gradient GEMM dA = dY W).
+__global__ void x3_weight_kernel(const float* __restrict__ W, int N, int K, int transpose,
+                                 __nv_bfloat16* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * K) return;
+    const int C = transpose ? N : K;
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    const float v = transpose ? W[(int64_t)c * K + r] : W[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    __nv_bfloat16* o = out + r * 3 * C;
+    o[c] = hi;
+    o[C + c] = hi;
+    o[2 * C + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
 // out_bf16[r, :] = bf16(X[r, :] + add[r % add_rows, :]); E % 4 == 0 (key-side K input: tokens +
 // the batch-invariant sine embedding)
 __global__ void add_rows_bf16_kernel(const float* __restrict__ X, const float* __restrict__ add, int add_rows,
@@ -990,9 +1030,22 @@ extern "C" int petr_split_rows_bf16(const float* X, int ldx, const float* add, i
     PETR_REQUIRE(rows > 0 && E > 0 && ldx >= E, PETR_E_BADARG, "petr_split_rows_bf16: bad dimension");
     if (add) PETR_REQUIRE(add_rows > 0, PETR_E_BADARG, "petr_split_rows_bf16: add_rows <= 0");
     int64_t total = (int64_t)rows * E;
-    split_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        X, ldx, add, add_rows, (__nv_bfloat16*)out, rows, E, relu);
+    if (E % 8 == 0 && ldx % 4 == 0 && aligned16(X) && aligned16(out) && (!add || aligned16(add)))
+        split_rows8_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            X, ldx, add, add_rows, (__nv_bfloat16*)out, rows, E, relu);
+    else
+        split_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            X, ldx, add, add_rows, (__nv_bfloat16*)out, rows, E, relu);
     return after_launch("petr_split_rows_bf16");
+}
+
+extern "C" int petr_x3_weight_bf16(const float* W, int N, int K, int transpose, void* out, void* stream) {
+    PETR_REQUIRE(W && out, PETR_E_BADARG, "petr_x3_weight_bf16: null pointer");
+    PETR_REQUIRE(N > 0 && K > 0, PETR_E_BADARG, "petr_x3_weight_bf16: bad dimension");
+    int64_t total = (int64_t)N * K;
+    x3_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, N, K, transpose ? 1 : 0,
+                                                                                        (__nv_bfloat16*)out);
+    return after_launch("petr_x3_weight_bf16");
 }
 
 extern "C" int petr_add_rows_bf16(const float* X, const float* add, int add_rows, void* out, int rows, int E,

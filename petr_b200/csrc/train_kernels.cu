@@ -701,7 +701,7 @@ extern "C" int petr_gemm_f32_tn(const float* dY, int ldy, const float* A, int ld
 extern "C" int petr_colsum_f32(const float* X, int ldx, int M, int N, float* out, void* stream) {
     PETR_REQUIRE(X && out, PETR_E_BADARG, "petr_colsum_f32: null pointer");
     PETR_REQUIRE(M > 0 && N > 0, PETR_E_BADARG, "petr_colsum_f32: bad dimension");
-    int splits = (M + 2047) / 2048;
+    int splits = (M + 255) / 256;                              // 900 query rows: 4 x N/32 CTAs; 24 000 tokens: 94 x N/32
     if (splits > 1024) splits = 1024;
     const int rows_per_cta = (M + splits - 1) / splits;
     dim3 grid((N + 31) / 32, (M + rows_per_cta - 1) / rows_per_cta);

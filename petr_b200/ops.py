@@ -234,6 +234,16 @@ def x3_weight(W: torch.Tensor) -> torch.Tensor:
     return torch.cat([hi, hi, lo], 1).contiguous()
 
 
+def x3_weight_kernel(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+    """x3_weight(W) (or of W.T) in one launch of the library: fp32 (N,K) -> bf16 (N,3K) | (K,3N)."""
+    _cuda(W, "W")
+    assert W.dim() == 2 and W.is_contiguous() and W.dtype == torch.float32
+    N, K = W.shape
+    out = torch.empty((K, 3 * N) if transpose else (N, 3 * K), dtype=torch.bfloat16, device=W.device)
+    call("petr_x3_weight_bf16", ptr(W), N, K, int(bool(transpose)), ptr(out), stream_ptr(W.device))
+    return out
+
+
 OUT_SPLIT = 3
 
 

@@ -46,6 +46,42 @@ def _transpose(W2: torch.Tensor) -> torch.Tensor:
     return ops.tokens_to_nchw(_c(W2), 1, N).view(K, N)
 
 
+# The large Linear layers run on the tensor cores as bf16x3 GEMMs (operands split [hi | lo], three bf16 products per fp32
+# product, fp32 accumulation: ~1e-6 of the output scale, the tier the inference path uses for its query side); small or
+# ragged shapes (the 256 -> 10 tails, NCHW input maps) stay on the FFMA kernel.
+TC_GEMM = True
+TC_MIN_ROWS = 256
+
+
+def _tc_ok(M: int, N: int, K: int) -> bool:
+    return TC_GEMM and M >= TC_MIN_ROWS and K % 64 == 0 and N % 8 == 0 and N >= 64
+
+
+_SPLIT_CACHE: dict = {}          # forward only, big activations: (ptr, version, A2 ptr) -> (A, A2, split); see _gemm_x3
+SPLIT_CACHE_MIN_ROWS = 4096
+
+
+def _gemm_x3(A, W2, bias, A2, residual, act, transpose_w=False, cache=False):
+    """act((A + A2[m % rows]) W^T + bias) (+ residual) with W = W2 (or W2^T), fp32 in / out, on tcgen05: A is split
+    to bf16 [hi | lo] by the library's split kernel, the weight packed [hi | hi | lo] by petr_x3_weight_bf16.
+    cache: the split of a large forward activation is kept until the next forward starts -- the image tokens and
+    their position embedding feed the K / V projections of all six decoder layers (the entry holds A, so its
+    address cannot be reused while it is cached)."""
+    A = _c(A)
+    As = None
+    key = ((A.data_ptr(), A._version, tuple(A.shape)) + ((A2.data_ptr(), A2._version) if A2 is not None else (0, 0))) if cache else None
+    if key is not None and A.shape[0] >= SPLIT_CACHE_MIN_ROWS:
+        hit = _SPLIT_CACHE.get(key)
+        if hit is not None:
+            As = hit[2]
+    if As is None:
+        As = ops.split_rows(A, add=A2)
+        if key is not None and A.shape[0] >= SPLIT_CACHE_MIN_ROWS:
+            _SPLIT_CACHE[key] = (A, A2, As)
+    W3 = ops.x3_weight_kernel(W2, transpose_w)
+    return ops.gemm_bf16_tc(As, W3, bias, residual=residual, act=act, x3=True)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # autograd wrappers
 # ------------------------------------------------------------------------------------------------------------
@@ -57,9 +93,14 @@ class _Linear(Function):
         W2 = W.detach().reshape(W.shape[0], -1)
         assert not (act != ACT_NONE and residual is not None)
         A = _c(A.detach())
-        out = ops.gemm_f32(A, _c(W2), bias.detach() if bias is not None else None,
-                           A2=A2.detach() if A2 is not None else None,
-                           residual=residual.detach() if residual is not None else None, act=act, nchw_hw=nchw_hw)
+        if _tc_ok(A.shape[0], W2.shape[0], W2.shape[1]) and nchw_hw == 0:
+            out = _gemm_x3(A, _c(W2), bias.detach() if bias is not None else None,
+                           A2.detach() if A2 is not None else None,
+                           _c(residual.detach()) if residual is not None else None, act, cache=True)
+        else:
+            out = ops.gemm_f32(A, _c(W2), bias.detach() if bias is not None else None,
+                               A2=A2.detach() if A2 is not None else None,
+                               residual=residual.detach() if residual is not None else None, act=act, nchw_hw=nchw_hw)
         ctx.act, ctx.nchw_hw, ctx.wshape = act, nchw_hw, W.shape
         ctx.save_for_backward(A, W2, A2.detach() if A2 is not None else None, out if act == ACT_RELU else None)
         ctx.has_bias = bias is not None
@@ -79,7 +120,10 @@ class _Linear(Function):
         need = ctx.needs_input_grad
         dA = dW = db = dA2 = dres = None
         if need[0] or (A2 is not None and need[3]):
-            dA_tok = ops.gemm_f32(dZ, _transpose(W2))                       # (M, K) = dZ @ W
+            if _tc_ok(M, K, N):
+                dA_tok = _gemm_x3(dZ, W2, None, None, None, ACT_NONE, transpose_w=True)
+            else:
+                dA_tok = ops.gemm_f32(dZ, _transpose(W2))                   # (M, K) = dZ @ W
             if need[0]:
                 if ctx.nchw_hw > 0:
                     G = M // ctx.nchw_hw
@@ -424,6 +468,7 @@ class TrainEngine:
         s = eng.spec
         if not x.is_cuda:
             raise RuntimeError("petr_b200: features must be CUDA tensors (no CPU fallback)")
+        _SPLIT_CACHE.clear()
         x = x.float()
         B, N, Cin, H, W = x.shape
         dev = x.device

@@ -30,20 +30,23 @@ def _close(a, b, rel=2e-3, name=""):
     return err / max(scale, 1e-30)
 
 
-def _close_l2(a, b, name="", floor=1e-6):
+def _close_l2(a, b, name="", floor=1e-6, l2_bound=3e-3, max_bound=2e-2):
     """Whole-head gradients: a ReLU unit whose fp32 pre-activation sits within rounding of 0 may switch side between two
     correct implementations, which moves ONE row of a weight gradient by a finite amount.  Bound: relative L2 error
     <= 3e-3 and max error <= 2e-2 of the tensor's scale (a wrong kernel is off by O(1) in both).  `floor`: absolute
     noise level (1e-7 of the largest gradient of the model) below which a tensor is numerically zero -- e.g. the Q/K
-    projections of the first self-attention, whose values are all zero."""
+    projections of the first self-attention, whose values are all zero.  With the Linear layers on the bf16x3 tensor-core
+    tier (operands carry 16 mantissa bits: ~1e-5 of the output scale instead of 1e-7) about a hundred times more units
+    sit within rounding of 0, and the cross-attention concentrates the key-side gradient on few tokens, so one
+    switched unit can carry a few percent of a bias gradient: relative L2 <= 1e-2, max <= 5e-2 of the scale there."""
     a, b = a.detach().cpu().double(), b.detach().cpu().double()
     assert a.shape == b.shape, (name, a.shape, b.shape)
     scale = b.abs().max().item()
     err = (a - b).abs().max().item()
-    assert math.isfinite(err) and err <= 2e-2 * scale + floor, (name, err, scale)
+    assert math.isfinite(err) and err <= max_bound * scale + floor, (name, err, scale)
     dn, bn = (a - b).norm().item(), b.norm().item()
     l2 = dn / max(bn, 1e-30)
-    assert l2 <= 3e-3 or dn <= floor * math.sqrt(a.numel()), (name, err, scale, l2)
+    assert l2 <= l2_bound or dn <= floor * math.sqrt(a.numel()), (name, err, scale, l2)
     return l2 if scale > 100 * floor else 0.0
 
 
@@ -51,25 +54,30 @@ def _leaf(t):
     return t.clone().to(DEV).requires_grad_(True)
 
 
-def test_linear_backward_variants():
+@pytest.mark.parametrize("M,K,N,rows,tc", [(333, 192, 100, 111, False), (640, 192, 128, 128, True)])
+def test_linear_backward_variants(M, K, N, rows, tc):
+    """Ragged shape: FFMA kernels; 64-aligned shape: bf16x3 tcgen05 GEMMs for the forward and the input gradient."""
+    assert train._tc_ok(M, N, K) == tc and train._tc_ok(M, K, N) == tc
     g = torch.Generator().manual_seed(0)
-    M, K, N, rows = 333, 192, 100, 111
     A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.1, torch.randn(N, generator=g)
     A2, R = torch.randn(rows, K, generator=g), torch.randn(M, N, generator=g)
     dY = torch.randn(M, N, generator=g)
     for act, use_a2, use_res in ((ACT_NONE, True, True), (ACT_RELU, True, False), (ACT_NONE, False, False)):
+        mine = [_leaf(t) for t in (A, W, b, A2, R)]
+        out = train.linear(mine[0], mine[1], mine[2], A2=mine[3] if use_a2 else None,
+                           residual=mine[4] if use_res else None, act=act)
         ref_in = [t.clone().double().requires_grad_(True) for t in (A, W, b, A2, R)]
         a = ref_in[0] + (ref_in[3].repeat(M // rows, 1) if use_a2 else 0)
         y = F.linear(a, ref_in[1], ref_in[2])
         if act == ACT_RELU:
-            y = F.relu(y)
+            # the reference takes the kernel's own ReLU mask: a pre-activation within rounding of 0 may sit on either
+            # side in two correct implementations, and one switched unit moves a row of dA by |dY| |W|
+            assert (F.relu(y) - out.detach().cpu().double()).abs().max() <= 3e-5 * y.abs().max()
+            y = y * (out.detach().cpu() > 0)
         if use_res:
             y = y + ref_in[4]
         y.backward(dY.double())
-        mine = [_leaf(t) for t in (A, W, b, A2, R)]
-        out = train.linear(mine[0], mine[1], mine[2], A2=mine[3] if use_a2 else None,
-                           residual=mine[4] if use_res else None, act=act)
-        _close(out, y, 1e-5, "linear fwd")
+        _close(out, y, 3e-5 if tc else 1e-5, "linear fwd")     # bf16x3: operands carry 16 mantissa bits
         out.backward(dY.to(DEV))
         for i, nm in enumerate(("dA", "dW", "db", "dA2", "dres")):
             if (nm == "dA2" and not use_a2) or (nm == "dres" and not use_res):
@@ -321,9 +329,12 @@ TRAIN_CASES = {
 }
 
 
+@pytest.mark.parametrize("tc_gemm", [False, True], ids=["ffma", "bf16x3"])
 @pytest.mark.parametrize("name", list(TRAIN_CASES))
-def test_head_loss_and_gradients_match_oracle_autograd(name):
-    _check_head_gradients(name, TRAIN_CASES[name])
+def test_head_loss_and_gradients_match_oracle_autograd(name, tc_gemm):
+    """Both GEMM tiers of the training path: exact FFMA (train.TC_GEMM = False; pins the gradients) and the default
+    bf16x3 tcgen05 GEMMs for the large Linear layers."""
+    _check_head_gradients(name, TRAIN_CASES[name], tc_gemm=tc_gemm)
 
 
 # the reference branches no shipped config takes (petr_head.py:231-234, 396-420), in train mode
@@ -344,7 +355,16 @@ def test_head_gradients_config_branches(variant):
     _check_head_gradients(variant, TRAIN_CASES["tiny"], hc, oc)
 
 
-def _check_head_gradients(name, case, head_over=None, oracle_over=None):
+def _check_head_gradients(name, case, head_over=None, oracle_over=None, tc_gemm=True):
+    saved = train.TC_GEMM
+    train.TC_GEMM = tc_gemm
+    try:
+        _check_head_gradients_impl(name, case, head_over, oracle_over, 1e-2 if tc_gemm else 3e-3)
+    finally:
+        train.TC_GEMM = saved
+
+
+def _check_head_gradients_impl(name, case, head_over, oracle_over, l2_bound):
     wl, feats, metas = cases.inputs(case)
     cfg = cases.head_cfg(case)
     ocfg = cases.oracle_cfg(case)
@@ -388,7 +408,8 @@ def _check_head_gradients(name, case, head_over=None, oracle_over=None):
     sum(lossm.values()).backward()
     assert ops.launch_count() > 150          # forward + loss launches (the counter is per thread; autograd runs backward on its own)
     floor = 1e-7 * max(float(v.grad.abs().max()) for v in sdr.values() if torch.is_tensor(v) and v.grad is not None)
-    _close_l2(xm.grad, xr.grad, "d features", floor)
+    max_bound = 5e-2 if l2_bound > 3e-3 else 2e-2
+    _close_l2(xm.grad, xr.grad, "d features", floor, l2_bound, max_bound)
     worst = 0.0
     named = dict(head.named_parameters())
     checked = 0
@@ -404,7 +425,7 @@ def _check_head_gradients(name, case, head_over=None, oracle_over=None):
         if k.startswith(("cls_branches.0.", "reg_branches.0.")) and head.cls_branches[0] is head.cls_branches[-1]:
             gr = sum(sdr[k.replace(".0.", f".{l}.", 1)].grad for l in range(6))
         assert p.grad is not None, k
-        worst = max(worst, _close_l2(p.grad, gr, k, floor))
+        worst = max(worst, _close_l2(p.grad, gr, k, floor, l2_bound, max_bound))
         checked += 1
     print(f"{name}: {checked} parameter gradients checked, worst relative L2 error {worst:.2e}")
     assert checked >= 100
