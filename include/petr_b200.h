@@ -365,6 +365,13 @@ int petr_norm_scale_f32(const float* x, float* out, int B, int Q, int E, int alo
  * hold zeros or a running gradient (partial sums over row chunks are added atomically). */
 int petr_gemm_f32_tn(const float* dY, int ldy, const float* A, int lda, int a_layout, int hw,
                      const float* A2, int a2_rows, float* dW, int M, int N, int K, void* stream);
+/* Operands of the weight-gradient GEMM on tcgen05 (dW = dY^T (A + A2) is K-major over m once both factors are
+ * transposed): fp32 X[M, C] (+ add[m % add_rows, C]) -> bf16 out[C, w * Mpad], w3 0: [hi | lo] (A operand of a bf16x3
+ * petr_gemm_bf16_tc), w3 1: [hi | hi | lo] (its W operand); Mpad >= M, a multiple of 64 for the GEMM; columns >= M are 0. */
+int petr_split_transpose_bf16(const float* X, int ldx, const float* add, int add_rows, int M, int C, int Mpad, int w3,
+                              void* out, void* stream);
+/* out[i] = sum over p < nparts of parts[p * n + i] (split-K parts of a GEMM; n a multiple of 4). */
+int petr_sum_parts_f32(const float* parts, int nparts, int64_t n, float* out, void* stream);
 /* out[N] += column sums of X[M,N] (bias gradient). */
 int petr_colsum_f32(const float* X, int ldx, int M, int N, float* out, void* stream);
 /* out[period_rows, E] += sum_j X[j*period_rows + r, :] (gradient of the row-periodic A2 / query_pos add). */

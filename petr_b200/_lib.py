@@ -66,6 +66,8 @@ SIGNATURES = {
     "petr_p2p_epoch_inc": (c_int, [_P, _P]),
     "petr_attention_merge_p2p": (c_int, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _I, _P]),
     "petr_gemm_f32_tn": (c_int, [_P, _I, _P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "petr_split_transpose_bf16": (c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "petr_sum_parts_f32": (c_int, [_P, _I, c_int64, _P, _P]),
     "petr_colsum_f32": (c_int, [_P, _I, _I, _I, _P, _P]),
     "petr_rowsum_periodic_f32": (c_int, [_P, _I, _I, _I, _P, _P]),
     "petr_relu_bwd_f32": (c_int, [_P, _P, _P, c_int64, _P]),

@@ -673,6 +673,59 @@ __global__ void learned_pos_bwd_kernel(const float* __restrict__ d, int G, int H
     }
 }
 
+
+// ---- operands of the weight-gradient GEMM on tcgen05: dW[n,k] = sum_m dY[m,n] (A[m,k] + A2[m % a2_rows, k]) is a
+// K-major GEMM over m once both factors are transposed.  fp32 X[M, C] (+ add[m % add_rows, C]) -> bf16 out[C, w * Mpad]:
+// w = 2: [hi | lo] (the A operand of a bf16x3 GEMM), w = 3: [hi | hi | lo] (its W operand); columns m >= M are zero.
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ add, int add_rows, int M, int C,
+                       int Mpad, int w3, __nv_bfloat16* __restrict__ out) {
+    // tile: 64 rows (m) x 32 columns (c); reads are 128-byte row segments, writes bf16 pairs = 128 bytes per warp
+    __shared__ float tile[64][33];
+    const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 64; i += 8) {
+        const int m = m0 + i, c = c0 + tx;
+        float v = 0.f;
+        if (m < M && c < C) {
+            v = X[(int64_t)m * ldx + c];
+            if (add) v += add[(int64_t)(m % add_rows) * C + c];
+        }
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    const int64_t ldo = (int64_t)(w3 ? 3 : 2) * Mpad;
+    const int m = m0 + 2 * tx;                       // Mpad is even: m and m + 1 are inside or outside together
+    if (m >= Mpad) return;
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i;
+        if (c >= C) continue;
+        const float v0 = tile[2 * tx][i], v1 = tile[2 * tx + 1][i];
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v0 - __low2float(hi), v1 - __high2float(hi));
+        __nv_bfloat16* o = out + (int64_t)c * ldo + m;
+        *reinterpret_cast<__nv_bfloat162*>(o) = hi;
+        if (w3) {
+            *reinterpret_cast<__nv_bfloat162*>(o + Mpad) = hi;
+            *reinterpret_cast<__nv_bfloat162*>(o + 2 * (int64_t)Mpad) = lo;
+        } else {
+            *reinterpret_cast<__nv_bfloat162*>(o + Mpad) = lo;
+        }
+    }
+}
+
+// out[i] = sum_p parts[p][i] (the split-K parts of the weight-gradient GEMM), four elements per thread
+__global__ void sum_parts_kernel(const float4* __restrict__ parts, int nparts, int64_t n4, float4* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 a = parts[i];
+    for (int p = 1; p < nparts; ++p) {
+        const float4 b = parts[(int64_t)p * n4 + i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    out[i] = a;
+}
+
 }  // namespace
 }  // namespace petr
 
@@ -696,6 +749,29 @@ extern "C" int petr_gemm_f32_tn(const float* dY, int ldy, const float* A, int ld
     dim3 grid((N + 63) / 64, (K + 63) / 64, splits);
     gemm_f32_tn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     return after_launch("petr_gemm_f32_tn");
+}
+
+extern "C" int petr_split_transpose_bf16(const float* X, int ldx, const float* add, int add_rows, int M, int C,
+                                         int Mpad, int w3, void* out, void* stream) {
+    PETR_REQUIRE(X && out, PETR_E_BADARG, "petr_split_transpose_bf16: null pointer");
+    PETR_REQUIRE(M > 0 && C > 0 && ldx >= C && Mpad >= M && Mpad % 8 == 0, PETR_E_BADARG,
+                 "petr_split_transpose_bf16: bad dimension");
+    if (add) PETR_REQUIRE(add_rows > 0, PETR_E_BADARG, "petr_split_transpose_bf16: add_rows <= 0");
+    dim3 grid((Mpad + 63) / 64, (C + 31) / 32);
+    PETR_REQUIRE(grid.y <= 65535, PETR_E_SHAPE, "petr_split_transpose_bf16: C too large");
+    split_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, add, add_rows, M, C, Mpad, w3 ? 1 : 0,
+                                                                   (__nv_bfloat16*)out);
+    return after_launch("petr_split_transpose_bf16");
+}
+
+extern "C" int petr_sum_parts_f32(const float* parts, int nparts, int64_t n, float* out, void* stream) {
+    PETR_REQUIRE(parts && out, PETR_E_BADARG, "petr_sum_parts_f32: null pointer");
+    PETR_REQUIRE(nparts > 0 && n > 0 && n % 4 == 0 && aligned16(parts) && aligned16(out), PETR_E_BADARG,
+                 "petr_sum_parts_f32: n must be a positive multiple of 4, pointers 16-byte aligned");
+    const int64_t n4 = n / 4;
+    sum_parts_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)parts, nparts, n4,
+                                                                                    (float4*)out);
+    return after_launch("petr_sum_parts_f32");
 }
 
 extern "C" int petr_colsum_f32(const float* X, int ldx, int M, int N, float* out, void* stream) {

@@ -244,6 +244,20 @@ def x3_weight_kernel(W: torch.Tensor, transpose: bool = False) -> torch.Tensor:
     return out
 
 
+def split_transpose(X: torch.Tensor, add, Mpad: int, w3: bool) -> torch.Tensor:
+    """fp32 (M,C) (+ add[m % rows]) -> bf16 (C, 2*Mpad) [hi | lo] or (C, 3*Mpad) [hi | hi | lo] of the transpose, zero
+    beyond column M: the operands of the weight-gradient GEMM."""
+    _cuda(X, "X")
+    assert X.dim() == 2 and X.stride(1) == 1 and X.dtype == torch.float32
+    M, C = X.shape
+    out = torch.empty((C, (3 if w3 else 2) * Mpad), dtype=torch.bfloat16, device=X.device)
+    if add is not None:
+        assert add.is_contiguous() and add.shape[1] == C
+    call("petr_split_transpose_bf16", ptr(X), X.stride(0), ptr(add), add.shape[0] if add is not None else 0, M, C,
+         int(Mpad), int(bool(w3)), ptr(out), stream_ptr(X.device))
+    return out
+
+
 OUT_SPLIT = 3
 
 

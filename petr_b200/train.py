@@ -2,8 +2,9 @@
 petrv2_head.py:429-540 in train mode with autograd, `loss` / `loss_single` / `get_targets` (petr_head.py:470-728) and
 the Hungarian matching cost (core/bbox/assigners/hungarian_assigner_3d.py:117-143).
 
-Every differentiable op is a `torch.autograd.Function` whose forward AND backward are kernels of libpetr_b200.so (fp32
-path: petr_gemm_f32 / petr_attention_f32 / petr_layernorm_f32 forward, train_kernels.cu backward).  PyTorch supplies
+Every differentiable op is a `torch.autograd.Function` whose forward AND backward are kernels of libpetr_b200.so
+(petr_attention_f32 / petr_layernorm_f32 forward, train_kernels.cu backward; the large Linear layers -- forward, input
+and weight gradient -- as bf16x3 GEMMs on tcgen05, the ragged rest on the FFMA GEMMs).  PyTorch supplies
 the tape, device memory, index bookkeeping of the matched targets and the optimizer; scipy's linear_sum_assignment does
 the assignment on the host exactly as the reference does.  Dropout (attention probabilities, projection / FFN outputs)
 uses a counter-based mask that the backward kernels re-evaluate, so nothing of size Lq x Lk is ever stored.
@@ -82,6 +83,40 @@ def _gemm_x3(A, W2, bias, A2, residual, act, transpose_w=False, cache=False):
     return ops.gemm_bf16_tc(As, W3, bias, residual=residual, act=act, x3=True)
 
 
+def _tc_dw_ok(M: int, N: int, K: int) -> bool:
+    return TC_GEMM and M >= TC_MIN_ROWS and N >= 64 and K >= 64 and N % 8 == 0 and K % 8 == 0
+
+
+def _dw_x3(dZ, A, A2):
+    """dW (N,K) = dZ^T (A + A2[m % rows]) on tcgen05: both factors transposed and split by the library
+    (petr_split_transpose_bf16, rows padded to a multiple of 64 with zeros; the transposed image tokens / position
+    embedding are shared by the K / V projections of all six layers through the same cache as their forward split), one
+    bf16x3 GEMM over the row axis cut into split-K parts so that ~148 CTAs run, parts summed by petr_sum_parts_f32."""
+    M, N = dZ.shape
+    K = A.shape[1]
+    Mp = (M + 63) // 64 * 64
+    Yt = ops.split_transpose(dZ, None, Mp, False)                   # (N, 2 Mp)
+    At = None
+    key = ("T", A.data_ptr(), A._version, tuple(A.shape)) + ((A2.data_ptr(), A2._version) if A2 is not None else (0, 0))
+    if M >= SPLIT_CACHE_MIN_ROWS:
+        hit = _SPLIT_CACHE.get(key)
+        if hit is not None:
+            At = hit[2]
+    if At is None:
+        At = ops.split_transpose(A, A2, Mp, True)                   # (K, 3 Mp)
+        if M >= SPLIT_CACHE_MIN_ROWS:
+            _SPLIT_CACHE[key] = (A, A2, At)
+    num_k = 3 * Mp // 64
+    tiles = ((N + 127) // 128) * ((K + 255) // 256)
+    ks = max(1, min(148 // tiles, num_k // 4))
+    parts = ops.gemm_bf16_tc(Yt, At, None, x3=True, ksplit=ks, name="gemm_bf16_tc_dw")
+    if ks == 1:
+        return parts
+    dW = torch.empty((N, K), dtype=torch.float32, device=dZ.device)
+    call("petr_sum_parts_f32", ptr(parts), ks, N * K, ptr(dW), stream_ptr(dZ.device))
+    return dW
+
+
 # ------------------------------------------------------------------------------------------------------------
 # autograd wrappers
 # ------------------------------------------------------------------------------------------------------------
@@ -133,7 +168,9 @@ class _Linear(Function):
             if A2 is not None and need[3]:
                 dA2 = torch.zeros_like(A2)
                 call("petr_rowsum_periodic_f32", ptr(dA_tok), M, K, A2.shape[0], ptr(dA2), stream_ptr(dev))
-        if need[1]:
+        if need[1] and ctx.nchw_hw == 0 and _tc_dw_ok(M, N, K):
+            dW = _dw_x3(dZ, A, A2).view(ctx.wshape)
+        elif need[1]:
             dW = torch.zeros((N, K), dtype=torch.float32, device=dev)
             if ctx.nchw_hw > 0:
                 call("petr_gemm_f32_tn", ptr(dZ), dZ.stride(0), ptr(A), K, ops.A_NCHW, ctx.nchw_hw, None, 0, ptr(dW),
