@@ -92,13 +92,17 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 #define PETR_REQUIRE(cond, code, ...) \
     do { if (!(cond)) return ::petr::fail((code), __VA_ARGS__); } while (0)
 
-// Counter-based dropout decision shared by forward and backward kernels: splitmix64 of (seed, element index).
+// Counter-based dropout decision shared by forward and backward kernels: a 32-bit integer hash (two multiply /
+// xor-shift rounds, the "lowbias32" constants) of the element index and the seed, both folded to 32 bits first, compared
+// as a 24-bit integer against p.  ~12 integer instructions per element: the attention kernels evaluate it for every
+// (query, key) pair, where the 64-bit splitmix it replaces cost a quarter of their issue slots.
 __host__ __device__ inline bool dropout_keep(uint64_t seed, uint64_t idx, float p) {
-    uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    return (float)(z >> 40) * (1.f / 16777216.f) >= p;
+    const uint32_t s32 = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0xC2B2AE35u);         // loop-invariant
+    uint32_t x = (uint32_t)idx * 0x9E3779B1u + (uint32_t)(idx >> 32) * 0x85EBCA77u + s32;
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return (x >> 8) >= (uint32_t)(p * 16777216.f);
 }
 
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
