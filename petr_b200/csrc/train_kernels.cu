@@ -839,7 +839,10 @@ extern "C" int petr_attention_f32_bwd(const float* Q, int ldq, const float* K, i
     AttBwdParams p{Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, key_mask, attn_bias,
                    bias_per_head ? (int64_t)Lq * Lk : 0, dQ, lddq, dK, lddk, dV, lddv, Lq, Lk, heads, scale, drop_p, seed, 1};
     const int qblocks = (Lq + AB_ROWS - 1) / AB_ROWS;
-    int ksplit = (2 * 148) / (qblocks * heads * B);
+    // 165 registers: three CTAs per SM.  Aim at two full waves of the CTAs that have work (a last query block with
+    // fewer than half its rows live -- 900 = 7 x 128 + 4 -- ends at once and is not counted).
+    const int busy = (Lq / AB_ROWS) + ((Lq % AB_ROWS) >= AB_ROWS / 2 ? 1 : 0);
+    int ksplit = (2 * 3 * 148) / ((busy > 0 ? busy : 1) * heads * B);
     const int tiles = (Lk + AB_TILE - 1) / AB_TILE;
     if (ksplit > tiles / 8) ksplit = tiles / 8;
     if (ksplit < 1) ksplit = 1;
