@@ -220,6 +220,22 @@ layernorm_bwd_kernel(const float* __restrict__ X, const float* __restrict__ gamm
 // ------------------------------------------------------------------------------------------
 constexpr int AB_ROWS = 128, AB_TILE = 32;
 
+// Ampere-style asynchronous copies: the next key / query tile streams into the other shared-memory buffer while the
+// FMAs of the current one run (bytes beyond `valid` are zero-filled, nothing is read when valid is false).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, bool valid) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct AttBwdParams {
     const float* Q; int ldq; const float* K; int ldk; const float* V; int ldv; const float* O; int ldo;
     const float* dO; int lddo; const float* lse; const uint8_t* key_mask; const float* attn_bias; int64_t bias_bh_stride;
@@ -229,9 +245,9 @@ struct AttBwdParams {
 
 __global__ void __launch_bounds__(AB_ROWS)
 attention_bwd_dq_kernel(AttBwdParams p) {
-    __shared__ __align__(16) float sK[AB_TILE][32];
-    __shared__ __align__(16) float sV[AB_TILE][32];
-    __shared__ float sBias[AB_TILE];
+    __shared__ __align__(16) float sKb[2][AB_TILE][32];
+    __shared__ __align__(16) float sVb[2][AB_TILE][32];
+    __shared__ float sBiasb[2][AB_TILE];
     const int head = blockIdx.y, b = blockIdx.z / p.ksplit, part = blockIdx.z % p.ksplit;
     const int q = blockIdx.x * AB_ROWS + threadIdx.x;
     const bool live = q < p.Lq;
@@ -262,26 +278,31 @@ attention_bwd_dq_kernel(AttBwdParams p) {
     const float* Vb = p.V + (int64_t)b * p.Lk * p.ldv + head * 32;
     const int tiles = (p.Lk + AB_TILE - 1) / AB_TILE;
     const int t_begin = (int)((int64_t)tiles * part / p.ksplit), t_end = (int)((int64_t)tiles * (part + 1) / p.ksplit);
-    for (int t = t_begin; t < t_end; ++t) {
+    auto issue_tile = [&](int t, int buf) {
         const int k0 = t * AB_TILE;
-        __syncthreads();
         for (int i = threadIdx.x; i < AB_TILE * 8; i += AB_ROWS) {
             const int r = i >> 3, c4 = (i & 7) * 4;
-            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-            if (k0 + r < p.Lk) {
-                kv = *reinterpret_cast<const float4*>(Kb + (int64_t)(k0 + r) * p.ldk + c4);
-                vv = *reinterpret_cast<const float4*>(Vb + (int64_t)(k0 + r) * p.ldv + c4);
-            }
-            *reinterpret_cast<float4*>(&sK[r][c4]) = kv;
-            *reinterpret_cast<float4*>(&sV[r][c4]) = vv;
+            const bool valid = k0 + r < p.Lk;
+            const int64_t row = valid ? k0 + r : 0;
+            cp_async16(&sKb[buf][r][c4], Kb + row * p.ldk + c4, valid);
+            cp_async16(&sVb[buf][r][c4], Vb + row * p.ldv + c4, valid);
         }
         if (threadIdx.x < AB_TILE) {
             const int r = threadIdx.x;
             const bool dead = (k0 + r >= p.Lk) || (p.key_mask && p.key_mask[(int64_t)b * p.Lk + k0 + r]);
-            sBias[r] = dead ? -INFINITY : 0.f;
+            sBiasb[buf][r] = dead ? -INFINITY : 0.f;
         }
-        __syncthreads();
-        if (dead_row) continue;
+        cp_async_commit();
+    };
+    if (t_begin < t_end) issue_tile(t_begin, 0);
+    for (int t = t_begin; t < t_end; ++t) {
+        const int k0 = t * AB_TILE, buf = (t - t_begin) & 1;
+        if (t + 1 < t_end) { issue_tile(t + 1, buf ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();                                   // tile t has landed for every thread
+        const float (*sK)[32] = sKb[buf];
+        const float (*sV)[32] = sVb[buf];
+        const float* sBias = sBiasb[buf];
+        if (!dead_row) {
 #pragma unroll 2
         for (int r = 0; r < AB_TILE; ++r) {
             uint64_t s0 = 0ull, s1 = 0ull, s2 = 0ull, s3 = 0ull, d0 = 0ull, d1 = 0ull, d2 = 0ull, d3 = 0ull;   // short chains
@@ -310,6 +331,8 @@ attention_bwd_dq_kernel(AttBwdParams p) {
                 dq2[i + 1] = fma2(ds2, kk.y, dq2[i + 1]);
             }
         }
+        }
+        __syncthreads();                                   // buffer free before tile t + 2 is issued into it
     }
     float dq[32];
 #pragma unroll
@@ -328,22 +351,24 @@ attention_bwd_dq_kernel(AttBwdParams p) {
 
 __global__ void __launch_bounds__(AB_ROWS)
 attention_bwd_dkv_kernel(AttBwdParams p) {
-    __shared__ __align__(16) float sQ[AB_TILE][32];
-    __shared__ __align__(16) float sdO[AB_TILE][32];
+    __shared__ __align__(16) float sQb[2][AB_TILE][32];
+    __shared__ __align__(16) float sdOb[2][AB_TILE][32];
+    __shared__ __align__(16) float sOb[2][AB_TILE][32];
+    __shared__ float sLseRaw[2][AB_TILE];
     __shared__ float sLse[AB_TILE], sD[AB_TILE];
     const int head = blockIdx.y, b = blockIdx.z;
     const int k = blockIdx.x * AB_ROWS + threadIdx.x;
     const int bh = b * p.heads + head;
     const bool live = k < p.Lk && !(p.key_mask && p.key_mask[(int64_t)b * p.Lk + k]);
     const float scale_log2 = p.scale * LOG2E;
-    uint64_t k2[16], v2[16], dk2[16], dv2[16];    // packed fp32 pairs
+    uint64_t k2[16], v2[16], dk2[16], dv2[16];    // packed fp32 pairs; k2 carries scale * log2(e)
     {
         const int64_t row = (int64_t)b * p.Lk + (k < p.Lk ? k : 0);
         const float* kp = p.K + row * p.ldk + head * 32;
         const float* vp = p.V + row * p.ldv + head * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-            k2[i >> 1] = pack2(kp[i], kp[i + 1]);
+            k2[i >> 1] = pack2(kp[i] * scale_log2, kp[i + 1] * scale_log2);
             v2[i >> 1] = pack2(vp[i], vp[i + 1]);
             dk2[i >> 1] = 0ull;
             dv2[i >> 1] = 0ull;
@@ -353,34 +378,46 @@ attention_bwd_dkv_kernel(AttBwdParams p) {
     const float* Qb = p.Q + (int64_t)b * p.Lq * p.ldq + head * 32;
     const float* dOb = p.dO + (int64_t)b * p.Lq * p.lddo + head * 32;
     const float* Ob = p.O + (int64_t)b * p.Lq * p.ldo + head * 32;
-    for (int q0 = 0; q0 < p.Lq; q0 += AB_TILE) {
-        __syncthreads();
+    const float* lse_b = p.lse + (int64_t)bh * p.Lq;
+    auto issue_tile = [&](int q0, int buf) {
         for (int i = threadIdx.x; i < AB_TILE * 8; i += AB_ROWS) {
             const int r = i >> 3, c4 = (i & 7) * 4;
-            float4 qq = make_float4(0.f, 0.f, 0.f, 0.f), dd = qq;
-            if (q0 + r < p.Lq) {
-                qq = *reinterpret_cast<const float4*>(Qb + (int64_t)(q0 + r) * p.ldq + c4);
-                dd = *reinterpret_cast<const float4*>(dOb + (int64_t)(q0 + r) * p.lddo + c4);
-            }
-            qq.x *= scale_log2; qq.y *= scale_log2; qq.z *= scale_log2; qq.w *= scale_log2;
-            *reinterpret_cast<float4*>(&sQ[r][c4]) = qq;
-            *reinterpret_cast<float4*>(&sdO[r][c4]) = dd;
+            const bool valid = q0 + r < p.Lq;
+            const int64_t row = valid ? q0 + r : 0;
+            cp_async16(&sQb[buf][r][c4], Qb + row * p.ldq + c4, valid);
+            cp_async16(&sdOb[buf][r][c4], dOb + row * p.lddo + c4, valid);
+            cp_async16(&sOb[buf][r][c4], Ob + row * p.ldo + c4, valid);
         }
         if (threadIdx.x < AB_TILE) {
-            const int r = threadIdx.x;
-            float l = INFINITY, D = 0.f;                      // rows beyond Lq: exp2(s - inf) = 0
-            if (q0 + r < p.Lq) {
-                l = p.lse[(int64_t)bh * p.Lq + q0 + r];
-                const float* dop = dOb + (int64_t)(q0 + r) * p.lddo;
-                const float* op = Ob + (int64_t)(q0 + r) * p.ldo;
-                for (int i = 0; i < 32; ++i) D = fmaf(dop[i], op[i], D);
-                if (!isfinite(l) || !isfinite(D)) { l = INFINITY; D = 0.f; }      // fully masked query row: no gradient
+            const bool valid = q0 + (int)threadIdx.x < p.Lq;
+            cp_async4(&sLseRaw[buf][threadIdx.x], lse_b + (valid ? q0 + (int)threadIdx.x : 0), valid);
+        }
+        cp_async_commit();
+    };
+    issue_tile(0, 0);
+    for (int q0 = 0, it = 0; q0 < p.Lq; q0 += AB_TILE, ++it) {
+        const int buf = it & 1;
+        if (q0 + AB_TILE < p.Lq) { issue_tile(q0 + AB_TILE, buf ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();                                   // tile has landed for every thread
+        {
+            // D = <dO, O> per query row: four lanes per row, eight columns each
+            const int r = threadIdx.x >> 2, part = (threadIdx.x & 3) * 8;
+            float D = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) D = fmaf(sdOb[buf][r][part + i], sOb[buf][r][part + i], D);
+            D += __shfl_xor_sync(0xffffffffu, D, 1);
+            D += __shfl_xor_sync(0xffffffffu, D, 2);
+            if ((threadIdx.x & 3) == 0) {
+                float l = sLseRaw[buf][r];
+                if (q0 + r >= p.Lq || !isfinite(l) || !isfinite(D)) { l = INFINITY; D = 0.f; }   // exp2(s - inf) = 0: beyond Lq,
+                sLse[r] = l;                                                                     // or a fully masked row
+                sD[r] = D;
             }
-            sLse[r] = l;
-            sD[r] = D;
         }
         __syncthreads();
-        if (!live) continue;
+        const float (*sQ)[32] = sQb[buf];
+        const float (*sdO)[32] = sdOb[buf];
+        if (live) {
 #pragma unroll 2
         for (int r = 0; r < AB_TILE; ++r) {
             uint64_t s0 = 0ull, s1 = 0ull, s2 = 0ull, s3 = 0ull, d0 = 0ull, d1 = 0ull, d2 = 0ull, d3 = 0ull;   // short chains
@@ -414,6 +451,8 @@ attention_bwd_dkv_kernel(AttBwdParams p) {
                 dk2[i] = fma2(ds2, qq.x, dk2[i]); dk2[i + 1] = fma2(ds2, qq.y, dk2[i + 1]);
             }
         }
+        }
+        __syncthreads();                                   // buffers and sLse / sD free for the next tile
     }
     float dk[32], dv[32];
 #pragma unroll
@@ -424,9 +463,9 @@ attention_bwd_dkv_kernel(AttBwdParams p) {
     if (k < p.Lk) {
         float* ok = p.dK + ((int64_t)b * p.Lk + k) * p.lddk + head * 32;
         float* ov = p.dV + ((int64_t)b * p.Lk + k) * p.lddv + head * 32;
-        // sQ holds q * scale * log2(e): dK = scale * sum ds q = ln2 * sum ds sQ
+        // dK = scale * sum ds q (the tiles hold the raw q; scale * log2(e) rides on k2 for the scores)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { ok[i] = live ? dk[i] * LN2 : 0.f; ov[i] = live ? dv[i] : 0.f; }
+        for (int i = 0; i < 32; ++i) { ok[i] = live ? dk[i] * p.scale : 0.f; ov[i] = live ? dv[i] : 0.f; }
     }
 }
 
@@ -834,7 +873,8 @@ extern "C" int petr_attention_f32_bwd(const float* Q, int ldq, const float* K, i
     PETR_REQUIRE(Q && K && V && O && dO && lse && dQ && dK && dV, PETR_E_BADARG, "petr_attention_f32_bwd: null pointer");
     PETR_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && heads > 0, PETR_E_BADARG, "petr_attention_f32_bwd: bad dimension");
     PETR_REQUIRE(head_dim == 32, PETR_E_SHAPE, "petr_attention_f32_bwd: head_dim must be 32");
-    PETR_REQUIRE(((ldq | ldk | ldv | lddo) & 3) == 0 && aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(dO),
+    PETR_REQUIRE(((ldq | ldk | ldv | lddo | ldo) & 3) == 0 && aligned16(Q) && aligned16(K) && aligned16(V) &&
+                     aligned16(dO) && aligned16(O),
                  PETR_E_ALIGN, "petr_attention_f32_bwd: rows must be 16-byte aligned");
     AttBwdParams p{Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, key_mask, attn_bias,
                    bias_per_head ? (int64_t)Lq * Lk : 0, dQ, lddq, dK, lddk, dV, lddv, Lq, Lk, heads, scale, drop_p, seed, 1};
