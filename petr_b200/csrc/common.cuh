@@ -105,6 +105,22 @@ __host__ __device__ inline bool dropout_keep(uint64_t seed, uint64_t idx, float 
     return (x >> 8) >= (uint32_t)(p * 16777216.f);
 }
 
+// Ampere-style asynchronous copies: the next key / query tile streams into the other shared-memory buffer while the
+// FMAs of the current one run (bytes beyond `valid` are zero-filled, nothing is read when valid is false).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, bool valid) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __host__ __device__ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace petr

@@ -386,9 +386,9 @@ attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restri
                      int Lq, int Lk, float scale_log2, const float* __restrict__ attn_bias,
                      int64_t bias_bh_stride, float* __restrict__ lse, float drop_p, uint64_t seed,
                      float* __restrict__ partial, int ksplit) {
-    __shared__ __align__(16) float sK[ATT_KT][32];
-    __shared__ __align__(16) float sV[ATT_KT][32];
-    __shared__ float sBias[ATT_KT];
+    __shared__ __align__(16) float sKb[2][ATT_KT][32];
+    __shared__ __align__(16) float sVb[2][ATT_KT][32];
+    __shared__ float sBiasb[2][ATT_KT];
     // ksplit > 1: the key axis is split over `ksplit` blocks per (row block, head, sample) -- 900 query rows x 8 heads
     // are 113 warps per sample, too few for 148 SMs -- and every part writes its un-normalised (o, m, l) to `partial`
     // in the layout petr_attention_merge reads
@@ -418,24 +418,30 @@ attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restri
     const int tiles = (Lk + ATT_KT - 1) / ATT_KT;
     const int k_begin = (int)((int64_t)tiles * part / ksplit) * ATT_KT;
     const int k_end = min(Lk, (int)((int64_t)tiles * (part + 1) / ksplit) * ATT_KT);
-    for (int k0 = k_begin; k0 < k_end; k0 += ATT_KT) {
-        __syncthreads();
+    // the next key tile streams into the other buffer (cp.async) while this one is processed
+    auto issue_tile = [&](int k0, int buf) {
         for (int i = threadIdx.x; i < ATT_KT * 8; i += ATT_ROWS) {
             const int r = i >> 3, c4 = (i & 7) * 4;
-            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-            if (k0 + r < k_end) {
-                kv = *reinterpret_cast<const float4*>(Kb + (int64_t)(k0 + r) * ldk + c4);
-                vv = *reinterpret_cast<const float4*>(Vb + (int64_t)(k0 + r) * ldv + c4);
-            }
-            *reinterpret_cast<float4*>(&sK[r][c4]) = kv;
-            *reinterpret_cast<float4*>(&sV[r][c4]) = vv;
+            const bool valid = k0 + r < k_end;
+            const int64_t row = valid ? k0 + r : 0;
+            cp_async16(&sKb[buf][r][c4], Kb + row * ldk + c4, valid);
+            cp_async16(&sVb[buf][r][c4], Vb + row * ldv + c4, valid);
         }
         if (threadIdx.x < ATT_KT) {
             const int r = threadIdx.x;
             const bool dead = (k0 + r >= k_end) || (key_mask && key_mask[(int64_t)b * Lk + k0 + r]);
-            sBias[r] = dead ? -INFINITY : 0.f;
+            sBiasb[buf][r] = dead ? -INFINITY : 0.f;
         }
-        __syncthreads();
+        cp_async_commit();
+    };
+    if (k_begin < k_end) issue_tile(k_begin, 0);
+    for (int k0 = k_begin, it = 0; k0 < k_end; k0 += ATT_KT, ++it) {
+        const int buf = it & 1;
+        if (k0 + ATT_KT < k_end) { issue_tile(k0 + ATT_KT, buf ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();                               // tile has landed for every thread
+        const float (*sK)[32] = sKb[buf];
+        const float (*sV)[32] = sVb[buf];
+        const float* sBias = sBiasb[buf];
 #pragma unroll 1
         for (int g = 0; g < ATT_KT / 8; ++g) {
             float sc[8];
@@ -481,6 +487,7 @@ attention_f32_kernel(const float* __restrict__ Q, int ldq, const float* __restri
                 }
             }
         }
+        __syncthreads();                               // buffer free before the tile after next is issued into it
     }
     if (!live) return;
     if (ksplit > 1) {

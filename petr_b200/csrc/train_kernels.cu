@@ -220,21 +220,6 @@ layernorm_bwd_kernel(const float* __restrict__ X, const float* __restrict__ gamm
 // ------------------------------------------------------------------------------------------
 constexpr int AB_ROWS = 128, AB_TILE = 32;
 
-// Ampere-style asynchronous copies: the next key / query tile streams into the other shared-memory buffer while the
-// FMAs of the current one run (bytes beyond `valid` are zero-filled, nothing is read when valid is false).
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
-    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, bool valid) {
-    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
-    const int sz = valid ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct AttBwdParams {
     const float* Q; int ldq; const float* K; int ldk; const float* V; int ldv; const float* O; int ldo;

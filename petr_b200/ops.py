@@ -146,9 +146,10 @@ def attention_f32(Q, K, V, key_mask, B: int, Lq: int, Lk: int, heads: int, out=N
         assert attn_bias.dtype == torch.float32 and attn_bias.is_contiguous()
         assert tuple(attn_bias.shape) in ((Lq, Lk), (B * heads, Lq, Lk)), attn_bias.shape
         per_head = int(attn_bias.dim() == 3)
-    # one thread per query row: split the key axis until the grid has ~4 blocks per SM (each part >= 8 key tiles)
-    blocks = ((Lq + 63) // 64) * heads * B
-    ksplit = max(1, min((4 * 148 + blocks - 1) // blocks, ((Lk + 31) // 32) // 8, 65535 // max(B, 1)))
+    # one thread per query row, 64 rows per CTA, 144 registers: seven CTAs per SM.  Split the key axis until the CTAs
+    # that have work (a last row block less than half full ends at once) make two full waves; each part >= 8 key tiles
+    busy = max(1, (Lq // 64 + (1 if Lq % 64 >= 32 else 0)) * heads * B)
+    ksplit = max(1, min((2 * 7 * 148) // busy, ((Lk + 31) // 32) // 8, 65535 // max(B, 1)))
     partial = None
     if ksplit > 1:
         partial = torch.empty((ksplit * attention_partial_floats(B, Lq, heads),), dtype=torch.float32, device=Q.device)
