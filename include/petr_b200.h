@@ -359,7 +359,8 @@ int petr_norm_scale_f32(const float* x, float* out, int B, int Q, int E, int alo
                         float eps, float mult, void* stream);
 
 /* ---- Training path: backward of the fp32 forward kernels above, the loss of
- * petr_head.py:578-728 and the matching cost of hungarian_assigner_3d.py:117-123.  Exact fp32 arithmetic. ---- */
+ * petr_head.py:578-728 and the matching cost of hungarian_assigner_3d.py:117-123.  Exact fp32 arithmetic, except that the host side
+ * routes the large Linear layers through petr_gemm_bf16_tc in bf16x3 mode (16 mantissa bits per operand). ---- */
 
 /* dW[N,K] += dY[M,N]^T (A[M,K] + A2[m % a2_rows]) -- weight gradient of petr_gemm_f32 (A layouts as there).  dW must
  * hold zeros or a running gradient (partial sums over row chunks are added atomically). */
