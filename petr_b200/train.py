@@ -58,8 +58,7 @@ def _tc_ok(M: int, N: int, K: int) -> bool:
     return TC_GEMM and M >= TC_MIN_ROWS and K % 64 == 0 and N % 8 == 0 and N >= 64
 
 
-_SPLIT_CACHE: dict = {}          # forward only, big activations: (ptr, version, A2 ptr) -> (A, A2, split); see _gemm_x3
-SPLIT_CACHE_MIN_ROWS = 4096
+_SPLIT_CACHE: dict = {}          # shared operands only (linear(share_split=True)): key -> (A, A2, split); see _gemm_x3
 
 
 def _gemm_x3(A, W2, bias, A2, residual, act, transpose_w=False, cache=False):
@@ -71,13 +70,13 @@ def _gemm_x3(A, W2, bias, A2, residual, act, transpose_w=False, cache=False):
     A = _c(A)
     As = None
     key = ((A.data_ptr(), A._version, tuple(A.shape)) + ((A2.data_ptr(), A2._version) if A2 is not None else (0, 0))) if cache else None
-    if key is not None and A.shape[0] >= SPLIT_CACHE_MIN_ROWS:
+    if key is not None:
         hit = _SPLIT_CACHE.get(key)
         if hit is not None:
             As = hit[2]
     if As is None:
         As = ops.split_rows(A, add=A2)
-        if key is not None and A.shape[0] >= SPLIT_CACHE_MIN_ROWS:
+        if key is not None:
             _SPLIT_CACHE[key] = (A, A2, As)
     W3 = ops.x3_weight_kernel(W2, transpose_w)
     return ops.gemm_bf16_tc(As, W3, bias, residual=residual, act=act, x3=True)
@@ -87,7 +86,7 @@ def _tc_dw_ok(M: int, N: int, K: int) -> bool:
     return TC_GEMM and M >= TC_MIN_ROWS and N >= 64 and K >= 64 and N % 8 == 0 and K % 8 == 0
 
 
-def _dw_x3(dZ, A, A2):
+def _dw_x3(dZ, A, A2, share=False):
     """dW (N,K) = dZ^T (A + A2[m % rows]) on tcgen05: both factors transposed and split by the library
     (petr_split_transpose_bf16, rows padded to a multiple of 64 with zeros; the transposed image tokens / position
     embedding are shared by the K / V projections of all six layers through the same cache as their forward split), one
@@ -98,13 +97,13 @@ def _dw_x3(dZ, A, A2):
     Yt = ops.split_transpose(dZ, None, Mp, False)                   # (N, 2 Mp)
     At = None
     key = ("T", A.data_ptr(), A._version, tuple(A.shape)) + ((A2.data_ptr(), A2._version) if A2 is not None else (0, 0))
-    if M >= SPLIT_CACHE_MIN_ROWS:
+    if share:
         hit = _SPLIT_CACHE.get(key)
         if hit is not None:
             At = hit[2]
     if At is None:
         At = ops.split_transpose(A, A2, Mp, True)                   # (K, 3 Mp)
-        if M >= SPLIT_CACHE_MIN_ROWS:
+        if share:
             _SPLIT_CACHE[key] = (A, A2, At)
     num_k = 3 * Mp // 64
     tiles = ((N + 127) // 128) * ((K + 255) // 256)
@@ -124,19 +123,19 @@ class _Linear(Function):
     """y = act((A + A2[m % rows]) W^T + b) (+ residual); A row-major (M,K) or an NCHW map read as tokens."""
 
     @staticmethod
-    def forward(ctx, A, W, bias, A2, residual, act, nchw_hw):
+    def forward(ctx, A, W, bias, A2, residual, act, nchw_hw, share_split=False):
         W2 = W.detach().reshape(W.shape[0], -1)
         assert not (act != ACT_NONE and residual is not None)
         A = _c(A.detach())
         if _tc_ok(A.shape[0], W2.shape[0], W2.shape[1]) and nchw_hw == 0:
             out = _gemm_x3(A, _c(W2), bias.detach() if bias is not None else None,
                            A2.detach() if A2 is not None else None,
-                           _c(residual.detach()) if residual is not None else None, act, cache=True)
+                           _c(residual.detach()) if residual is not None else None, act, cache=share_split)
         else:
             out = ops.gemm_f32(A, _c(W2), bias.detach() if bias is not None else None,
                                A2=A2.detach() if A2 is not None else None,
                                residual=residual.detach() if residual is not None else None, act=act, nchw_hw=nchw_hw)
-        ctx.act, ctx.nchw_hw, ctx.wshape = act, nchw_hw, W.shape
+        ctx.act, ctx.nchw_hw, ctx.wshape, ctx.share_split = act, nchw_hw, W.shape, share_split
         ctx.save_for_backward(A, W2, A2.detach() if A2 is not None else None, out if act == ACT_RELU else None)
         ctx.has_bias = bias is not None
         return out
@@ -169,7 +168,7 @@ class _Linear(Function):
                 dA2 = torch.zeros_like(A2)
                 call("petr_rowsum_periodic_f32", ptr(dA_tok), M, K, A2.shape[0], ptr(dA2), stream_ptr(dev))
         if need[1] and ctx.nchw_hw == 0 and _tc_dw_ok(M, N, K):
-            dW = _dw_x3(dZ, A, A2).view(ctx.wshape)
+            dW = _dw_x3(dZ, A, A2, ctx.share_split).view(ctx.wshape)
         elif need[1]:
             dW = torch.zeros((N, K), dtype=torch.float32, device=dev)
             if ctx.nchw_hw > 0:
@@ -184,11 +183,13 @@ class _Linear(Function):
             call("petr_colsum_f32", ptr(dZ), dZ.stride(0), M, N, ptr(db), stream_ptr(dev))
         if need[4]:
             dres = dOut
-        return dA, dW, db, dA2, dres, None, None
+        return dA, dW, db, dA2, dres, None, None, None
 
 
-def linear(A, W, bias=None, A2=None, residual=None, act=ACT_NONE, nchw_hw=0):
-    return _Linear.apply(A, W, bias, A2, residual, act, nchw_hw)
+def linear(A, W, bias=None, A2=None, residual=None, act=ACT_NONE, nchw_hw=0, share_split=False):
+    """share_split: A (+ A2) feeds several Linear layers of one step (the image tokens and their position embedding
+    under the K / V projections of all decoder layers): keep its bf16 split / transposed split until the next forward."""
+    return _Linear.apply(A, W, bias, A2, residual, act, nchw_hw, share_split)
 
 
 class _LinearGate(Function):
@@ -460,8 +461,9 @@ class TrainEngine:
         E = att.embed_dims
         w, b = att.attn.in_proj_weight, att.attn.in_proj_bias
         q = linear(X, w[:E], b[:E], A2=qpos)
-        k = linear(Kin, w[E:2 * E], b[E:2 * E], A2=Kpos)
-        v = linear(Vin, w[2 * E:], b[2 * E:])
+        shared = Kin is not X                           # cross-attention: the same tokens under every layer's K / V
+        k = linear(Kin, w[E:2 * E], b[E:2 * E], A2=Kpos, share_split=shared)
+        v = linear(Vin, w[2 * E:], b[2 * E:], share_split=shared)
         p_attn = float(att.attn.dropout) if training else 0.0
         o = _Attention.apply(q, k, v, kmask, B, Lq, Lk, att.num_heads, p_attn, _next_seed() if p_attn > 0 else 0)
         p_proj = float(att.proj_drop.p) if training else 0.0
